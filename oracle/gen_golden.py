@@ -1,0 +1,244 @@
+"""Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE under oracle/ref_shim.py.
+
+TEST INFRASTRUCTURE ONLY.  Run here (the container that mounts /root/reference):
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+
+The vectors are committed; the GPU box has no /root/reference and only reads the .npz files.
+Each file records inputs, every intermediate the reference exposes, and the outputs of one
+reference function on the hot path.  No reference source is copied: the
+functions are imported from where they lie and called.
+
+Gradient injection: reference PGD obtains its gradient from `torch.autograd.grad(loss(model(x_adv)))`
+(Classification/attack_algo.py:50-52).  To pin the UPDATE arithmetic independently of any network
+we hand PGD a "model" whose output is a scalar with a prescribed gradient (including 0, -0, NaN,
++-inf, denormals) and `loss_fn = lambda out, y: out`.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
+SPECIALS = np.array([0.0, -0.0, np.nan, np.inf, -np.inf, 1e-45, -1e-45, 1.17549435e-38, 3.4e38, -3.4e38,
+                     1.0, -1.0], dtype=np.float32)
+
+
+class _InjectGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g):
+        ctx.save_for_backward(g)
+        return x.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, go):
+        (g,) = ctx.saved_tensors
+        return g.clone(), None
+
+
+class InjectingModel:
+    """Callable in all three reference model conventions; records x_adv at each call."""
+
+    def __init__(self, grads):
+        self.grads, self.calls, self.states = grads, 0, []
+
+    def _next(self, x_adv):
+        self.states.append(x_adv.detach().clone())
+        g = self.grads[self.calls]
+        self.calls += 1
+        return _InjectGrad.apply(x_adv, g)
+
+    def __call__(self, x, end_point=None, start_point=None):       # Classification + Segmentation
+        if isinstance(x, dict):
+            return self._next(x["adv"])
+        return self._next(x)
+
+    def train(self):                                                # Detection: model.train().forward(...)
+        return self
+
+    def forward(self, inputs, bb, lb):
+        out = self._next(inputs["adv"])
+        z = out * 0
+        return out, z, z, z
+
+
+def feature_like(shape, gen):
+    """Post-ReLU-like activations (about half exact zeros), SURVEY 8d."""
+    return torch.relu(1.5 * torch.randn(shape, generator=gen))
+
+
+def grads_like(shape, steps, gen, specials=True):
+    out = []
+    for _ in range(steps):
+        g = 1e-3 * torch.randn(shape, generator=gen)
+        g[torch.rand(shape, generator=gen) < 0.05] = 0.0
+        if specials:
+            flat = g.view(-1)
+            flat[: len(SPECIALS)] = torch.from_numpy(SPECIALS)
+        out.append(g)
+    return out
+
+
+def gen_pgd_cases():
+    cls = ref_shim.load("Classification", "attack_algo")
+    seg = ref_shim.load("Segmentation", "attack_algo")
+    det = ref_shim.load("Detection", "attack_algo")
+    gen = torch.Generator().manual_seed(3)
+    cases = {}
+    shape = (4, 8, 6, 7)
+    idx = 0
+    for flavour in ("cls", "seg", "det"):
+        for randinit in (False, True):
+            for clip in (False, True):
+                for gamma255, steps in ((0.5, 5), (1.5, 3)):
+                    if flavour != "cls" and gamma255 == 1.5:
+                        continue
+                    x = feature_like(shape, gen)
+                    xf = x.view(-1)
+                    xf[-len(SPECIALS):] = torch.from_numpy(SPECIALS)        # special clean values too
+                    grads = grads_like(shape, steps, gen)
+                    gamma, eps = gamma255 / 255, 2 / 255
+                    torch.manual_seed(3)
+                    u = torch.rand(shape)                                   # the draw PGD will make
+                    torch.manual_seed(3)
+                    model = InjectingModel(grads)
+                    with ref_shim.cpu_cuda_identity():
+                        if flavour == "cls":
+                            out = cls.PGD(x, lambda o, y: o, y=None, model=model, steps=steps, gamma=gamma,
+                                          start_idx=1, layer_number=16, eps=eps, randinit=randinit, clip=clip)
+                        elif flavour == "seg":
+                            out = seg.PGD(x, None, None, lambda o, y: o, y=None, model=model, steps=steps,
+                                          eps=eps, gamma=gamma, idx=3, randinit=randinit, clip=clip)
+                        else:
+                            out = det.PGD(x, None, y={"bb": None, "lb": None}, model=model, steps=steps,
+                                          eps=eps, gamma=gamma, idx=3, randinit=randinit, clip=clip)
+                    assert out.requires_grad and out.is_leaf
+                    key = f"case{idx}"
+                    idx += 1
+                    cases[key + "_meta"] = np.array([gamma, eps, steps, int(randinit), int(clip),
+                                                     {"cls": 0, "seg": 1, "det": 2}[flavour]], dtype=np.float64)
+                    cases[key + "_x"] = x.numpy().copy()
+                    cases[key + "_u"] = u.numpy().copy()
+                    cases[key + "_grads"] = torch.stack(grads).numpy().copy()
+                    cases[key + "_states"] = torch.stack(model.states).numpy().copy()   # x_adv BEFORE step t
+                    cases[key + "_out"] = out.detach().numpy().copy()
+    cases["n_cases"] = np.array(idx)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "pgd_linf.npz"), **cases)
+    print("pgd_linf.npz:", idx, "cases")
+
+
+def gen_helper_cases():
+    cls = ref_shim.load("Classification", "attack_algo")
+    seg = ref_shim.load("Segmentation", "attack_algo")
+    det = ref_shim.load("Detection", "attack_algo")
+    gen = torch.Generator().manual_seed(5)
+    out = {}
+    # tensor_clamp / linfball_proj (Classification/attack_algo.py:9-19,35-36) incl. specials
+    c = feature_like((3, 5, 4, 4), gen)
+    t = c + 0.02 * torch.randn(c.shape, generator=gen)
+    t.view(-1)[: len(SPECIALS)] = torch.from_numpy(SPECIALS)
+    c.view(-1)[len(SPECIALS): 2 * len(SPECIALS)] = torch.from_numpy(SPECIALS)
+    out["linf_center"], out["linf_t"] = c.numpy().copy(), t.numpy().copy()
+    out["linf_radius"] = np.float32(2 / 255)
+    out["linf_out"] = cls.linfball_proj(c, 2 / 255, t.clone(), in_place=True).numpy().copy()
+    # l2ball_proj (attack_algo.py:21-33): inside ball, outside ball, t == center (0/0 -> NaN)
+    c = feature_like((4, 3, 5, 5), gen)
+    t = c.clone()
+    t[0] += 1e-4 * torch.randn(t[0].shape, generator=gen)
+    t[1] += 0.5 * torch.randn(t[1].shape, generator=gen)
+    t[3] += 0.01 * torch.randn(t[3].shape, generator=gen)
+    out["l2_center"], out["l2_t"] = c.numpy().copy(), t.numpy().copy()
+    out["l2_radius"] = np.float32(0.05)
+    out["l2_out"] = cls.l2ball_proj(c, 0.05, t.clone(), in_place=True).numpy().copy()
+    # mix_feature (Seg :121-130, Det :254-265) and get_sample_points (Seg :108-118, Det :236-245)
+    for i, shape in enumerate(((2, 16, 5, 7), (1, 256, 3, 3), (3, 2, 4, 4), (2, 40, 1, 9))):
+        cl = feature_like(shape, gen)
+        ad = cl + (2 / 255) * torch.sign(torch.randn(shape, generator=gen))
+        if i == 0:
+            cl[0, :, 0, 0] = 0.25          # constant channel column: var == 0
+            ad[0, :, 0, 1] = 0.5
+        out[f"mix{i}_clean"], out[f"mix{i}_adv"] = cl.numpy().copy(), ad.numpy().copy()
+        out[f"mix{i}_seg"] = seg.mix_feature(cl, ad).numpy().copy()
+        out[f"mix{i}_det"] = det.mix_feature(cl, ad).numpy().copy()
+        for n in (3, 5):
+            pts = seg.get_sample_points(cl, ad, n)
+            pts_d = det.get_sample_points(cl, ad, n)
+            assert all(torch.equal(a, b) for a, b in zip(pts, pts_d))
+            out[f"mix{i}_pts{n}"] = torch.stack(pts).numpy().copy()
+    out["n_mix"] = np.array(4)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "helpers.npz"), **out)
+    print("helpers.npz written")
+
+
+class _RecordingCE(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.ce, self.values = nn.CrossEntropyLoss(), []
+
+    def forward(self, out, y):
+        v = self.ce(out, y)
+        self.values.append(float(v.detach()))
+        return v
+
+
+def gen_train_cases():
+    """Execute the unmodified reference training loop (Classification/main_perturb.py:153-225)."""
+    rs = ref_shim.load("Classification", "resnet_s")
+    mp = ref_shim.load("Classification", "main_perturb")
+    recipes = {
+        # name: (num_blocks, n_cls, perturb_idx, steps, gamma, eps, randinit, clip, batch, iters, epoch)
+        "cls_train_randclip": ([1, 1, 1], 10, 6, 3, 1.0, 2.0, True, True, 4, 3, 1),
+        "cls_train_shipped": ([1, 1, 1], 10, 5, 5, 0.5, 2.0, False, False, 4, 3, 1),   # cmd/run_perturb.sh:1
+        "cls_train_warmup": ([2, 1, 1], 100, 5, 2, 1.5, 2.0, False, True, 4, 3, 0),     # epoch 0: warmup_lr
+    }
+    for name, (nb, ncls, pidx, steps, gamma, eps, randinit, clip, bs, iters, epoch) in recipes.items():
+        torch.manual_seed(3)
+        model = rs.ResNet(rs.BasicBlock, nb, num_classes=ncls)
+        init_state = {k: v.clone() for k, v in model.state_dict().items()}
+        gen = torch.Generator().manual_seed(11)
+        images = [torch.rand(bs, 3, 32, 32, generator=gen) for _ in range(iters)]
+        targets = [torch.randint(0, ncls, (bs,), generator=gen) for _ in range(iters)]
+        with torch.no_grad():
+            fshape = model(images[0], end_point=pidx, start_point=0).shape
+        model.load_state_dict(init_state)          # undo the BN running-stat update of the probe
+        torch.manual_seed(3)
+        noises = [torch.rand(fshape) for _ in range(iters)] if randinit else []
+        torch.manual_seed(3)
+        mp.args = argparse.Namespace(perturb_idx=pidx, steps=steps, gamma=gamma, eps=eps, randinit=randinit,
+                                     clip=clip, print_freq=10 ** 9, lr=0.1)
+        mp.layer_number = len(model.sequential_model)
+        crit = _RecordingCE()
+        opt = torch.optim.SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=5e-4)
+        with ref_shim.cpu_cuda_identity():
+            top1, loss_avg, l2m, linfm = mp.train(list(zip(images, targets)), model, crit, opt, epoch)
+        per_iter = np.array(crit.values, dtype=np.float64).reshape(iters, steps + 2)
+        out = {"num_blocks": np.array(nb), "num_classes": np.array(ncls),
+               "meta": np.array([pidx, steps, gamma, eps, int(randinit), int(clip), bs, iters, epoch],
+                                dtype=np.float64),
+               "images": torch.stack(images).numpy(), "targets": torch.stack(targets).numpy(),
+               "ce_values": per_iter,      # per iteration: CE at each PGD step, CE(adv), CE(clean)
+               "top1_avg": np.float64(top1), "loss_avg": np.float64(loss_avg),
+               "l2_mean": np.float64(l2m), "linf_mean": np.float64(linfm)}
+        if randinit:
+            out["noises"] = torch.stack(noises).numpy()
+        for k, v in init_state.items():
+            out["init/" + k] = v.numpy()
+        for k, v in model.state_dict().items():
+            out["final/" + k] = v.detach().numpy()
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+        print(name, "ce:", per_iter[-1], "l2/linf mean:", float(l2m), float(linfm))
+
+
+if __name__ == "__main__":
+    assert ref_shim.available(), "reference not mounted; goldens can only be generated where it is"
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    gen_pgd_cases()
+    gen_helper_cases()
+    gen_train_cases()
