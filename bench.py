@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- A-FAN training throughput (img/s) + hand-written-kernel rooflines on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's sm_100a path
+    python bench.py --impl reference [--gpus N] [--steps K] ...      # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...                # one rank per GPU, NCCL, weak scaling
+
+Workload (BASELINE.json configs[1]): ResNet-56 (resnet_s [9,9,9]) on CIFAR-100-shaped synthetic data,
+A-FAN with PGD-5 on the layer-13 feature map (128x16x32x32 per GPU), random start + L-inf projection,
+dual-BN tail, batch 128 PER GPU (1024 over 8 GPUs), fp32.  One "step" = one full training iteration
+(Classification/main_perturb.py:173-201): head fwd, 5 x (tail fwd + dgrad + fused PGD step), [adv; clean]
+dual-BN tail fwd, backward, gradient all-reduce, fused SGD.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = the same step through the
+public API with pinned HOST inputs (H2D of images/labels and D2H of the loss inside the timed region).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(net="resnet_s [9,9,9] (ResNet-56)", num_blocks=(9, 9, 9), num_classes=100, batch_per_gpu=128,
+                image=(3, 32, 32), perturb_idx=13, steps=5, gamma=0.5, eps=2.0, randinit=True, clip=True)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = sorted(float(r[0]) for r in rows)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for i, n in enumerate(names) if any("Active" in r[2 + i] and "Not" not in r[2 + i] for r in rows)]
+            out["samples"] = len(rows)
+        except Exception as e:       # no nvidia-smi (CPU box) -> nulls
+            out["error"] = str(e)[:80]
+        finally:
+            if self.path and os.path.exists(self.path):
+                os.unlink(self.path)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU port of the reference iteration (oracle/afan_ref_torch.py)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, batch=None):
+    from oracle import afan_ref_torch as ref_t
+    w = WORKLOAD
+    batch = batch or w["batch_per_gpu"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(3)
+    model = ref_t.CifarResNetRef(w["num_blocks"], w["num_classes"])
+    model.train()
+    opt, crit = ref_t.make_sgd(model), torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(batch, *w["image"], generator=g)
+    y = torch.randint(0, w["num_classes"], (batch,), generator=g)
+    kw = dict(steps=w["steps"], gamma=w["gamma"], eps=w["eps"], perturb_idx=w["perturb_idx"],
+              randinit=w["randinit"], clip=w["clip"])
+    for _ in range(warmup):
+        ref_t.afan_train_iteration(model, opt, crit, x, y, **kw)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref_t.afan_train_iteration(model, opt, crit, x, y, **kw)
+    dt = time.perf_counter() - t0
+    return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} full iterations (after {warmup} warm-up) of the same workload at batch {batch} "
+                      f"on {cores} host threads, oracle/afan_ref_torch.py (plain-PyTorch port of main_perturb.py:173-201)",
+            "ms_per_step": 1e3 * dt / steps}
+
+
+def config_dict(n_gpus):
+    w = WORKLOAD
+    return {"workload": "BASELINE configs[1]: ResNet-56 CIFAR-100-shaped synthetic 32x32, A-FAN PGD-5 with dual BN",
+            "global_batch": w["batch_per_gpu"] * n_gpus, "batch_per_gpu": w["batch_per_gpu"],
+            "perturb_idx": w["perturb_idx"], "perturbed_feature": "128x16x32x32 fp32 per GPU",
+            "pgd_steps": w["steps"], "gamma_255": w["gamma"], "eps_255": w["eps"], "randinit": w["randinit"],
+            "clip": w["clip"], "parallelism": f"dp{n_gpus} (one process per GPU, NCCL)",
+            "conv_math": "fp32 (TF32 off)",
+            "l2": "no flush between steps: per-step working set (saved activations ~0.9 GB) exceeds the 126 MB L2; "
+                  "kernel rooflines are measured separately with an L2 flush between launches"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "A-FAN train img/s", "value": r["value"], "unit": "img/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel rooflines: cold-L2 micro-benchmarks of the hand-written kernels at the workload's shapes
+# ---------------------------------------------------------------------------------------------------
+def kernel_rooflines(pkg, dev, reps=20):
+    ops = pkg.ops
+    peak, peak_src = peaks()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
+    g = torch.Generator(device=dev).manual_seed(3)
+
+    def timed(fn, cold=True):
+        ts = []
+        for i in range(reps + 3):
+            if cold:
+                flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            e.synchronize()
+            if i >= 3:
+                ts.append(s.elapsed_time(e) * 1e-3)
+        return sum(ts) / len(ts)
+
+    res = []
+
+    def add(name, bytes_per_launch, fn, launches_per_iter, note):
+        t_cold, t_warm = timed(fn, True), timed(fn, False)
+        res.append({"kernel": name, "bytes": bytes_per_launch, "us_cold": t_cold * 1e6, "us_warm": t_warm * 1e6,
+                    "achieved": bytes_per_launch / t_cold / 1e9, "achieved_warm_l2": bytes_per_launch / t_warm / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / t_cold / 1e9 / peak,
+                    "launches_per_iter": launches_per_iter, "note": note})
+
+    w = WORKLOAD
+    n = w["batch_per_gpu"]
+    # the perturbed feature map of the workload and an L2-exceeding one (FRCNN config 4, B=8: 8x1024x38x63)
+    for tag, shape in (("cfg2 128x16x32x32", (n, 16, 32, 32)), ("cfg4 8x1024x38x63", (8, 1024, 38, 63))):
+        E = 1
+        for s in shape:
+            E *= s
+        x = torch.relu(1.5 * torch.randn(shape, device=dev, generator=g))
+        grad = 1e-3 * torch.randn(shape, device=dev, generator=g)
+        xa, delta = x.clone(), torch.empty_like(x)
+        norms, ws = torch.zeros(2, shape[0], device=dev), ops.norms_workspace(shape[0], dev)
+        gm, ep = w["gamma"] / 255, w["eps"] / 255
+        add(f"pgd_linf_step clip [{tag}]", 16 * E, lambda: ops.pgd_linf_step_(grad, x, xa, gm, ep, True),
+            w["steps"] - 1 if tag.startswith("cfg2") else 0, "read g,x_adv,x + write x_adv = 16 B/elem")
+        add(f"pgd_linf_step clip+delta+norms [{tag}]", 20 * E,
+            lambda: ops.pgd_linf_step_(grad, x, xa, gm, ep, True, delta_out=delta, norms_out=norms, workspace=ws),
+            0, "+ write delta = 20 B/elem, per-sample norms fused")
+        add(f"pgd_linf_step clip+norms [{tag}]", 16 * E,
+            lambda: ops.pgd_linf_step_(grad, x, xa, gm, ep, True, norms_out=norms, workspace=ws),
+            1 if tag.startswith("cfg2") else 0, "16 B/elem, per-sample norms fused (last PGD step of the trainer)")
+        add(f"pgd_linf_step noclip [{tag}]", 12 * E, lambda: ops.pgd_linf_step_(grad, None, xa, gm, ep, False), 0,
+            "shipped recipe (no clip): 12 B/elem")
+        add(f"pgd_init philox [{tag}]", 8 * E, lambda: ops.pgd_init(x, ep, seed=1, out=xa),
+            1 if tag.startswith("cfg2") else 0, "8 B/elem")
+        del x, grad, xa, delta
+    # dual BN at the tail shapes of the workload (stage 2/3 of ResNet-56) and one large shape
+    for tag, (G, N, C, H, W), lpi in (("G2 128x32x16x16", (2, n, 32, 16, 16), 18), ("G2 128x64x8x8", (2, n, 64, 8, 8), 18),
+                                      ("G1 128x32x16x16", (1, n, 32, 16, 16), 18 * w["steps"]),
+                                      ("G1 128x16x32x32", (1, n, 16, 32, 32), 19),
+                                      ("G2 256x64x56x56 (L2-exceeding)", (2, 256, 64, 56, 56), 0)):
+        x = torch.randn(G * N, C, H, W, device=dev, generator=g)
+        dy = torch.randn(G * N, C, H, W, device=dev, generator=g)
+        wt, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        wsb = ops.bn_workspace(G, C, dev)
+        L = pkg._lib.lib()
+        y = torch.empty_like(x)
+        dx = torch.empty_like(x)
+        sm, si = torch.empty(G, C, device=dev), torch.empty(G, C, device=dev)
+        dw, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
+        E = x.numel()
+        st = pkg._lib.stream
+        nb = wsb.numel() * 8
+
+        def fwd():
+            pkg._lib.check(L.afan_bn_fwd_f32(x.data_ptr(), None, wt.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                             y.data_ptr(), sm.data_ptr(), si.data_ptr(), wsb.data_ptr(), nb, G, N, C, H * W,
+                                             1e-5, 0.1, 1, 1, st()), "afan_bn_fwd_f32")
+
+        def bwd():
+            pkg._lib.check(L.afan_bn_bwd_f32(dy.data_ptr(), x.data_ptr(), y.data_ptr(), wt.data_ptr(), sm.data_ptr(),
+                                             si.data_ptr(), dx.data_ptr(), None, dw.data_ptr(), db.data_ptr(),
+                                             wsb.data_ptr(), nb, G, N, C, H * W, 1, st()), "afan_bn_bwd_f32")
+        add(f"dual_bn fwd+relu [{tag}]", 8 * E, fwd, lpi, "read x + write y = 8 B/elem (16 B per clean+adv pair); 2 launches")
+        fwd()
+        add(f"dual_bn bwd+relu [{tag}]", 16 * E, bwd, lpi, "read dy,x,y + write dx = 16 B/elem (12 without the ReLU mask); 2 launches")
+        del x, dy, y, dx
+    return res, peak_src
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="afan_b200", choices=["afan_b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--no-sync-bn", action="store_true", help="per-replica BN statistics (the reference's DataParallel behaviour)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-rooflines", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the afan_b200 path has no CPU fallback "
+                         "(use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        pg = torch.distributed.group.WORLD
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+
+    pkg = importlib.import_module("cv_a-fan_b200")
+    w = WORKLOAD
+    torch.manual_seed(3)                                     # identical weights on every rank
+    model = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)
+    trainer = pkg.trainer.AfanTrainer(model, perturb_idx=w["perturb_idx"], steps=w["steps"], gamma=w["gamma"],
+                                      eps=w["eps"], randinit=w["randinit"], clip=w["clip"], rng="philox", seed=3 + rank,
+                                      process_group=pg, sync_bn=not args.no_sync_bn, use_cuda_graph=not args.no_graph)
+    n = w["batch_per_gpu"]
+    g = torch.Generator().manual_seed(3 + rank)              # per-rank data
+    host_x = [torch.rand(n, *w["image"], generator=g).pin_memory() for _ in range(4)]
+    host_y = [torch.randint(0, w["num_classes"], (n,), generator=g).pin_memory() for _ in range(4)]
+    dev_x, dev_y = [t.to(dev) for t in host_x], [t.to(dev) for t in host_y]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed_run(step_fn):
+        for i in range(args.warmup):
+            step_fn(i)
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            s.record()
+            for i in range(args.steps):
+                step_fn(i)
+            e.record()
+            barrier()
+        ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms) / 1e3, clk.summary()
+
+    # (1) device-resident inputs
+    lib = pkg._lib
+    l0 = lib.launch_count
+    trainer.step(dev_x[0], dev_y[0])                         # builds arena, captures the graph
+    out = {}
+
+    def step_dev(i):
+        out["r"] = trainer.step(dev_x[i % 4], dev_y[i % 4])
+    sec, clocks = timed_run(step_dev)
+    loss_dev = float(out["r"]["loss"])
+
+    # (2) end to end: pinned host inputs -> H2D -> step -> D2H loss
+    host_loss = torch.zeros(1).pin_memory()
+    dx, dy = torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])
+
+    def step_e2e(i):
+        dx.copy_(host_x[i % 4], non_blocking=True)
+        dy.copy_(host_y[i % 4], non_blocking=True)
+        r = trainer.step(dx, dy)
+        host_loss.copy_(r["loss"].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()            # the user reads the loss every step (main_perturb.py:208)
+    sec_e2e, _ = timed_run(step_e2e)
+
+    per_iter = trainer.kernel_launches_per_iter      # afan kernels per iteration, counted at capture/trace time
+
+    global_batch = n * world
+    line = {"metric": "A-FAN train img/s", "value": global_batch * args.steps / sec, "unit": "img/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(world), "clocks": clocks,
+            "e2e": {"value": global_batch * args.steps / sec_e2e, "unit": "img/s",
+                    "h2d_bytes_per_step": (host_x[0].numel() * 4 + host_y[0].numel() * 8) * world,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * sec_e2e / args.steps},
+            "gpu_launches": per_iter * args.steps, "afan_kernels_per_step": per_iter,
+            "cuda_graph": not args.no_graph, "sync_bn": (not args.no_sync_bn) and world > 1, "final_loss": loss_dev}
+
+    if rank == 0 and not args.skip_rooflines:
+        ks, peak_src = kernel_rooflines(pkg, dev)
+        in_step = [k for k in ks if k["launches_per_iter"] > 0]
+        dom = max(in_step, key=lambda k: k["us_warm"] * k["launches_per_iter"])
+        line["roofline"] = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
+                            "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                            "timing": "CUDA events around one launch, L2 flushed (256 MB memset) before each"}
+        line["kernels"] = ks
+    if world > 1:
+        torch.distributed.barrier()
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        cb = cpu_reference(steps=4, warmup=1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

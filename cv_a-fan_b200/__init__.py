@@ -1,0 +1,18 @@
+"""afan_b200 -- B200-native (sm_100a) implementation of A-FAN's adversarial-feature inner loop.
+
+The directory is named `cv_a-fan_b200` (not a valid identifier): import it with
+`importlib.import_module("cv_a-fan_b200")` or through the `afan_b200` alias module at the repo root.
+
+Public surface (mirrors the reference's Python interface for this path):
+    attack_algo        PGD / linfball_proj / l2ball_proj / tensor_clamp      (Classification/attack_algo.py)
+    segmentation       PGD / mix_feature / get_sample_points                 (Segmentation/attack_algo.py)
+    detection          PGD / mix_feature / get_sample_points                 (Detection/attack_algo.py)
+    dual_bn            DualBatchNorm2d (clean/adversarial statistics in one sweep)
+    resnet_s           splittable CIFAR ResNet (Classification/resnet_s.py)
+    trainer            AfanTrainer: head-cached, CUDA-graphed A-FAN training step (main_perturb.py:173-201)
+    ops, _lib          tensor-level / ctypes bindings of include/afan_b200.h
+"""
+from . import _lib, ops  # noqa: F401
+from ._lib import AfanError, version  # noqa: F401
+
+__all__ = ["ops", "AfanError", "version"]

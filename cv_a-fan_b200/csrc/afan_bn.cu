@@ -1,0 +1,588 @@
+// afan_bn.cu -- dual (grouped-statistics) train-mode BatchNorm2d for sm_100a, forward + backward,
+// with normalise + affine + residual-add + ReLU fused.
+//
+// Replaces nn.BatchNorm2d / F.relu / `out += shortcut` of the reference tail,
+// Classification/resnet_s.py:54,56,70-76,89, as driven by main_perturb.py:195-196 where the SAME
+// module sees the adversarial and then the clean batch: here both halves of a [adv; clean] batch
+// are swept together, each with its own statistics ("groups"), shared affine and running averages.
+//
+// Layout: x [G*N][C][HW] contiguous fp32 (NCHW).  Per (group, channel) the statistic domain is N
+// planes of HW contiguous elements.
+//   pass 1 (bn_reduce_kernel): grid (S, G*C).  CTA (s, gc) streams slice s of the domain with 128-bit
+//     loads, reduces with warp shuffles + a shared-memory tree, writes one double2 partial.  The CTA
+//     that arrives last for a channel folds the partials of all its groups in a fixed order
+//     (deterministic; no float atomics) and finalises: mean/invstd, running-stat update in pass
+//     order, and the per-(g,c) coefficient table used by pass 2.
+//   pass 2 (bn_apply_kernel): flat streaming sweep, y = relu(x*scale + shift (+res)).
+// HBM bytes per element: fwd 8 algorithmic (read x, write y); the second read of x in pass 2 hits
+// the 126 MB L2 for every shape in BASELINE.json's configs.  bwd: 12 algorithmic (+4 for y if relu).
+#include <type_traits>
+
+#include "afan_common.cuh"
+
+namespace afan {
+
+constexpr int kBnUnroll = 4;
+
+struct BnLayout {            // workspace carve-up (bytes), shared by every BN entry point
+    int64_t counters, table, coef, partials, total;
+};
+__host__ inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+__host__ inline BnLayout bn_layout(int64_t groups, int64_t c) {
+    BnLayout l;
+    l.counters = 0;
+    l.table = align256(c * 4);
+    l.coef = l.table + align256(groups * c * 8);
+    l.partials = l.coef + align256(groups * c * 16);
+    l.total = l.partials + (static_cast<int64_t>(sm_count()) * kCtasPerSm + groups * c) * 16;
+    return l;
+}
+
+struct ReduceParams {
+    const float* a;          // fwd: x            bwd: dy
+    const float* b;          // fwd: unused       bwd: x
+    const float* y;          // bwd + relu: forward output (mask = y > 0)
+    const float* save_mean;  // bwd
+    const float* save_invstd;
+    double2* partials;
+    unsigned int* counters;
+    double* sums_out;        // nullable: [G][C][2] local sums for the NCCL path
+    // finalisation (do_finalize != 0)
+    int do_finalize;
+    const float* weight;
+    const float* bias;
+    float* running_mean;
+    float* running_var;
+    float* out_mean;         // fwd: save_mean
+    float* out_invstd;       // fwd: save_invstd
+    float2* table;           // fwd: (scale, shift) per (g,c)
+    float4* coef;            // bwd: (w*invstd, mean(dy), mean(dy*xhat)*invstd, mean) per (g,c)
+    float* dweight;          // bwd
+    float* dbias;
+    double count;            // elements per (g,c) statistic (global count under NCCL sync)
+    float eps, momentum;
+    int replay;
+    unsigned int groups, n, c, hwv, splits;
+};
+
+// ---- finalisation math, shared by the in-kernel path and the stand-alone finalize kernels ----
+__device__ __forceinline__ void fwd_finalize_channel(const ReduceParams& p, unsigned int ch, const double* sum,
+                                                     const double* sumsq) {
+    float rm = p.running_mean ? p.running_mean[ch] : 0.f, rv = p.running_var ? p.running_var[ch] : 0.f;
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        const double mean = sum[g] / p.count;
+        double var = sumsq[g] / p.count - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const double invstd = rsqrt(var + static_cast<double>(p.eps));
+        const double unbiased = p.count > 1.0 ? var * (p.count / (p.count - 1.0)) : var;
+        for (int r = 0; r < p.replay; ++r) {          // pass order: group 0 (adv) first, then group 1 (clean)
+            rm = static_cast<float>((1.0 - p.momentum) * rm + p.momentum * mean);
+            rv = static_cast<float>((1.0 - p.momentum) * rv + p.momentum * unbiased);
+        }
+        const unsigned int gc = g * p.c + ch;
+        const float w = p.weight ? p.weight[ch] : 1.f, b = p.bias ? p.bias[ch] : 0.f;
+        const float scale = static_cast<float>(w * invstd);
+        p.out_mean[gc] = static_cast<float>(mean);
+        p.out_invstd[gc] = static_cast<float>(invstd);
+        p.table[gc] = make_float2(scale, static_cast<float>(b - mean * w * invstd));
+    }
+    if (p.running_mean) p.running_mean[ch] = rm;
+    if (p.running_var) p.running_var[ch] = rv;
+}
+
+__device__ __forceinline__ void bwd_finalize_group(const ReduceParams& p, unsigned int gc, unsigned int ch,
+                                                   double s_dy, double s_dyxh) {
+    const float w = p.weight ? p.weight[ch] : 1.f;
+    const float invstd = p.save_invstd[gc];
+    p.coef[gc] = make_float4(w * invstd, static_cast<float>(s_dy / p.count),
+                             static_cast<float>(s_dyxh / p.count * invstd), p.save_mean[gc]);
+}
+
+// ---- pass 1 -------------------------------------------------------------------------------------
+template <int VEC, bool BWD, bool RELU>
+__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams p) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    const unsigned int s = blockIdx.x, gc = blockIdx.y;
+    const unsigned int g = gc / p.c, ch = gc - g * p.c;
+    const unsigned int J = p.n * p.hwv;                                   // vectors in this (g,c) domain
+    const unsigned int lo = static_cast<unsigned int>(static_cast<unsigned long long>(J) * s / p.splits);
+    const unsigned int hi = static_cast<unsigned int>(static_cast<unsigned long long>(J) * (s + 1) / p.splits);
+    const V* a_v = reinterpret_cast<const V*>(p.a);
+    const V* b_v = reinterpret_cast<const V*>(p.b);
+    const V* y_v = reinterpret_cast<const V*>(p.y);
+    const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;   // vector offset of plane (g*N+0, ch)
+    const size_t plane_stride = static_cast<size_t>(p.c) * p.hwv;
+    const float mean = BWD ? p.save_mean[gc] : 0.f;
+
+    float acc0 = 0.f, acc1 = 0.f;
+    for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kThreads * kBnUnroll) {
+        V a[kBnUnroll] = {}, b[kBnUnroll] = {}, y[kBnUnroll] = {};
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const unsigned int j = j0 + u * kThreads;
+            if (j < hi) {
+                const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
+                const size_t idx = plane0 + nn * plane_stride + off;
+                a[u] = a_v[idx];                                         // everything is re-read by pass 2 -> keep in L2
+                if (BWD) b[u] = b_v[idx];
+                if (BWD && RELU) y[u] = y_v[idx];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const unsigned int j = j0 + u * kThreads;
+            if (j < hi) {
+                if constexpr (VEC == 4) {
+                    const float av[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+                    const float bv[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+                    const float yv[4] = {y[u].x, y[u].y, y[u].z, y[u].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (BWD) {
+                            const float d = (RELU && !(yv[e] > 0.f)) ? 0.f : av[e];
+                            acc0 += d;
+                            acc1 = fmaf(d, bv[e] - mean, acc1);
+                        } else {
+                            acc0 += av[e];
+                            acc1 = fmaf(av[e], av[e], acc1);
+                        }
+                    }
+                } else {
+                    if (BWD) {
+                        const float d = (RELU && !(y[u] > 0.f)) ? 0.f : a[u];
+                        acc0 += d;
+                        acc1 = fmaf(d, b[u] - mean, acc1);
+                    } else {
+                        acc0 += a[u];
+                        acc1 = fmaf(a[u], a[u], acc1);
+                    }
+                }
+            }
+        }
+    }
+
+    __shared__ double scratch[64];
+    __shared__ int sflag;
+    double d0 = acc0, d1 = acc1;
+    block_sum2(d0, d1, scratch);
+    if (threadIdx.x == 0) {
+        if (BWD) d1 *= static_cast<double>(p.save_invstd[gc]);            // sum dy*(x-mean) -> sum dy*xhat
+        p.partials[static_cast<size_t>(gc) * p.splits + s] = make_double2(d0, d1);
+    }
+    // last CTA of this CHANNEL (all groups, all splits) folds and finalises
+    if (!last_cta_arrives(p.counters + ch, p.groups * p.splits, &sflag)) return;
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    constexpr int kMaxGroups = 8;
+    double t0[kMaxGroups], t1[kMaxGroups];
+    for (unsigned int gg = 0; gg < p.groups; ++gg) {
+        const volatile double* pp = reinterpret_cast<const volatile double*>(p.partials + (static_cast<size_t>(gg) * p.c + ch) * p.splits);
+        double x0 = 0.0, x1 = 0.0;
+        for (unsigned int k = lane; k < p.splits; k += 32) { x0 += pp[2 * k]; x1 += pp[2 * k + 1]; }
+        t0[gg] = warp_sum(x0);
+        t1[gg] = warp_sum(x1);
+    }
+    if (lane != 0) return;
+    if (p.sums_out)
+        for (unsigned int gg = 0; gg < p.groups; ++gg) {
+            p.sums_out[(static_cast<size_t>(gg) * p.c + ch) * 2] = t0[gg];
+            p.sums_out[(static_cast<size_t>(gg) * p.c + ch) * 2 + 1] = t1[gg];
+        }
+    if (BWD) {
+        double dw = 0.0, db = 0.0;
+        for (unsigned int gg = 0; gg < p.groups; ++gg) { db += t0[gg]; dw += t1[gg]; }
+        if (p.dweight) p.dweight[ch] = static_cast<float>(dw);
+        if (p.dbias) p.dbias[ch] = static_cast<float>(db);
+        if (p.do_finalize)
+            for (unsigned int gg = 0; gg < p.groups; ++gg) bwd_finalize_group(p, gg * p.c + ch, ch, t0[gg], t1[gg]);
+    } else if (p.do_finalize) {
+        fwd_finalize_channel(p, ch, t0, t1);
+    }
+}
+
+// stand-alone finalisers for the NCCL path (sums already all-reduced): one thread per channel
+__global__ void bn_fwd_finalize_kernel(const ReduceParams p, const double* sums) {
+    const unsigned int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.c) return;
+    double t0[8], t1[8];
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        t0[g] = sums[(static_cast<size_t>(g) * p.c + ch) * 2];
+        t1[g] = sums[(static_cast<size_t>(g) * p.c + ch) * 2 + 1];
+    }
+    fwd_finalize_channel(p, ch, t0, t1);
+}
+__global__ void bn_bwd_finalize_kernel(const ReduceParams p, const double* sums) {
+    const unsigned int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.c) return;
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        const size_t gc = static_cast<size_t>(g) * p.c + ch;
+        bwd_finalize_group(p, static_cast<unsigned int>(gc), ch, sums[gc * 2], sums[gc * 2 + 1]);
+    }
+}
+
+// ---- pass 2 -------------------------------------------------------------------------------------
+struct ApplyParams {
+    const float* x;          // fwd: x     bwd: dy
+    const float* b;          // fwd: residual (nullable)   bwd: x
+    const float* y;          // bwd + relu: forward output
+    float* out;              // fwd: y     bwd: dx
+    float* out2;             // bwd: dresidual (nullable)
+    const void* table;       // fwd: float2 [G*C]   bwd: float4 [G*C]
+    unsigned int total_v;    // vectors in the tensor
+    unsigned int hwv, c, n;  // n = samples per group
+};
+
+template <int VEC, bool RELU, bool RES>
+__global__ void __launch_bounds__(kThreads) bn_fwd_apply_kernel(const ApplyParams p) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    const V* x_v = reinterpret_cast<const V*>(p.x);
+    const V* r_v = reinterpret_cast<const V*>(p.b);
+    V* y_v = reinterpret_cast<V*>(p.out);
+    const float2* table = static_cast<const float2*>(p.table);
+    const unsigned int span = gridDim.x * kThreads * kBnUnroll;
+    for (unsigned int i0 = blockIdx.x * kThreads * kBnUnroll + threadIdx.x; i0 < p.total_v; i0 += span) {
+        V x[kBnUnroll] = {}, r[kBnUnroll] = {};
+        float2 ss[kBnUnroll] = {};
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const unsigned int i = i0 + u * kThreads;
+            if (i < p.total_v) {
+                x[u] = ld_stream(x_v + i);                 // last use of x in the forward pass
+                if (RES) r[u] = ld_stream(r_v + i);
+                const unsigned int plane = i / p.hwv;      // = sample * C + channel
+                const unsigned int smp = plane / p.c, ch = plane - smp * p.c;
+                ss[u] = __ldg(table + (smp / p.n) * p.c + ch);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const unsigned int i = i0 + u * kThreads;
+            if (i < p.total_v) {
+                V o;
+                if constexpr (VEC == 4) {
+                    o.x = fmaf(x[u].x, ss[u].x, ss[u].y); o.y = fmaf(x[u].y, ss[u].x, ss[u].y);
+                    o.z = fmaf(x[u].z, ss[u].x, ss[u].y); o.w = fmaf(x[u].w, ss[u].x, ss[u].y);
+                    if (RES) { o.x += r[u].x; o.y += r[u].y; o.z += r[u].z; o.w += r[u].w; }
+                    if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                } else {
+                    o = fmaf(x[u], ss[u].x, ss[u].y);
+                    if (RES) o += r[u];
+                    if (RELU) o = fmaxf(o, 0.f);
+                }
+                y_v[i] = o;                                // consumed by the next conv: default policy (stay in L2)
+            }
+        }
+    }
+}
+
+template <int VEC, bool RELU, bool DRES>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParams p) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    const V* dy_v = reinterpret_cast<const V*>(p.x);
+    const V* x_v = reinterpret_cast<const V*>(p.b);
+    const V* y_v = reinterpret_cast<const V*>(p.y);
+    V* dx_v = reinterpret_cast<V*>(p.out);
+    V* dr_v = reinterpret_cast<V*>(p.out2);
+    const float4* coef = static_cast<const float4*>(p.table);
+    const unsigned int span = gridDim.x * kThreads * kBnUnroll;
+    for (unsigned int i0 = blockIdx.x * kThreads * kBnUnroll + threadIdx.x; i0 < p.total_v; i0 += span) {
+        V dy[kBnUnroll] = {}, x[kBnUnroll] = {}, y[kBnUnroll] = {};
+        float4 cf[kBnUnroll] = {};
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const unsigned int i = i0 + u * kThreads;
+            if (i < p.total_v) {
+                dy[u] = ld_stream(dy_v + i);
+                x[u] = ld_stream(x_v + i);
+                if (RELU) y[u] = ld_stream(y_v + i);
+                const unsigned int plane = i / p.hwv;
+                const unsigned int smp = plane / p.c, ch = plane - smp * p.c;
+                cf[u] = __ldg(coef + (smp / p.n) * p.c + ch);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const unsigned int i = i0 + u * kThreads;
+            if (i < p.total_v) {
+                V dx, dr;
+                // dx = w*invstd * (dy_eff - mean(dy) - (x - mean) * invstd * mean(dy*xhat))
+                auto one = [&](float d, float xv, float yv, float& o, float& r) {
+                    const float de = (RELU && !(yv > 0.f)) ? 0.f : d;
+                    r = de;
+                    o = cf[u].x * (de - cf[u].y - (xv - cf[u].w) * cf[u].z);
+                };
+                if constexpr (VEC == 4) {
+                    one(dy[u].x, x[u].x, y[u].x, dx.x, dr.x); one(dy[u].y, x[u].y, y[u].y, dx.y, dr.y);
+                    one(dy[u].z, x[u].z, y[u].z, dx.z, dr.z); one(dy[u].w, x[u].w, y[u].w, dx.w, dr.w);
+                } else {
+                    one(dy[u], x[u], y[u], dx, dr);
+                }
+                dx_v[i] = dx;
+                if (DRES) dr_v[i] = dr;
+            }
+        }
+    }
+}
+
+// ---- host helpers -------------------------------------------------------------------------------
+struct BnShape {
+    bool ok, vec;
+    unsigned int groups, n, c, hwv, splits, total_v;
+    int err;
+};
+
+__host__ inline BnShape bn_shape(int64_t groups, int64_t n, int64_t c, int64_t hw, bool all_aligned) {
+    BnShape s{};
+    s.err = AFAN_OK;
+    if (groups < 1 || n < 0 || c < 0 || hw < 0) { s.err = AFAN_ERR_SIZE; return s; }
+    if (groups > 8 || groups * c > 65535) { s.err = AFAN_ERR_UNSUPPORTED; return s; }
+    const int64_t total = groups * n * c * hw;
+    if (total >= (int64_t(1) << 32) || n * hw >= (int64_t(1) << 32)) { s.err = AFAN_ERR_UNSUPPORTED; return s; }
+    s.vec = all_aligned && (hw % 4 == 0);
+    const int64_t v = s.vec ? 4 : 1;
+    s.groups = static_cast<unsigned int>(groups);
+    s.n = static_cast<unsigned int>(n);
+    s.c = static_cast<unsigned int>(c);
+    s.hwv = static_cast<unsigned int>(hw / v);
+    s.total_v = static_cast<unsigned int>(total / v);
+    // splits of each (g,c) domain: fill 148 x 8 CTAs, but keep >= 256*unroll vectors per CTA
+    const int64_t J = n * (hw / v);
+    int64_t target = (static_cast<int64_t>(sm_count()) * kCtasPerSm + groups * c - 1) / (groups * c > 0 ? groups * c : 1);
+    int64_t by_work = (J + kThreads * kBnUnroll - 1) / (kThreads * kBnUnroll);
+    int64_t sp = target < by_work ? target : by_work;
+    s.splits = static_cast<unsigned int>(sp < 1 ? 1 : sp);
+    s.ok = total > 0;
+    return s;
+}
+
+__host__ inline int apply_grid(unsigned int total_v) {
+    const int64_t want = (static_cast<int64_t>(total_v) + kThreads * kBnUnroll - 1) / (kThreads * kBnUnroll);
+    const int64_t cap = static_cast<int64_t>(sm_count()) * kCtasPerSm;
+    return static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+template <bool BWD>
+int launch_reduce(const ReduceParams& p, bool vec, bool relu, cudaStream_t st) {
+    dim3 grid(p.splits, p.groups * p.c);
+    if (vec) {
+        if (BWD && relu) bn_reduce_kernel<4, BWD, true><<<grid, kThreads, 0, st>>>(p);
+        else bn_reduce_kernel<4, BWD, false><<<grid, kThreads, 0, st>>>(p);
+    } else {
+        if (BWD && relu) bn_reduce_kernel<1, BWD, true><<<grid, kThreads, 0, st>>>(p);
+        else bn_reduce_kernel<1, BWD, false><<<grid, kThreads, 0, st>>>(p);
+    }
+    return launch_status();
+}
+
+int launch_fwd_apply(const ApplyParams& p, bool vec, bool relu, bool res, cudaStream_t st) {
+    const int grid = apply_grid(p.total_v);
+#define AFAN_FA(V, R, S) bn_fwd_apply_kernel<V, R, S><<<grid, kThreads, 0, st>>>(p)
+    if (vec) { if (relu) { if (res) AFAN_FA(4, true, true); else AFAN_FA(4, true, false); }
+               else      { if (res) AFAN_FA(4, false, true); else AFAN_FA(4, false, false); } }
+    else     { if (relu) { if (res) AFAN_FA(1, true, true); else AFAN_FA(1, true, false); }
+               else      { if (res) AFAN_FA(1, false, true); else AFAN_FA(1, false, false); } }
+#undef AFAN_FA
+    return launch_status();
+}
+
+int launch_bwd_apply(const ApplyParams& p, bool vec, bool relu, bool dres, cudaStream_t st) {
+    const int grid = apply_grid(p.total_v);
+#define AFAN_BA(V, R, S) bn_bwd_apply_kernel<V, R, S><<<grid, kThreads, 0, st>>>(p)
+    if (vec) { if (relu) { if (dres) AFAN_BA(4, true, true); else AFAN_BA(4, true, false); }
+               else      { if (dres) AFAN_BA(4, false, true); else AFAN_BA(4, false, false); } }
+    else     { if (relu) { if (dres) AFAN_BA(1, true, true); else AFAN_BA(1, true, false); }
+               else      { if (dres) AFAN_BA(1, false, true); else AFAN_BA(1, false, false); } }
+#undef AFAN_BA
+    return launch_status();
+}
+
+__host__ inline bool ws_ok(void* ws, int64_t bytes, int64_t groups, int64_t c) {
+    return ws && aligned16(ws) && bytes >= bn_layout(groups, c).total;
+}
+__host__ inline char* wsp(const void* ws, int64_t off) { return static_cast<char*>(const_cast<void*>(ws)) + off; }
+
+}  // namespace afan
+
+using namespace afan;
+
+AFAN_EXPORT int64_t afan_bn_workspace_bytes(int64_t groups, int64_t channels) {
+    if (groups < 1 || channels < 0) return AFAN_ERR_SIZE;
+    return bn_layout(groups, channels).total;
+}
+
+// ---- forward ------------------------------------------------------------------------------------
+static int bn_fwd_reduce_impl(const float* x, double* sums_out, bool finalize, const float* weight, const float* bias,
+                              float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                              void* ws, int64_t ws_bytes, int64_t groups, int64_t n, int64_t c, int64_t hw, float eps,
+                              float momentum, int replay, cudaStream_t st, BnShape* shape_out) {
+    BnShape s = bn_shape(groups, n, c, hw, aligned16(x));
+    if (s.err != AFAN_OK) return s.err;
+    *shape_out = s;
+    if (!s.ok) return AFAN_OK;
+    if (!x || (finalize && (!save_mean || !save_invstd))) return AFAN_ERR_NULL;
+    if (!ws_ok(ws, ws_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
+    const BnLayout l = bn_layout(groups, c);
+    ReduceParams p{};
+    p.a = x;
+    p.partials = reinterpret_cast<double2*>(wsp(ws, l.partials));
+    p.counters = reinterpret_cast<unsigned int*>(wsp(ws, l.counters));
+    p.sums_out = sums_out;
+    p.do_finalize = finalize ? 1 : 0;
+    p.weight = weight; p.bias = bias; p.running_mean = running_mean; p.running_var = running_var;
+    p.out_mean = save_mean; p.out_invstd = save_invstd;
+    p.table = reinterpret_cast<float2*>(wsp(ws, l.table));
+    p.count = static_cast<double>(n) * static_cast<double>(hw);
+    p.eps = eps; p.momentum = momentum; p.replay = replay;
+    p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv; p.splits = s.splits;
+    return launch_reduce<false>(p, s.vec, false, st);
+}
+
+AFAN_EXPORT int afan_bn_fwd_apply_f32(const float* x, const float* residual, float* y, const void* workspace,
+                                      int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c, int64_t hw,
+                                      int relu, afan_stream_t stream) {
+    BnShape s = bn_shape(groups, n, c, hw, aligned16(x) && aligned16(y) && (!residual || aligned16(residual)));
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_OK;
+    if (!x || !y) return AFAN_ERR_NULL;
+    if (!ws_ok(const_cast<void*>(workspace), workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
+    ApplyParams p{};
+    p.x = x; p.b = residual; p.out = y;
+    p.table = wsp(workspace, bn_layout(groups, c).table);
+    p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
+    return launch_fwd_apply(p, s.vec, relu != 0, residual != nullptr, static_cast<cudaStream_t>(stream));
+}
+
+AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const float* weight, const float* bias,
+                                float* running_mean, float* running_var, float* y, float* save_mean,
+                                float* save_invstd, void* workspace, int64_t workspace_bytes, int64_t groups,
+                                int64_t n, int64_t c, int64_t hw, float eps, float momentum, int relu, int replay,
+                                afan_stream_t stream) {
+    BnShape s{};   // (each pass picks its own vector/scalar path; partial and table formats do not depend on it)
+    int rc = bn_fwd_reduce_impl(x, nullptr, true, weight, bias, running_mean, running_var, save_mean, save_invstd,
+                                workspace, workspace_bytes, groups, n, c, hw, eps, momentum, replay,
+                                static_cast<cudaStream_t>(stream), &s);
+    if (rc != AFAN_OK || !s.ok) return rc;
+    return afan_bn_fwd_apply_f32(x, residual, y, workspace, workspace_bytes, groups, n, c, hw, relu, stream);
+}
+
+AFAN_EXPORT int afan_bn_fwd_stats_f32(const float* x, double* sums, void* workspace, int64_t workspace_bytes,
+                                      int64_t groups, int64_t n, int64_t c, int64_t hw, afan_stream_t stream) {
+    if (!sums) return AFAN_ERR_NULL;
+    BnShape s{};
+    return bn_fwd_reduce_impl(x, sums, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, workspace,
+                              workspace_bytes, groups, n, c, hw, 0.f, 0.f, 0, static_cast<cudaStream_t>(stream), &s);
+}
+
+AFAN_EXPORT int afan_bn_fwd_finalize_f32(const double* sums, double count, const float* weight, const float* bias,
+                                         float* running_mean, float* running_var, float* save_mean,
+                                         float* save_invstd, void* workspace, int64_t workspace_bytes, int64_t groups,
+                                         int64_t c, float eps, float momentum, int replay, afan_stream_t stream) {
+    if (groups < 1 || c < 0 || !(count > 0)) return AFAN_ERR_SIZE;
+    if (groups > 8) return AFAN_ERR_UNSUPPORTED;
+    if (c == 0) return AFAN_OK;
+    if (!sums || !save_mean || !save_invstd) return AFAN_ERR_NULL;
+    if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
+    ReduceParams p{};
+    p.weight = weight; p.bias = bias; p.running_mean = running_mean; p.running_var = running_var;
+    p.out_mean = save_mean; p.out_invstd = save_invstd;
+    p.table = reinterpret_cast<float2*>(wsp(workspace, bn_layout(groups, c).table));
+    p.count = count; p.eps = eps; p.momentum = momentum; p.replay = replay;
+    p.groups = static_cast<unsigned int>(groups); p.c = static_cast<unsigned int>(c);
+    bn_fwd_finalize_kernel<<<static_cast<unsigned int>((c + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p, sums);
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_bn_affine_f32(const float* x, const float* residual, const float* scale_shift, float* y,
+                                   int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream) {
+    BnShape s = bn_shape(1, n, c, hw, aligned16(x) && aligned16(y) && (!residual || aligned16(residual)));
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_OK;
+    if (!x || !y || !scale_shift) return AFAN_ERR_NULL;
+    ApplyParams p{};
+    p.x = x; p.b = residual; p.out = y; p.table = scale_shift;
+    p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
+    return launch_fwd_apply(p, s.vec, relu != 0, residual != nullptr, static_cast<cudaStream_t>(stream));
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+static int bn_bwd_reduce_impl(const float* dy, const float* x, const float* y, const float* weight,
+                              const float* save_mean, const float* save_invstd, double* sums_out, bool finalize,
+                              float* dweight, float* dbias, void* ws, int64_t ws_bytes, int64_t groups, int64_t n,
+                              int64_t c, int64_t hw, int relu, bool aligned_all, cudaStream_t st, BnShape* shape_out) {
+    BnShape s = bn_shape(groups, n, c, hw, aligned_all);
+    if (s.err != AFAN_OK) return s.err;
+    *shape_out = s;
+    if (!s.ok) return AFAN_OK;
+    if (!dy || !x || !save_mean || !save_invstd || (relu && !y)) return AFAN_ERR_NULL;
+    if (!ws_ok(ws, ws_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
+    const BnLayout l = bn_layout(groups, c);
+    ReduceParams p{};
+    p.a = dy; p.b = x; p.y = y; p.save_mean = save_mean; p.save_invstd = save_invstd;
+    p.partials = reinterpret_cast<double2*>(wsp(ws, l.partials));
+    p.counters = reinterpret_cast<unsigned int*>(wsp(ws, l.counters));
+    p.sums_out = sums_out;
+    p.do_finalize = finalize ? 1 : 0;
+    p.weight = weight;
+    p.coef = reinterpret_cast<float4*>(wsp(ws, l.coef));
+    p.dweight = dweight; p.dbias = dbias;
+    p.count = static_cast<double>(n) * static_cast<double>(hw);
+    p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv; p.splits = s.splits;
+    return launch_reduce<true>(p, s.vec, relu != 0, st);
+}
+
+AFAN_EXPORT int afan_bn_bwd_apply_f32(const float* dy, const float* x, const float* y, float* dx, float* dresidual,
+                                      const void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n,
+                                      int64_t c, int64_t hw, int relu, afan_stream_t stream) {
+    const bool al = aligned16(dy) && aligned16(x) && aligned16(dx) && (!y || aligned16(y)) &&
+                    (!dresidual || aligned16(dresidual));
+    BnShape s = bn_shape(groups, n, c, hw, al);
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_OK;
+    if (!dy || !x || !dx || (relu && !y)) return AFAN_ERR_NULL;
+    if (!ws_ok(const_cast<void*>(workspace), workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
+    ApplyParams p{};
+    p.x = dy; p.b = x; p.y = y; p.out = dx; p.out2 = dresidual;
+    p.table = wsp(workspace, bn_layout(groups, c).coef);
+    p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
+    return launch_bwd_apply(p, s.vec, relu != 0, dresidual != nullptr, static_cast<cudaStream_t>(stream));
+}
+
+AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y, const float* weight,
+                                const float* save_mean, const float* save_invstd, float* dx, float* dresidual,
+                                float* dweight, float* dbias, void* workspace, int64_t workspace_bytes,
+                                int64_t groups, int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream) {
+    BnShape s{};
+    const bool al = aligned16(dy) && aligned16(x) && (!y || aligned16(y));
+    int rc = bn_bwd_reduce_impl(dy, x, y, weight, save_mean, save_invstd, nullptr, true, dweight, dbias, workspace,
+                                workspace_bytes, groups, n, c, hw, relu, al, static_cast<cudaStream_t>(stream), &s);
+    if (rc != AFAN_OK || !s.ok) return rc;
+    return afan_bn_bwd_apply_f32(dy, x, y, dx, dresidual, workspace, workspace_bytes, groups, n, c, hw, relu, stream);
+}
+
+AFAN_EXPORT int afan_bn_bwd_reduce_f32(const float* dy, const float* x, const float* y, const float* save_mean,
+                                       const float* save_invstd, double* sums, float* dweight, float* dbias,
+                                       void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c,
+                                       int64_t hw, int relu, afan_stream_t stream) {
+    if (!sums) return AFAN_ERR_NULL;
+    BnShape s{};
+    const bool al = aligned16(dy) && aligned16(x) && (!y || aligned16(y));
+    return bn_bwd_reduce_impl(dy, x, y, nullptr, save_mean, save_invstd, sums, false, dweight, dbias, workspace,
+                              workspace_bytes, groups, n, c, hw, relu, al, static_cast<cudaStream_t>(stream), &s);
+}
+
+AFAN_EXPORT int afan_bn_bwd_finalize_f32(const double* sums, double count, const float* weight, const float* save_mean,
+                                         const float* save_invstd, void* workspace, int64_t workspace_bytes,
+                                         int64_t groups, int64_t c, afan_stream_t stream) {
+    if (groups < 1 || c < 0 || !(count > 0)) return AFAN_ERR_SIZE;
+    if (groups > 8) return AFAN_ERR_UNSUPPORTED;
+    if (c == 0) return AFAN_OK;
+    if (!sums || !save_mean || !save_invstd) return AFAN_ERR_NULL;
+    if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
+    ReduceParams p{};
+    p.weight = weight; p.save_mean = save_mean; p.save_invstd = save_invstd;
+    p.coef = reinterpret_cast<float4*>(wsp(workspace, bn_layout(groups, c).coef));
+    p.count = count;
+    p.groups = static_cast<unsigned int>(groups); p.c = static_cast<unsigned int>(c);
+    bn_bwd_finalize_kernel<<<static_cast<unsigned int>((c + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p, sums);
+    return launch_status();
+}

@@ -1,0 +1,161 @@
+// afan_mix.cu -- mix_feature for sm_100a: the reference's adversarial feature NORMALISATION.
+//
+// Replaces Segmentation/attack_algo.py:121-130 == Detection/attack_algo.py:254-265 (12 un-fused ATen
+// launches, ~10 passes over memory):  per pixel (n,h,w), mean and sqrt(unbiased var + 1e-5) over the
+// CHANNEL dim of the clean feature are swapped for those of the adversarial feature.
+//
+// NCHW makes the reduction dim (C) the strided one (stride H*W) while coalescing wants threads along
+// W, so a CTA owns a tile of 32*VEC consecutive pixels of one sample: lanes run along pixels (128-bit
+// loads when H*W % 4 == 0), the 16 warps split the channels.  Sweep 1 keeps one Welford state per
+// (pixel, tensor) in registers -- clean and adversarial statistics in the SAME sweep -- then the warps'
+// states are merged through shared memory in a fixed order (Chan).  Sweep 2 re-reads the tile (L1/L2
+// hot: it was touched microseconds ago) and writes the mixed feature: 12 B/elem of HBM traffic.
+#include <type_traits>
+
+#include "afan_common.cuh"
+
+namespace afan {
+
+constexpr int kMixThreads = 512;
+constexpr int kMixWarps = kMixThreads / 32;
+constexpr int kMixUnroll = 4;                 // channels in flight per thread per tensor
+
+struct Welford {
+    float mean = 0.f, m2 = 0.f;
+    __device__ __forceinline__ void push(float x, float rcp_count) {
+        const float d = x - mean;
+        mean = fmaf(d, rcp_count, mean);
+        m2 = fmaf(d, x - mean, m2);
+    }
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kMixThreads)
+mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ adv, float* __restrict__ out,
+                   unsigned int c, unsigned int hw, unsigned int tiles_per_sample) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    constexpr int PT = 32 * VEC;                                     // pixels per CTA tile
+    __shared__ float s_mean[2][kMixWarps][PT], s_m2[2][kMixWarps][PT];
+    __shared__ float s_stat[4][PT];                                  // mean_cl, std_cl, mean_ad, std_ad
+
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int n = blockIdx.x / tiles_per_sample, tile = blockIdx.x - n * tiles_per_sample;
+    const unsigned int p0 = tile * PT + lane * VEC;                  // first pixel of this lane
+    const bool active = p0 < hw;                                     // VEC==4 implies hw % 4 == 0: whole vector valid
+    const size_t base = static_cast<size_t>(n) * c * hw + p0;
+
+    // ---- sweep 1: Welford over this warp's channels (warp, warp+16, ...) ----
+    Welford wc[VEC], wa[VEC];
+    unsigned int count = 0;
+    if (active) {
+        for (unsigned int k0 = warp; k0 < c; k0 += kMixWarps * kMixUnroll) {
+            V xc[kMixUnroll] = {}, xa[kMixUnroll] = {};
+#pragma unroll
+            for (int u = 0; u < kMixUnroll; ++u) {
+                const unsigned int k = k0 + u * kMixWarps;
+                if (k < c) {
+                    xc[u] = *reinterpret_cast<const V*>(clean + base + static_cast<size_t>(k) * hw);
+                    xa[u] = *reinterpret_cast<const V*>(adv + base + static_cast<size_t>(k) * hw);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kMixUnroll; ++u) {
+                const unsigned int k = k0 + u * kMixWarps;
+                if (k < c) {
+                    const float r = 1.0f / static_cast<float>(++count);
+                    if constexpr (VEC == 4) {
+                        wc[0].push(xc[u].x, r); wc[1].push(xc[u].y, r); wc[2].push(xc[u].z, r); wc[3].push(xc[u].w, r);
+                        wa[0].push(xa[u].x, r); wa[1].push(xa[u].y, r); wa[2].push(xa[u].z, r); wa[3].push(xa[u].w, r);
+                    } else {
+                        wc[0].push(xc[u], r);
+                        wa[0].push(xa[u], r);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        s_mean[0][warp][lane * VEC + v] = wc[v].mean; s_m2[0][warp][lane * VEC + v] = wc[v].m2;
+        s_mean[1][warp][lane * VEC + v] = wa[v].mean; s_m2[1][warp][lane * VEC + v] = wa[v].m2;
+    }
+    __syncthreads();
+
+    // ---- merge the warps' states in warp order (Chan et al.), one thread per (pixel, tensor) ----
+    if (threadIdx.x < 2 * PT) {
+        const unsigned int t = threadIdx.x / PT, px = threadIdx.x - t * PT;
+        float mean = 0.f, m2 = 0.f, cnt = 0.f;
+        for (unsigned int w = 0; w < kMixWarps; ++w) {
+            const float nb = w < c ? static_cast<float>((c - w + kMixWarps - 1) / kMixWarps) : 0.f;   // channels warp w saw
+            if (nb == 0.f) continue;
+            const float mb = s_mean[t][w][px], qb = s_m2[t][w][px];
+            const float tot = cnt + nb, d = mb - mean;
+            mean = fmaf(d, nb / tot, mean);
+            m2 = m2 + qb + d * d * (cnt * nb / tot);
+            cnt = tot;
+        }
+        const float var = m2 / (static_cast<float>(c) - 1.0f);        // torch.var default: unbiased; C == 1 -> NaN
+        s_stat[2 * t][px] = mean;
+        s_stat[2 * t + 1][px] = sqrtf(var + 1e-5f);
+    }
+    __syncthreads();
+    if (!active) return;
+
+    // ---- sweep 2: out = (clean - mean_cl) / std_cl * std_adv + mean_adv, in the reference's op order ----
+    float mcl[VEC], scl[VEC], mad[VEC], sad[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        mcl[v] = s_stat[0][lane * VEC + v]; scl[v] = s_stat[1][lane * VEC + v];
+        mad[v] = s_stat[2][lane * VEC + v]; sad[v] = s_stat[3][lane * VEC + v];
+    }
+    auto mix1 = [](float x, float m_c, float s_c, float m_a, float s_a) {
+        return __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, m_c), s_c), s_a), m_a);
+    };
+    for (unsigned int k0 = warp; k0 < c; k0 += kMixWarps * kMixUnroll) {
+        V xc[kMixUnroll] = {};
+#pragma unroll
+        for (int u = 0; u < kMixUnroll; ++u) {
+            const unsigned int k = k0 + u * kMixWarps;
+            if (k < c) xc[u] = *reinterpret_cast<const V*>(clean + base + static_cast<size_t>(k) * hw);
+        }
+#pragma unroll
+        for (int u = 0; u < kMixUnroll; ++u) {
+            const unsigned int k = k0 + u * kMixWarps;
+            if (k < c) {
+                V o;
+                if constexpr (VEC == 4) {
+                    o.x = mix1(xc[u].x, mcl[0], scl[0], mad[0], sad[0]); o.y = mix1(xc[u].y, mcl[1], scl[1], mad[1], sad[1]);
+                    o.z = mix1(xc[u].z, mcl[2], scl[2], mad[2], sad[2]); o.w = mix1(xc[u].w, mcl[3], scl[3], mad[3], sad[3]);
+                } else {
+                    o = mix1(xc[u], mcl[0], scl[0], mad[0], sad[0]);
+                }
+                st_stream(reinterpret_cast<V*>(out + base + static_cast<size_t>(k) * hw), o);
+            }
+        }
+    }
+}
+
+}  // namespace afan
+
+using namespace afan;
+
+AFAN_EXPORT int afan_mix_feature_f32(const float* clean, const float* adv, float* out, int64_t n, int64_t c,
+                                     int64_t hw, afan_stream_t stream) {
+    if (n < 0 || c < 0 || hw < 0) return AFAN_ERR_SIZE;
+    if (n == 0 || c == 0 || hw == 0) return AFAN_OK;
+    if (!clean || !adv || !out) return AFAN_ERR_NULL;
+    if (c >= (int64_t(1) << 31) || hw >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (hw % 4 == 0) && aligned16(clean) && aligned16(adv) && aligned16(out);
+    const int64_t pt = vec ? 128 : 32;
+    const int64_t tiles = (hw + pt - 1) / pt;
+    if (n * tiles >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
+    const unsigned int grid = static_cast<unsigned int>(n * tiles);
+    if (vec)
+        mix_feature_kernel<4><<<grid, kMixThreads, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
+                                                           static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
+    else
+        mix_feature_kernel<1><<<grid, kMixThreads, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
+                                                           static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
+    return launch_status();
+}

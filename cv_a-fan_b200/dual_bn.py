@@ -1,0 +1,110 @@
+"""Dual (grouped-statistics) BatchNorm2d with fused residual-add + ReLU, backed by the sm_100a kernels.
+
+What "dual BN" means for A-FAN: the reference has no special module -- the SAME
+nn.BatchNorm2d in the tail sees the adversarial batch and then the clean batch in two separate forward
+passes (Classification/main_perturb.py:195-196 through resnet_s.py:54,56,89), i.e. separate batch
+statistics, shared weight/bias, one running average updated in pass order.  DualBatchNorm2d computes
+exactly that for a concatenated [adv; clean] batch in ONE sweep (`groups=2`), and degenerates to a plain
+train-mode BatchNorm2d for `groups=1` (the PGD inner-loop passes).  state_dict keys equal nn.BatchNorm2d's.
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import AfanError
+
+
+class _DualBNTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, ws, groups, eps, momentum, relu, replay,
+                process_group):
+        x = x.contiguous()
+        res = residual.contiguous() if residual is not None else None
+        y, save_mean, save_invstd = ops.bn_fwd(x, res, weight, bias, running_mean, running_var, ws, groups=groups,
+                                               eps=eps, momentum=momentum, relu=relu, replay=replay,
+                                               process_group=process_group)
+        ctx.save_for_backward(x, y if relu else None, weight, save_mean, save_invstd)
+        ctx.ws, ctx.groups, ctx.relu, ctx.has_res, ctx.pg = ws, groups, relu, residual is not None, process_group
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, save_mean, save_invstd = ctx.saved_tensors
+        want_res = ctx.has_res and ctx.needs_input_grad[1]
+        dx, dres, dw, db = ops.bn_bwd(dy.contiguous(), x, y, weight, save_mean, save_invstd, ctx.ws,
+                                      groups=ctx.groups, relu=ctx.relu, want_dresidual=want_res,
+                                      process_group=ctx.pg)
+        return (dx, dres, dw if ctx.needs_input_grad[2] else None, db if ctx.needs_input_grad[3] else None,
+                None, None, None, None, None, None, None, None, None)
+
+
+class _AffineEvalFn(torch.autograd.Function):
+    """model.eval(): y = relu?(x*scale + shift (+res)) from running statistics (main_perturb.py:232-246)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, scale_shift, relu):
+        x = x.contiguous()
+        res = residual.contiguous() if residual is not None else None
+        y = ops.bn_affine(x, res, scale_shift, relu=relu)
+        ctx.save_for_backward(y if relu else None, scale_shift)
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        raise AfanError("eval-mode DualBatchNorm2d is inference-only; the reference runs PGD and training "
+                        "passes in train() mode (Classification/main_perturb.py:160)")
+
+
+class DualBatchNorm2d(nn.Module):
+    """BatchNorm2d whose forward takes `groups` (statistic groups along the batch), an optional residual
+    and a fused ReLU.  Parameters / buffers are named like nn.BatchNorm2d so reference checkpoints load."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self._ws = {}                  # groups -> workspace tensor (device scratch owned by this module)
+        self._pending_batches = 0      # host-side count, folded into num_batches_tracked lazily (no launch per pass)
+        self.process_group = None      # set by the trainer for NCCL-synchronised statistics
+        self._register_state_dict_hook(_flush_hook)
+
+    def _workspace(self, groups: int, device):
+        ws = self._ws.get((groups, device))
+        if ws is None:
+            ws = self._ws[(groups, device)] = ops.bn_workspace(groups, self.num_features, device)
+        return ws
+
+    def flush_batches_tracked(self, multiplier: int = 1):
+        if self._pending_batches:
+            self.num_batches_tracked += self._pending_batches * multiplier
+            self._pending_batches = 0
+
+    def forward(self, x, residual: Optional[torch.Tensor] = None, relu: bool = False, groups: int = 1,
+                replay: int = 1):
+        if x.dim() != 4 or x.shape[1] != self.num_features:
+            raise AfanError(f"expected [N, {self.num_features}, H, W], got {tuple(x.shape)}")
+        if self.training:
+            self._pending_batches += groups * replay
+            return _DualBNTrainFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
+                                        self._workspace(groups, x.device), groups, self.eps, self.momentum, relu,
+                                        replay, self.process_group)
+        invstd = torch.rsqrt(self.running_var + self.eps)
+        scale = self.weight.detach() * invstd
+        scale_shift = torch.stack((scale, self.bias.detach() - self.running_mean * scale), dim=1).contiguous()
+        return _AffineEvalFn.apply(x, residual, scale_shift, relu)
+
+    def extra_repr(self):
+        return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}"
+
+
+def _flush_hook(module, state_dict, prefix, local_metadata):
+    module.flush_batches_tracked()
+    state_dict[prefix + "num_batches_tracked"] = module.num_batches_tracked.detach().clone()
+    return state_dict

@@ -1,0 +1,216 @@
+"""Tensor-level wrappers over the C ABI (include/afan_b200.h).  CUDA fp32 contiguous tensors only;
+every function launches on torch's current stream and never synchronises.  No fallback paths."""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AfanError, check, f32, ptr, stream
+
+
+def _samples(x: torch.Tensor) -> Tuple[int, int]:
+    n = x.shape[0] if x.dim() > 0 else 1
+    return n, (x.numel() // n if n > 0 else 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# PGD (a2, a3, a4, a11)
+# ------------------------------------------------------------------------------------------------
+def pgd_init(x: torch.Tensor, eps: float, *, noise: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+             offset: int = 0, offset_device: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Random start x + (2u-1)*eps (Classification/attack_algo.py:42-44).  `noise` = u drawn by the
+    caller (bitwise parity with the reference's CPU torch.rand); otherwise on-device Philox(seed, offset)."""
+    out = torch.empty_like(x) if out is None else out
+    if noise is not None:
+        if noise.shape != x.shape:
+            raise AfanError("noise must have the shape of x")
+        check(_lib.lib().afan_pgd_init_noise_f32(f32(x, "x"), f32(noise, "noise"), f32(out, "out"), x.numel(),
+                                                 float(eps), stream()), "afan_pgd_init_noise_f32")
+    else:
+        if seed is None:
+            raise AfanError("pgd_init needs either noise= or seed=")
+        if offset_device is not None and offset_device.dtype not in (torch.int64, torch.uint64):
+            raise AfanError("offset_device must be a 64-bit integer CUDA tensor")
+        check(_lib.lib().afan_pgd_init_philox_f32(f32(x, "x"), f32(out, "out"), x.numel(), float(eps),
+                                                  int(seed) & (2 ** 64 - 1), int(offset), ptr(offset_device),
+                                                  stream()), "afan_pgd_init_philox_f32")
+    return out
+
+
+def norms_workspace(n_samples: int, device) -> torch.Tensor:
+    nbytes = _lib.lib().afan_pgd_norms_workspace_bytes(int(n_samples))
+    return torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=device)
+
+
+def pgd_linf_step_(grad: torch.Tensor, x_clean: Optional[torch.Tensor], x_adv: torch.Tensor, gamma: float,
+                   eps: float, clip: bool, *, delta_out: Optional[torch.Tensor] = None,
+                   norms_out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One fused L-inf PGD update IN PLACE on x_adv (Classification/attack_algo.py:53-56).
+    norms_out: float32 [2, N] -> per-sample L2 and Linf of (x_adv - x_clean) (main_perturb.py:188-192)."""
+    n, per = _samples(x_adv)
+    if (grad is not None and grad.shape != x_adv.shape) or (x_clean is not None and x_clean.shape != x_adv.shape):
+        raise AfanError("grad / x_clean must have the shape of x_adv")
+    if norms_out is not None:
+        if workspace is None:
+            workspace = norms_workspace(n, x_adv.device)
+        if norms_out.numel() != 2 * n:
+            raise AfanError("norms_out must hold 2*N floats")
+    check(_lib.lib().afan_pgd_linf_step_f32(
+        f32(grad, "grad"), f32(x_clean, "x_clean"), f32(x_adv, "x_adv"), f32(delta_out, "delta_out"),
+        f32(norms_out, "norms_out"), ptr(workspace), workspace.numel() * workspace.element_size() if workspace is not None else 0,
+        n, per, float(gamma), float(eps), int(bool(clip)), stream()), "afan_pgd_linf_step_f32")
+    return x_adv
+
+
+def sample_l2norm(a: torch.Tensor, b: Optional[torch.Tensor] = None, *, out: Optional[torch.Tensor] = None,
+                  workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-sample ||a - b||_2 (b=None -> ||a||_2): `.view(N,-1).norm(p=2, dim=1)` of attack_algo.py:28."""
+    n, per = _samples(a)
+    out = torch.empty(n, dtype=torch.float32, device=a.device) if out is None else out
+    workspace = norms_workspace(n, a.device) if workspace is None else workspace
+    check(_lib.lib().afan_sample_l2norm_f32(f32(a, "a"), f32(b, "b"), f32(out, "out"), ptr(workspace),
+                                            workspace.numel() * workspace.element_size(), n, per, stream()),
+          "afan_sample_l2norm_f32")
+    return out
+
+
+def pgd_l2_step_(grad, x_clean, x_adv, gamma, eps, clip, *, delta_out=None, tiny=1e-12, workspace=None):
+    """L2-normalised ascent IN PLACE (+ l2ball_proj when clip), see include/afan_b200.h a5/a5b."""
+    n, per = _samples(x_adv)
+    workspace = norms_workspace(n, x_adv.device) if workspace is None else workspace
+    L = _lib.lib()
+    gnorm = sample_l2norm(grad, workspace=workspace)
+    check(L.afan_pgd_l2_step_f32(f32(grad), f32(gnorm), f32(x_adv), n, per, float(gamma), float(tiny), stream()),
+          "afan_pgd_l2_step_f32")
+    if clip:
+        l2ball_proj_(x_clean, eps, x_adv, delta_out=delta_out, workspace=workspace)
+    elif delta_out is not None:
+        pgd_linf_step_(None, x_clean, x_adv, 0.0, 0.0, False, delta_out=delta_out)   # delta = x_adv - x only
+    return x_adv
+
+
+def l2ball_proj_(center, radius, t, *, delta_out=None, workspace=None):
+    """Classification/attack_algo.py:21-33 IN PLACE on t."""
+    n, per = _samples(t)
+    dist = sample_l2norm(t, center, workspace=workspace)
+    check(_lib.lib().afan_l2ball_proj_f32(f32(center), f32(dist), f32(t), f32(delta_out), n, per, float(radius),
+                                          stream()), "afan_l2ball_proj_f32")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# mix_feature (a8)
+# ------------------------------------------------------------------------------------------------
+def mix_feature(clean: torch.Tensor, adv: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if clean.shape != adv.shape or clean.dim() < 2:
+        raise AfanError("mix_feature needs two [N, C, ...] tensors of the same shape")
+    out = torch.empty_like(clean) if out is None else out
+    n, c = clean.shape[0], clean.shape[1]
+    hw = clean.numel() // max(n * c, 1)
+    check(_lib.lib().afan_mix_feature_f32(f32(clean, "clean"), f32(adv, "adv"), f32(out, "out"), n, c, hw, stream()),
+          "afan_mix_feature_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# dual BatchNorm (a10)
+# ------------------------------------------------------------------------------------------------
+def bn_workspace(groups: int, channels: int, device) -> torch.Tensor:
+    nbytes = _lib.lib().afan_bn_workspace_bytes(int(groups), int(channels))
+    if nbytes < 0:
+        check(int(nbytes), "afan_bn_workspace_bytes")
+    return torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
+
+
+def _nchw(x: torch.Tensor, groups: int):
+    if x.dim() < 2:
+        raise AfanError("BatchNorm input must be [N, C, ...]")
+    gn, c = x.shape[0], x.shape[1]
+    if gn % groups:
+        raise AfanError(f"batch {gn} is not divisible into {groups} statistic groups")
+    return gn // groups, c, x.numel() // max(gn * c, 1)
+
+
+def _ws_bytes(ws):
+    return ws.numel() * ws.element_size()
+
+
+def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1, eps=1e-5, momentum=0.1,
+           relu=False, replay=1, process_group=None):
+    """Train-mode grouped-statistics BN (+residual, +ReLU).  Returns (y, save_mean[G,C], save_invstd[G,C]).
+    With a process group of size > 1 the per-(group, channel) sums are all-reduced over NCCL in ONE
+    message for all groups between the statistics kernel and the apply kernel."""
+    n, c, hw = _nchw(x, groups)
+    L = _lib.lib()
+    y = torch.empty_like(x)
+    save_mean = torch.empty((groups, c), dtype=torch.float32, device=x.device)
+    save_invstd = torch.empty_like(save_mean)
+    world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    if world == 1:
+        check(L.afan_bn_fwd_f32(f32(x), f32(residual), f32(weight), f32(bias), f32(running_mean), f32(running_var),
+                                f32(y), f32(save_mean), f32(save_invstd), ptr(ws), _ws_bytes(ws), groups, n, c, hw,
+                                float(eps), float(momentum), int(bool(relu)), int(replay), stream()), "afan_bn_fwd_f32")
+    else:
+        sums = torch.empty((groups, c, 2), dtype=torch.float64, device=x.device)
+        check(L.afan_bn_fwd_stats_f32(f32(x), ptr(sums), ptr(ws), _ws_bytes(ws), groups, n, c, hw, stream()),
+              "afan_bn_fwd_stats_f32")
+        torch.distributed.all_reduce(sums, group=process_group)
+        check(L.afan_bn_fwd_finalize_f32(ptr(sums), float(n * hw * world), f32(weight), f32(bias), f32(running_mean),
+                                         f32(running_var), f32(save_mean), f32(save_invstd), ptr(ws), _ws_bytes(ws),
+                                         groups, c, float(eps), float(momentum), int(replay), stream()),
+              "afan_bn_fwd_finalize_f32")
+        check(L.afan_bn_fwd_apply_f32(f32(x), f32(residual), f32(y), ptr(ws), _ws_bytes(ws), groups, n, c, hw,
+                                      int(bool(relu)), stream()), "afan_bn_fwd_apply_f32")
+    return y, save_mean, save_invstd
+
+
+def bn_bwd(dy, x, y, weight, save_mean, save_invstd, ws, *, groups=1, relu=False, want_dresidual=False,
+           process_group=None):
+    """Backward of bn_fwd.  Returns (dx, dresidual|None, dweight[C], dbias[C]) (dweight/dbias are LOCAL sums;
+    the data-parallel gradient all-reduce averages them with the other parameters)."""
+    n, c, hw = _nchw(x, groups)
+    L = _lib.lib()
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dresidual else None
+    dweight = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbias = torch.empty_like(dweight)
+    world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    if world == 1:
+        check(L.afan_bn_bwd_f32(f32(dy), f32(x), f32(y) if relu else None, f32(weight), f32(save_mean),
+                                f32(save_invstd), f32(dx), f32(dres), f32(dweight), f32(dbias), ptr(ws), _ws_bytes(ws),
+                                groups, n, c, hw, int(bool(relu)), stream()), "afan_bn_bwd_f32")
+    else:
+        sums = torch.empty((groups, c, 2), dtype=torch.float64, device=x.device)
+        check(L.afan_bn_bwd_reduce_f32(f32(dy), f32(x), f32(y) if relu else None, f32(save_mean), f32(save_invstd),
+                                       ptr(sums), f32(dweight), f32(dbias), ptr(ws), _ws_bytes(ws), groups, n, c, hw,
+                                       int(bool(relu)), stream()), "afan_bn_bwd_reduce_f32")
+        torch.distributed.all_reduce(sums, group=process_group)
+        check(L.afan_bn_bwd_finalize_f32(ptr(sums), float(n * hw * world), f32(weight), f32(save_mean),
+                                         f32(save_invstd), ptr(ws), _ws_bytes(ws), groups, c, stream()),
+              "afan_bn_bwd_finalize_f32")
+        check(L.afan_bn_bwd_apply_f32(f32(dy), f32(x), f32(y) if relu else None, f32(dx), f32(dres), ptr(ws),
+                                      _ws_bytes(ws), groups, n, c, hw, int(bool(relu)), stream()),
+              "afan_bn_bwd_apply_f32")
+    return dx, dres, dweight, dbias
+
+
+def bn_affine(x, residual, scale_shift, *, relu=False):
+    """Inference-mode BN: y = relu?(x*scale[c] + shift[c] (+residual)); scale_shift float32 [C, 2]."""
+    n, c, hw = _nchw(x, 1)
+    y = torch.empty_like(x)
+    check(_lib.lib().afan_bn_affine_f32(f32(x), f32(residual), f32(scale_shift), f32(y), n, c, hw, int(bool(relu)),
+                                        stream()), "afan_bn_affine_f32")
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# fused SGD (a7 tail)
+# ------------------------------------------------------------------------------------------------
+def sgd_momentum_(param, grad, buf, lr_device, *, momentum=0.9, weight_decay=5e-4, grad_scale=1.0):
+    if not (param.numel() == grad.numel() == buf.numel()):
+        raise AfanError("param / grad / momentum buffer sizes differ")
+    check(_lib.lib().afan_sgd_momentum_f32(f32(param), f32(grad), f32(buf), param.numel(), f32(lr_device),
+                                           float(momentum), float(weight_decay), float(grad_scale), stream()),
+          "afan_sgd_momentum_f32")
+    return param

@@ -1,0 +1,108 @@
+"""Splittable CIFAR ResNet for A-FAN, built on the fused dual-BN kernels.
+
+Interface parity with the reference's Classification/resnet_s.py:79-124: the network is ONE
+`nn.Sequential` (`sequential_model`) so `model(x, end_point=k, start_point=j)` runs layers [j, k)
+(head = [0, k), tail = [k, L)); index layout, parameter / buffer names and the learnable `w` vector
+match, so reference checkpoints load with `load_state_dict`.  Differences are internal: every
+BatchNorm (+ the ReLU / residual add that follows it, resnet_s.py:70-76) is ONE fused kernel pair, and
+forward takes two extra keyword arguments threaded to the BN layers:
+    groups  statistic groups along the batch ([adv; clean] -> 2), see dual_bn.DualBatchNorm2d
+    replay  how many times the running statistics are advanced (head cache: 2, main_perturb.py:173,196)
+"""
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .dual_bn import DualBatchNorm2d
+
+CIFAR_MEAN = (0.4914, 0.4822, 0.4465)
+CIFAR_STD = (0.2470, 0.2435, 0.2616)
+
+
+class NormalizeByChannelMeanStd(nn.Module):
+    """Input normalisation layer 0 of the Sequential (advertorch's module in the reference, resnet_s.py:87)."""
+
+    def __init__(self, mean: Sequence[float], std: Sequence[float]):
+        super().__init__()
+        self.register_buffer("mean", torch.tensor(mean, dtype=torch.float32))
+        self.register_buffer("std", torch.tensor(std, dtype=torch.float32))
+
+    def forward(self, x):
+        return (x - self.mean[None, :, None, None]) / self.std[None, :, None, None]
+
+
+class BasicBlock(nn.Module):
+    """conv-bn-relu-conv-bn-(+shortcut)-relu with option-A shortcut (resnet_s.py:45-77).  bn1+relu and
+    bn2+add+relu are each one fused dual-BN call."""
+    expansion = 1
+
+    def __init__(self, in_planes: int, planes: int, stride: int = 1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride, 1, bias=False)
+        self.bn1 = DualBatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = DualBatchNorm2d(planes)
+        self.shortcut = nn.Sequential()            # keeps the (parameter-free) child name of the reference
+        self.downsample = stride != 1 or in_planes != planes
+        self.pad = planes // 4
+
+    def _shortcut(self, x):
+        if not self.downsample:
+            return x
+        return F.pad(x[:, :, ::2, ::2], (0, 0, 0, 0, self.pad, self.pad), "constant", 0.0)
+
+    def forward(self, x, groups: int = 1, replay: int = 1):
+        h = self.bn1(self.conv1(x), relu=True, groups=groups, replay=replay)
+        return self.bn2(self.conv2(h), residual=self._shortcut(x), relu=True, groups=groups, replay=replay)
+
+
+class ResNet(nn.Module):
+    def __init__(self, block=BasicBlock, num_blocks=(9, 9, 9), num_classes: int = 10, init_weight: float = 1.0):
+        super().__init__()
+        layers = [NormalizeByChannelMeanStd(CIFAR_MEAN, CIFAR_STD),
+                  nn.Conv2d(3, 16, 3, 1, 1, bias=False), DualBatchNorm2d(16), nn.ReLU()]
+        in_planes = 16
+        for planes, stride, depth in zip((16, 32, 64), (1, 2, 2), num_blocks):
+            for i in range(depth):
+                layers.append(block(in_planes, planes, stride if i == 0 else 1))
+                in_planes = planes * block.expansion
+        layers += [nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten(), nn.Linear(64, num_classes)]
+        self.sequential_model = nn.Sequential(*layers)
+        self.all_layers = 9
+        self.w = nn.Parameter(torch.full((self.all_layers,), float(init_weight)))
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.kaiming_normal_(m.weight)
+
+    @property
+    def layer_number(self) -> int:
+        return len(self.sequential_model)
+
+    def forward(self, x, end_point: Optional[int] = None, start_point: int = 0, groups: int = 1, replay: int = 1):
+        layers = self.sequential_model
+        end_point = len(layers) if end_point is None else min(end_point, len(layers))
+        i = start_point
+        while i < end_point:
+            m = layers[i]
+            if isinstance(m, DualBatchNorm2d):
+                fuse = i + 1 < end_point and isinstance(layers[i + 1], nn.ReLU)     # stem bn + relu in one kernel pair
+                x = m(x, relu=fuse, groups=groups, replay=replay)
+                i += 2 if fuse else 1
+                continue
+            x = m(x, groups=groups, replay=replay) if isinstance(m, BasicBlock) else m(x)
+            i += 1
+        return x
+
+    def bn_layers(self):
+        return [m for m in self.modules() if isinstance(m, DualBatchNorm2d)]
+
+
+def resnet20(num_classes: int = 10, **kw):
+    return ResNet(BasicBlock, (3, 3, 3), num_classes, **kw)
+
+
+def resnet56(init_weight_eta: float = 1.0, num_classes: int = 10):
+    """Factory named like the reference's (resnet_s.py:123-124); num_classes=100 for CIFAR-100."""
+    return ResNet(BasicBlock, (9, 9, 9), num_classes, init_weight=init_weight_eta)

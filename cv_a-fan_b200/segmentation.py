@@ -1,0 +1,42 @@
+"""Drop-in for Segmentation/attack_algo.py's hot-path functions (DeepLabv3+ flavour).
+
+    PGD(x, image_batch, low_level_feat, criterion, y, model, steps, eps, gamma, idx, randinit, clip)
+                                                                  (Segmentation/attack_algo.py:40-59)
+    mix_feature(clean_feature, adv_feature)                       (:121-130)
+    get_sample_points(pointx, pointy, number)                     (:108-118)
+The model contract is the reference's dict API: model({'x','adv','out_idx','flag','low_level_feat'}).
+"""
+import torch
+
+from . import ops
+from .attack_algo import linfball_proj, l2ball_proj, pgd_loop  # noqa: F401  (same helpers as the reference file)
+from ._lib import AfanError
+
+
+def PGD(x, image_batch, low_level_feat, criterion, y=None, model=None, steps=3, eps=None, gamma=None, idx=1,
+        randinit=False, clip=False, **extras):
+    def tail_loss(x_adv):
+        inputs = {"x": image_batch, "adv": x_adv, "out_idx": idx, "flag": "tail", "low_level_feat": low_level_feat}
+        return criterion(model(inputs), y)
+
+    return pgd_loop(x, tail_loss, steps, gamma, eps, randinit, clip, **extras)
+
+
+def mix_feature(clean_feature, adv_feature):
+    """Channel-dim mean/std of clean swapped for those of adv, one fused kernel (forward only: the
+    reference applies it to detached / lerped features, main_aug_final.py:200-210)."""
+    if clean_feature.requires_grad or adv_feature.requires_grad:
+        clean_feature, adv_feature = clean_feature.detach(), adv_feature.detach()
+    if not clean_feature.is_cuda:
+        raise AfanError("mix_feature needs CUDA tensors: afan_b200 has no CPU path")
+    return ops.mix_feature(clean_feature.contiguous(), adv_feature.contiguous())
+
+
+def get_sample_points(pointx, pointy, number):
+    """[x, lerp(x, y, i/(number-1)) for i in 1..number-2, y] (SAT points on the clean->adv segment)."""
+    percent = 1.0 / (number - 1)
+    pts = [pointx]
+    for i in range(1, number - 1):
+        pts.append(torch.lerp(pointx, pointy, i * percent))
+    pts.append(pointy)
+    return pts

@@ -1,0 +1,231 @@
+"""A-FAN training step (Classification/main_perturb.py:173-201), re-designed for B200.
+
+Reference iteration (per batch):  head fwd -> PGD (steps x [tail fwd, dgrad, 13 elementwise launches,
+4 host syncs]) -> D2H of the whole perturbation for its norms -> adv tail fwd -> FULL clean fwd (head
+again) -> backward -> SGD.  Here:
+
+  * head cache      the head runs ONCE per batch; its output is reused (detached) as the PGD anchor and
+                    (with its graph) as the clean half of the final pass.  The head's BatchNorm running
+                    statistics are advanced twice (`replay=2`) because the reference forwards the head
+                    twice in train() mode.
+  * dual-BN tail    the final adversarial and clean tail passes run as ONE pass over [adv; clean] with
+                    per-half batch statistics (groups=2) -- same maths as the reference's two passes.
+  * fused PGD       one kernel per step (ascent + projection), per-sample ||delta|| norms fused into
+                    the last step (no D2H), tail parameters frozen during the ascent (dgrad only).
+  * flat arena      parameters / gradients / momentum live in three flat buffers: ONE fused SGD kernel,
+                    ONE NCCL all-reduce of the gradient arena per iteration (weak-scaling data parallel).
+  * CUDA graph      the whole iteration (forward, ascent loop, backward, all-reduce, SGD) is captured
+                    once and replayed: ~3000 launches per iteration cost no Python/launch latency.
+"""
+import contextlib
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, attack_algo, ops
+from ._lib import AfanError
+from .dual_bn import DualBatchNorm2d
+
+
+class AfanTrainer:
+    def __init__(self, model: nn.Module, *, perturb_idx: int = 13, steps: int = 5, gamma: float = 1.5,
+                 eps: float = 2.0, randinit: bool = False, clip: bool = False, lr: float = 0.1,
+                 momentum: float = 0.9, weight_decay: float = 5e-4, norm: str = "linf", rng: str = "philox",
+                 seed: int = 0, criterion: Optional[nn.Module] = None, process_group=None, sync_bn: bool = True,
+                 head_cache: bool = True, use_cuda_graph: bool = True):
+        """gamma / eps are in 1/255 units like the reference flags (main_perturb.py:180,183)."""
+        self.model, self.k, self.L = model, int(perturb_idx), len(model.sequential_model)
+        self.steps, self.gamma, self.eps = int(steps), gamma / 255.0, eps / 255.0
+        self.randinit, self.clip, self.norm, self.rng, self.seed = randinit, clip, norm, rng, int(seed)
+        self.momentum, self.weight_decay = momentum, weight_decay
+        self.criterion = criterion if criterion is not None else nn.CrossEntropyLoss()
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.head_cache, self.use_graph = head_cache, use_cuda_graph
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise AfanError("AfanTrainer needs the model on a CUDA device: there is no CPU path")
+        if sync_bn and self.world > 1:
+            for m in model.modules():
+                if isinstance(m, DualBatchNorm2d):
+                    m.process_group = process_group
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
+        self._lr = float(lr)
+        self.rng_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._arena_built = False
+        self._graph = None
+        self._static = {}
+        self._bn = [m for m in model.modules() if isinstance(m, DualBatchNorm2d)]
+        self._bn_per_iter = None
+        self.iterations = 0
+        self.kernel_launches_per_iter = None       # afan kernels per iteration (counted at trace time)
+
+    # ---- learning rate lives on the device so a captured graph follows the schedule --------------
+    def set_lr(self, lr: float):
+        if lr != self._lr:
+            self.lr_dev.fill_(float(lr))
+            self._lr = float(lr)
+
+    # ---- flat parameter arena -------------------------------------------------------------------
+    def _build_arena(self, used):
+        n = sum(p.numel() for p in used)
+        pad = (-n) % 4
+        self.flat_param = torch.zeros(n + pad, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros_like(self.flat_param)
+        self.flat_buf = torch.zeros_like(self.flat_param)
+        off = 0
+        for p in used:
+            k = p.numel()
+            self.flat_param[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + k].view_as(p.data)
+            p.grad = self.flat_grad[off:off + k].view_as(p.data)
+            off += k
+        self._params = used
+        self._arena_built = True
+
+    @contextlib.contextmanager
+    def _params_frozen(self):
+        """During the ascent only d(loss)/d(x_adv) is needed (attack_algo.py:52 `only_inputs=True`):
+        freezing the parameters makes every tail layer skip its weight gradient."""
+        ps = [p for p in self.model.parameters() if p.requires_grad]
+        for p in ps:
+            p.requires_grad_(False)
+        try:
+            yield
+        finally:
+            for p in ps:
+                p.requires_grad_(True)
+
+    # ---- one iteration (eager; also the body that gets captured) ----------------------------------
+    def _iteration(self, images, target, noise, norms_out, ws):
+        model, k, L, n = self.model, self.k, self.L, images.shape[0]
+        if self.head_cache and k > 0:
+            feat = model(images, end_point=k, start_point=0, replay=2)
+        elif k > 0:
+            with torch.no_grad():
+                feat = model(images, end_point=k, start_point=0)                    # main_perturb.py:173
+        else:
+            feat = images
+        anchor = feat.detach()
+        extras = dict(norms_out=norms_out, workspace=ws, norm=self.norm)
+        if self.randinit:
+            if noise is not None:
+                extras["noise"] = noise
+            else:
+                extras.update(rng=self.rng, seed=self.seed, offset_device=self.rng_offset)
+        with self._params_frozen():
+            x_adv = attack_algo.PGD(anchor, self.criterion, y=target, model=model, steps=self.steps,
+                                    gamma=self.gamma, start_idx=k, layer_number=L, eps=self.eps,
+                                    randinit=self.randinit, clip=self.clip, **extras)        # :176-185
+        if self.randinit and noise is None and self.rng == "philox":
+            self.rng_offset += (anchor.numel() + 3) // 4
+        if self.head_cache:
+            both = torch.cat([x_adv.detach(), feat], dim=0)
+            logits = model(both, end_point=L, start_point=k, groups=2)                  # :195 + :196 in one pass
+            out_adv, out_clean = logits[:n], logits[n:]
+        else:
+            out_adv = model(x_adv.detach(), end_point=L, start_point=k)                 # :195
+            out_clean = model(images, end_point=L, start_point=0)                       # :196
+        loss = (self.criterion(out_adv, target) + self.criterion(out_clean, target)) / 2     # :197
+        return loss, out_clean
+
+    def _optimize(self, loss):
+        self.flat_grad.zero_()                                                       # :199
+        loss.backward()                                                              # :200
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad, group=self.pg)              # one NCCL message / iteration
+        ops.sgd_momentum_(self.flat_param, self.flat_grad, self.flat_buf, self.lr_dev, momentum=self.momentum,
+                          weight_decay=self.weight_decay, grad_scale=1.0 / self.world)        # :201
+
+    def _discover_arena(self, images, target, noise, norms_out, ws):
+        """First iteration: find the parameters that actually receive gradients (torch.optim.SGD skips
+        parameters whose .grad is None, e.g. the unused `w` of resnet_s.py:113) and build the arena from
+        them, without touching any state (BN statistics are restored)."""
+        snap = self._snapshot()
+        for p in self.model.parameters():
+            p.grad = None
+        loss, _ = self._iteration(images, target, noise, norms_out, ws)
+        loss.backward()
+        used = [p for p in self.model.parameters() if p.grad is not None]
+        self._restore(snap)
+        self._build_arena(used)
+
+    # ---- state snapshot (graph warm-up must not leak into training state) -------------------------
+    def _snapshot(self):
+        s = {"bn": [(m.running_mean.clone(), m.running_var.clone(), m.num_batches_tracked.clone(), m._pending_batches)
+                    for m in self._bn], "rng": self.rng_offset.clone()}
+        if self._arena_built:
+            s["param"], s["buf"] = self.flat_param.clone(), self.flat_buf.clone()
+        return s
+
+    def _restore(self, s):
+        for m, (rm, rv, nbt, pend) in zip(self._bn, s["bn"]):
+            m.running_mean.copy_(rm); m.running_var.copy_(rv); m.num_batches_tracked.copy_(nbt)
+            m._pending_batches = pend
+        self.rng_offset.copy_(s["rng"])
+        if "param" in s:
+            self.flat_param.copy_(s["param"]); self.flat_buf.copy_(s["buf"])
+
+    # ---- public step --------------------------------------------------------------------------------
+    def step(self, images: torch.Tensor, target: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        """One A-FAN training iteration on device tensors.  Returns a dict of DEVICE tensors
+        {loss, output_clean, l2, linf}: nothing is synchronised or copied to the host."""
+        self.model.train()
+        n = images.shape[0]
+        if not self._static:
+            self._static = {"norms": torch.zeros(2, n, dtype=torch.float32, device=self.device),
+                            "ws": ops.norms_workspace(n, self.device)}
+        st = self._static
+        if not self._arena_built:
+            self._discover_arena(images, target, noise, st["norms"], st["ws"])
+        if not self.use_graph:
+            l0 = _lib.launch_count
+            loss, out_clean = self._iteration(images, target, noise, st["norms"], st["ws"])
+            self._optimize(loss)
+            self.kernel_launches_per_iter = _lib.launch_count - l0
+            self.iterations += 1
+            return {"loss": loss.detach(), "output_clean": out_clean.detach(), "l2": st["norms"][0], "linf": st["norms"][1]}
+        if self._graph is None:
+            self._capture(images, target, noise)
+        st["images"].copy_(images, non_blocking=True)
+        st["target"].copy_(target, non_blocking=True)
+        if noise is not None:
+            st["noise"].copy_(noise, non_blocking=True)
+        self._graph.replay()
+        for m, inc in zip(self._bn, self._bn_per_iter):
+            m._pending_batches += inc
+        self.iterations += 1
+        return {"loss": st["loss"], "output_clean": st["out_clean"], "l2": st["norms"][0], "linf": st["norms"][1]}
+
+    def _capture(self, images, target, noise):
+        st = self._static
+        st["images"], st["target"] = images.clone(), target.clone()
+        st["noise"] = noise.clone() if noise is not None else None
+        snap = self._snapshot()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                      # warm-up: cuDNN autotune, NCCL communicator, lazy module load
+                loss, _ = self._iteration(st["images"], st["target"], st["noise"], st["norms"], st["ws"])
+                self._optimize(loss)
+        torch.cuda.current_stream().wait_stream(side)
+        self._restore(snap)
+        pend0 = [m._pending_batches for m in self._bn]
+        self._graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count
+        with torch.cuda.graph(self._graph):
+            loss, out_clean = self._iteration(st["images"], st["target"], st["noise"], st["norms"], st["ws"])
+            self._optimize(loss)
+            st["loss"], st["out_clean"] = loss.detach(), out_clean.detach()
+        self.kernel_launches_per_iter = _lib.launch_count - l0      # afan kernels replayed per iteration
+        self._bn_per_iter = [m._pending_batches - p0 for m, p0 in zip(self._bn, pend0)]
+        for m, p0 in zip(self._bn, pend0):
+            m._pending_batches = p0                 # capture records launches, it does not run them
+
+    # ---- evaluation (main_perturb.py:227-262) ---------------------------------------------------------
+    @torch.no_grad()
+    def evaluate(self, images, target):
+        self.model.eval()
+        out = self.model(images, end_point=self.L, start_point=0)
+        return self.criterion(out, target), out

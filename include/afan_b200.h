@@ -1,0 +1,159 @@
+/* afan_b200.h -- C ABI of libafan_b200.so: hand-written sm_100a CUDA kernels for A-FAN's
+ * adversarial-feature inner loop (feature-space PGD + clean/adversarial normalisation).
+ *
+ * The reference (VITA-Group/CV_A-FAN) is pure Python/PyTorch and has NO FFI for this path; the
+ * "reference interface each entry point replaces" is therefore a span of un-fused ATen calls in the
+ * reference's Python, cited per function as file:line relative to the reference root.  The binding a
+ * maintainer would add to the reference (a ctypes stub) is shown in INTEGRATION.md.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers + sizes; no torch / C++ types.  All data pointers are DEVICE pointers to
+ *     caller-owned, contiguous NCHW fp32 storage unless stated; nothing is allocated or retained.
+ *   - `stream` is a cudaStream_t (0 = legacy default stream).  Every call is asynchronous: it only
+ *     enqueues kernels on `stream`, never synchronises, and is CUDA-graph capturable.
+ *   - returns AFAN_OK (0) or a negative AFAN_ERR_* code; never throws, exits or prints.
+ *   - re-entrant: no global mutable state.  16-byte aligned pointers with sizes that are multiples
+ *     of 4 elements take the 128-bit vector path; anything else takes a scalar path (same results).
+ *   - `workspace`: device scratch owned by the caller, at least *_workspace_bytes() bytes, zeroed
+ *     ONCE before first use (kernels leave it zeroed); one workspace per concurrently used stream.
+ */
+#ifndef AFAN_B200_H_
+#define AFAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* afan_stream_t; /* cudaStream_t */
+
+enum {
+    AFAN_OK = 0,
+    AFAN_ERR_NULL = -1,        /* a required pointer is NULL */
+    AFAN_ERR_SIZE = -2,        /* negative / inconsistent size */
+    AFAN_ERR_WORKSPACE = -3,   /* workspace missing or too small */
+    AFAN_ERR_LAUNCH = -4,      /* CUDA launch error (cudaPeekAtLastError) */
+    AFAN_ERR_UNSUPPORTED = -5  /* shape outside what the kernels handle */
+};
+
+/* Library identification / diagnostics. */
+const char* afan_version(void);
+const char* afan_strerror(int code);
+/* Fills SM count and compute capability of the current device; AFAN_ERR_UNSUPPORTED if not sm_100. */
+int afan_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- a2: random start ------------------------------------------------------------------------
+ * Replaces Classification/attack_algo.py:41-44 (== Segmentation/attack_algo.py:43-45,
+ * Detection/attack_algo.py:51-53):  x_adv = x + fl(fl(fl(2u) - 1) * eps).
+ * _noise: `u` is the caller's torch.rand draw (bitwise parity with the reference's CPU generator).
+ * _philox: u generated on the fly, Philox4x32-10, element i <- counter i/4 + offset, lane i%4,
+ *          u = (bits >> 8) * 2^-24 (no noise tensor in HBM: 8 B/elem instead of 12).
+ *          offset_device (nullable, device uint64): added to `offset` at run time, so a captured
+ *          CUDA graph draws fresh noise on every replay. */
+int afan_pgd_init_noise_f32(const float* x, const float* u, float* x_adv, int64_t n_elem, float eps,
+                            afan_stream_t stream);
+int afan_pgd_init_philox_f32(const float* x, float* x_adv, int64_t n_elem, float eps, uint64_t seed,
+                             uint64_t offset, const uint64_t* offset_device, afan_stream_t stream);
+
+/* ---- a3 + a4 (+ a11): one fused L-inf PGD update ------------------------------------------------
+ * Replaces Classification/attack_algo.py:53-56 incl. linfball_proj/tensor_clamp (:9-19,35-36)
+ * (== Segmentation/attack_algo.py:54-57, Detection/attack_algo.py:69-72), and optionally the
+ * perturbation-norm logging of Classification/main_perturb.py:188-192:
+ *     t = x_adv + fl(gamma) * sign(grad);  if clip: if (t < x-eps) t = x-eps; if (t > x+eps) t = x+eps
+ * x_adv is updated IN PLACE.  x_clean may be NULL iff !clip && !delta_out && !norms_out.
+ * grad == NULL: no ascent, projection (+ delta / norms) only == linfball_proj(x_clean, eps, x_adv).
+ * delta_out (nullable): receives fl(x_adv_new - x_clean).
+ * norms_out (nullable): [2][n_samples] -> per-sample ||delta||_2 then ||delta||_inf; needs workspace.
+ * Bitwise identical to the reference op sequence (sign(NaN) = sign(-0) = +0; NaN compares false). */
+int64_t afan_pgd_norms_workspace_bytes(int64_t n_samples);
+int afan_pgd_linf_step_f32(const float* grad, const float* x_clean, float* x_adv, float* delta_out,
+                           float* norms_out, void* workspace, int64_t workspace_bytes,
+                           int64_t n_samples, int64_t per_sample, float gamma, float eps, int clip,
+                           afan_stream_t stream);
+
+/* ---- a5 / a5b: L2 mode ---------------------------------------------------------------------------
+ * afan_sample_l2norm_f32: out_norm[s] = ||a_s - b_s||_2 (b nullable -> ||a_s||_2), deterministic
+ *   two-level reduction (replaces `.view(N,-1).norm(p=2, dim=1)`, Classification/attack_algo.py:28).
+ * afan_pgd_l2_step_f32:   x_adv += gamma / max(grad_norm[s], tiny) * grad   (L2-normalised ascent;
+ *   north-star item with NO reference implementation -- semantics defined in oracle/afan_oracle.c).
+ * afan_l2ball_proj_f32:   replaces l2ball_proj, Classification/attack_algo.py:21-33, given
+ *   dist[s] = ||t_s - center_s||_2:  d = t - c; d /= dist; d *= min(dist, radius); t = c + d
+ *   (t == center gives 0/0 = NaN exactly like the reference).  delta_out (nullable) receives d. */
+int afan_sample_l2norm_f32(const float* a, const float* b, float* out_norm, void* workspace,
+                           int64_t workspace_bytes, int64_t n_samples, int64_t per_sample,
+                           afan_stream_t stream);
+int afan_pgd_l2_step_f32(const float* grad, const float* grad_norm, float* x_adv, int64_t n_samples,
+                         int64_t per_sample, float gamma, float tiny, afan_stream_t stream);
+int afan_l2ball_proj_f32(const float* center, const float* dist, float* t, float* delta_out,
+                         int64_t n_samples, int64_t per_sample, float radius, afan_stream_t stream);
+
+/* ---- a8: mix_feature --------------------------------------------------------------------------
+ * Replaces Segmentation/attack_algo.py:121-130 == Detection/attack_algo.py:254-265: per (n,h,w),
+ * channel-dim mean / sqrt(unbiased var + 1e-5) of clean swapped for those of adv.
+ * clean/adv/out: [n][c][hw].  One sweep computes both statistics (Welford), a second (cache-hot)
+ * sweep writes out: 12 B/elem of HBM traffic. */
+int afan_mix_feature_f32(const float* clean, const float* adv, float* out, int64_t n, int64_t c,
+                         int64_t hw, afan_stream_t stream);
+
+/* ---- a10: dual (grouped-statistics) train-mode BatchNorm2d ---------------------------------------
+ * Replaces nn.BatchNorm2d (+ the F.relu / residual add that follow it) in the tail as seen by the
+ * adversarial and the clean batch, Classification/resnet_s.py:54,56,70-76,89 driven by
+ * main_perturb.py:195-196.  x: [groups*n][c][hw]; group g = samples [g*n, (g+1)*n) gets its OWN batch
+ * statistics, all groups share weight/bias and the running averages (updated group after group,
+ * `replay` times each: the head cache replays the reference's two head forwards, main_perturb.py:173,196).
+ *     y = relu?( weight * (x - mean_g) * invstd_g + bias  (+ residual) )
+ * Single-GPU entry points (stats + finalise in one kernel, apply in a second):                     */
+int64_t afan_bn_workspace_bytes(int64_t groups, int64_t channels);
+int afan_bn_fwd_f32(const float* x, const float* residual /*nullable*/, const float* weight,
+                    const float* bias, float* running_mean /*nullable*/, float* running_var /*nullable*/,
+                    float* y, float* save_mean /*[g][c]*/, float* save_invstd /*[g][c]*/,
+                    void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c,
+                    int64_t hw, float eps, float momentum, int relu, int replay, afan_stream_t stream);
+int afan_bn_bwd_f32(const float* dy, const float* x, const float* y /*required iff relu*/,
+                    const float* weight, const float* save_mean, const float* save_invstd, float* dx,
+                    float* dresidual /*nullable*/, float* dweight /*[c]*/, float* dbias /*[c]*/,
+                    void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c,
+                    int64_t hw, int relu, afan_stream_t stream);
+/* Multi-GPU (sync) split: the caller all-reduces `sums` (double [g][c][2]) over NCCL between the
+ * two halves -- ONE message carries the clean and the adversarial statistics.
+ *   fwd: sums = {sum x, sum x^2};  count = global elements per (group, channel) = n*hw*world
+ *   bwd: sums = {sum dy, sum dy*xhat}; dweight/dbias are written from the LOCAL sums by _reduce. */
+int afan_bn_fwd_stats_f32(const float* x, double* sums, void* workspace, int64_t workspace_bytes,
+                          int64_t groups, int64_t n, int64_t c, int64_t hw, afan_stream_t stream);
+int afan_bn_fwd_finalize_f32(const double* sums, double count, const float* weight, const float* bias,
+                             float* running_mean, float* running_var, float* save_mean,
+                             float* save_invstd, void* workspace, int64_t workspace_bytes,
+                             int64_t groups, int64_t c, float eps, float momentum, int replay,
+                             afan_stream_t stream);
+int afan_bn_fwd_apply_f32(const float* x, const float* residual, float* y, const void* workspace,
+                          int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c, int64_t hw,
+                          int relu, afan_stream_t stream);
+int afan_bn_bwd_reduce_f32(const float* dy, const float* x, const float* y, const float* save_mean,
+                           const float* save_invstd, double* sums, float* dweight, float* dbias,
+                           void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n,
+                           int64_t c, int64_t hw, int relu, afan_stream_t stream);
+int afan_bn_bwd_finalize_f32(const double* sums, double count, const float* weight,
+                             const float* save_mean, const float* save_invstd, void* workspace,
+                             int64_t workspace_bytes, int64_t groups, int64_t c, afan_stream_t stream);
+int afan_bn_bwd_apply_f32(const float* dy, const float* x, const float* y, float* dx, float* dresidual,
+                          const void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n,
+                          int64_t c, int64_t hw, int relu, afan_stream_t stream);
+/* Inference-mode affine (+residual, +relu) with a caller-supplied per-channel scale/shift table
+ * (float [c][2]); used for model.eval() (main_perturb.py:232-246). */
+int afan_bn_affine_f32(const float* x, const float* residual, const float* scale_shift, float* y,
+                       int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream);
+
+/* ---- a7 tail: fused SGD(momentum, weight decay) over a flat parameter arena ---------------------
+ * Replaces optimizer.step() of torch.optim.SGD, main_perturb.py:72-74,201:
+ *     g = grad*grad_scale + wd*p;  buf = momentum*buf + g;  p -= lr*buf      (buf starts at 0)
+ * lr is read from DEVICE memory so a captured CUDA graph follows the LR schedule (warm-up,
+ * main_perturb.py:167-168,288-293). */
+int afan_sgd_momentum_f32(float* param, const float* grad, float* momentum_buf, int64_t n_elem,
+                          const float* lr_device, float momentum, float weight_decay, float grad_scale,
+                          afan_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFAN_B200_H_ */

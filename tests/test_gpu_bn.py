@@ -1,0 +1,107 @@
+"""-m gpu: dual-BN forward/backward kernels vs the oracle and vs torch's own BatchNorm (the arithmetic
+the reference's nn.BatchNorm2d runs).  Tolerances: 1e-5 rel / 1e-5 abs fp32 (reduction order)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as orc
+from tests.util import PKG, dev
+
+pytestmark = pytest.mark.gpu
+ops = PKG.ops
+
+CASES = [  # groups, n, c, h, w
+    (1, 128, 16, 32, 32), (2, 128, 16, 32, 32), (2, 128, 32, 16, 16), (2, 128, 64, 8, 8),   # ResNet-56 tail, config 2
+    (1, 4, 2048, 33, 33), (2, 2, 256, 33, 33),                                              # DeepLab-shaped, odd HW -> scalar path
+    (1, 3, 5, 1, 1), (2, 1, 3, 2, 2), (1, 2, 1, 1, 7), (4, 2, 6, 4, 4)]
+
+
+def run_case(groups, n, c, h, w, relu, residual, replay=1, offset=0.0):
+    g = torch.Generator().manual_seed(groups * 1000 + c + h)
+    x = torch.randn(groups * n, c, h, w, generator=g) * 1.7 + 0.3 + offset
+    res = torch.randn(x.shape, generator=g) if residual else None
+    wt, b = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    rm, rv = torch.randn(c, generator=g) * 0.1, torch.rand(c, generator=g) + 0.5
+    dy = torch.randn(x.shape, generator=g)
+    d = dev()
+    rm_d, rv_d = rm.to(d), rv.to(d)
+    ws = ops.bn_workspace(groups, c, d)
+    y, sm, si = ops.bn_fwd(x.to(d), res.to(d) if residual else None, wt.to(d), b.to(d), rm_d, rv_d, ws,
+                           groups=groups, relu=relu, replay=replay)
+    dx, dres, dw, db = ops.bn_bwd(dy.to(d), x.to(d), y, wt.to(d), sm, si, ws, groups=groups, relu=relu,
+                                  want_dresidual=residual)
+    rm_o, rv_o = rm.numpy().copy(), rv.numpy().copy()
+    y_o, sm_o, si_o = orc.bn_fwd(x.numpy(), wt.numpy(), b.numpy(), rm_o, rv_o, groups=groups,
+                                 residual=res.numpy() if residual else None, relu=relu, replay=replay)
+    dx_o, dres_o, dw_o, db_o = orc.bn_bwd(dy.numpy(), x.numpy(), y_o, wt.numpy(), sm_o, si_o, groups=groups,
+                                          relu=relu, residual=residual)
+    tol = dict(rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(y.cpu().numpy(), y_o, **tol)
+    np.testing.assert_allclose(sm.cpu().numpy(), sm_o, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(si.cpu().numpy(), si_o, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rm_d.cpu().numpy(), rm_o, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rv_d.cpu().numpy(), rv_o, rtol=1e-5, atol=1e-6)
+    scale = max(1.0, float(np.abs(dx_o).max()))
+    np.testing.assert_allclose(dx.cpu().numpy(), dx_o, rtol=1e-4, atol=2e-5 * scale)
+    cnt = n * h * w
+    np.testing.assert_allclose(dw.cpu().numpy(), dw_o, rtol=1e-4, atol=1e-5 * cnt ** 0.5 * groups)
+    np.testing.assert_allclose(db.cpu().numpy(), db_o, rtol=1e-4, atol=1e-5 * cnt ** 0.5 * groups)
+    if residual:
+        # dresidual = dy masked by the ReLU of OUR y; elements whose pre-activation is within rounding of 0 may flip
+        mism = dres.cpu().numpy() != dres_o
+        assert mism.mean() < 1e-4
+    assert int(ws.view(torch.int32)[:c].abs().sum()) == 0          # last-CTA counters are left zeroed
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("relu,residual", [(False, False), (True, False), (True, True)])
+def test_bn_fwd_bwd_vs_oracle(case, relu, residual):
+    run_case(*case, relu=relu, residual=residual)
+
+
+def test_replay_and_large_mean():
+    run_case(2, 16, 8, 8, 8, relu=True, residual=False, replay=2)
+    run_case(1, 64, 16, 16, 16, relu=False, residual=False, offset=10.0)    # |mean| >> std: E[x^2]-E[x]^2 stays accurate
+
+
+def test_module_equals_two_reference_passes_through_nn_batchnorm():
+    """DualBatchNorm2d(groups=2) on [adv; clean] == nn.BatchNorm2d applied to adv, then to clean
+    (main_perturb.py:195-196), forward, backward, running stats and num_batches_tracked."""
+    g = torch.Generator().manual_seed(5)
+    n, c = 16, 32
+    adv, clean = torch.randn(n, c, 8, 8, generator=g), torch.randn(n, c, 8, 8, generator=g) + 0.2
+    ref = torch.nn.BatchNorm2d(c)
+    ref.weight.data = torch.rand(c, generator=g) + 0.5
+    ref.bias.data = torch.randn(c, generator=g)
+    mod = PKG.dual_bn.DualBatchNorm2d(c)
+    mod.load_state_dict(ref.state_dict())
+    mod.to(dev())
+    a_r, c_r = adv.clone().requires_grad_(True), clean.clone().requires_grad_(True)
+    out_ref = torch.cat([F.relu(ref(a_r)), F.relu(ref(c_r))])
+    dy = torch.randn(out_ref.shape, generator=g)
+    out_ref.backward(dy)
+    both = torch.cat([adv, clean]).to(dev()).requires_grad_(True)
+    out = mod(both, relu=True, groups=2)
+    out.backward(dy.to(dev()))
+    torch.testing.assert_close(out.detach().cpu(), out_ref.detach(), rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(both.grad.cpu(), torch.cat([a_r.grad, c_r.grad]), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(mod.weight.grad.cpu(), ref.weight.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(mod.bias.grad.cpu(), ref.bias.grad, rtol=1e-4, atol=1e-4)
+    sd = mod.state_dict()
+    torch.testing.assert_close(sd["running_mean"].cpu(), ref.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sd["running_var"].cpu(), ref.running_var, rtol=1e-5, atol=1e-6)
+    assert int(sd["num_batches_tracked"]) == int(ref.num_batches_tracked) == 2
+    # eval mode uses the running statistics through the affine kernel
+    ref.eval(); mod.eval()
+    xe = torch.randn(4, c, 8, 8, generator=g)
+    torch.testing.assert_close(mod(xe.to(dev())).cpu(), ref(xe), rtol=2e-5, atol=2e-5)
+
+
+def test_bn_rejects_bad_inputs():
+    d = dev()
+    with pytest.raises(PKG.AfanError):
+        ops.bn_fwd(torch.zeros(3, 4, 2, 2, device=d), None, None, None, None, None, ops.bn_workspace(2, 4, d), groups=2)
+    with pytest.raises(PKG.AfanError):      # workspace too small
+        ops.bn_fwd(torch.zeros(4, 4, 2, 2, device=d), None, None, None, None, None,
+                   torch.zeros(2, dtype=torch.int64, device=d), groups=2)

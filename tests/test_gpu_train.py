@@ -1,0 +1,101 @@
+"""-m gpu: the whole A-FAN training iteration vs goldens produced by the unmodified reference
+`main_perturb.train` (oracle/gen_golden.py) and vs the CPU torch port, in all trainer modes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import afan_ref_torch as ref_t
+from tests.util import GOLDEN, PKG, dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def strict_fp32():
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+MODES = {"faithful": dict(head_cache=False, use_cuda_graph=False),
+         "head_cache": dict(head_cache=True, use_cuda_graph=False),
+         "graph": dict(head_cache=True, use_cuda_graph=True)}
+
+
+@pytest.mark.parametrize("name", ["cls_train_randclip", "cls_train_shipped", "cls_train_warmup"])
+@pytest.mark.parametrize("mode", list(MODES))
+def test_training_matches_reference_golden(name, mode):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    pidx, steps, gamma, eps, randinit, clip, bs, iters, epoch = z["meta"]
+    model = PKG.resnet_s.ResNet(num_blocks=tuple(int(v) for v in z["num_blocks"]), num_classes=int(z["num_classes"]))
+    model.load_state_dict({k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("init/")})
+    model.to(dev())
+    tr = PKG.trainer.AfanTrainer(model, perturb_idx=int(pidx), steps=int(steps), gamma=float(gamma), eps=float(eps),
+                                 randinit=bool(randinit), clip=bool(clip), lr=0.1, **MODES[mode])
+    iters = int(iters)
+    for i in range(iters):
+        if int(epoch) == 0:
+            tr.set_lr(min(i * 0.1 / (iters - 1), 0.1))                    # main_perturb.py:288-293
+        noise = torch.from_numpy(z["noises"][i]).to(dev()) if bool(randinit) else None
+        out = tr.step(torch.from_numpy(z["images"][i]).to(dev()), torch.from_numpy(z["targets"][i]).to(dev()), noise)
+        ce_adv, ce_clean = z["ce_values"][i][-2:]
+        assert abs(float(out["loss"]) - (ce_adv + ce_clean) / 2) < 2e-3 * (ce_adv + ce_clean) / 2, (i, mode)
+        assert float(out["linf"].max()) <= float(z["linf_mean"]) * 1.5 + 1e-6
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for k in z.files:
+        if not k.startswith("final/"):
+            continue
+        ref, got = z[k], sd[k[6:]]
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(ref), k
+        elif k.endswith(("running_mean", "running_var")) and mode != "faithful":
+            # head cache: (1-m)^2 r + m(2-m) s replay of the double head forward -> same value up to rounding
+            np.testing.assert_allclose(got.numpy(), ref, rtol=1e-3, atol=1e-4, err_msg=k)
+        else:
+            np.testing.assert_allclose(got.numpy(), ref, rtol=5e-3, atol=2e-4, err_msg=k)
+
+
+def test_graph_and_eager_agree_and_unused_w_is_untouched():
+    torch.manual_seed(3)
+    g = torch.Generator().manual_seed(4)
+    imgs = [torch.rand(8, 3, 32, 32, generator=g) for _ in range(3)]
+    tgts = [torch.randint(0, 10, (8,), generator=g) for _ in range(3)]
+    results = []
+    for graph in (False, True):
+        torch.manual_seed(3)
+        model = PKG.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev())
+        tr = PKG.trainer.AfanTrainer(model, perturb_idx=5, steps=2, gamma=1.0, eps=2.0, randinit=True, clip=True,
+                                     rng="philox", seed=9, use_cuda_graph=graph)
+        losses = [float(tr.step(i.to(dev()), t.to(dev()))["loss"]) for i, t in zip(imgs, tgts)]
+        results.append((losses, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}))
+        assert torch.equal(model.w.detach().cpu(), torch.ones(9))          # SGD skips grad-less params (resnet_s.py:113)
+    (l0, s0), (l1, s1) = results
+    np.testing.assert_allclose(l0, l1, rtol=1e-4)
+    for k in s0:
+        torch.testing.assert_close(s0[k].float(), s1[k].float(), rtol=1e-3, atol=1e-4, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_trainer_vs_cpu_port_resnet20_config1():
+    """BASELINE config 1 network (resnet_s [3,3,3]), small batch: GPU trainer vs oracle/afan_ref_torch.py."""
+    torch.manual_seed(3)
+    model = PKG.resnet_s.resnet20()
+    ref = ref_t.CifarResNetRef((3, 3, 3), 10)
+    ref.load_state_dict(model.state_dict())
+    model.to(dev())
+    g = torch.Generator().manual_seed(8)
+    tr = PKG.trainer.AfanTrainer(model, perturb_idx=10, steps=3, gamma=1.0, eps=2.0, randinit=True, clip=True)
+    opt, crit = ref_t.make_sgd(ref), torch.nn.CrossEntropyLoss()
+    ref.train()
+    for _ in range(2):
+        x, y = torch.rand(16, 3, 32, 32, generator=g), torch.randint(0, 10, (16,), generator=g)
+        noise = torch.rand(16, 32, 16, 16, generator=g)          # layers [0,10) of [3,3,3] end after stage 2
+        out = tr.step(x.to(dev()), y.to(dev()), noise.to(dev()))
+        loss_ref, _, l2, linf, _ = ref_t.afan_train_iteration(ref, opt, crit, x, y, steps=3, gamma=1.0, eps=2.0,
+                                                              perturb_idx=10, randinit=True, clip=True, noise=noise)
+        assert abs(float(out["loss"]) - float(loss_ref)) < 2e-3 * float(loss_ref)
+        np.testing.assert_allclose(out["l2"].cpu().numpy(), l2.numpy(), rtol=2e-2)
+        np.testing.assert_allclose(out["linf"].cpu().numpy(), linf.numpy(), rtol=1e-4)
