@@ -145,94 +145,126 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
-# kernel rooflines: cold-L2 micro-benchmarks of the hand-written kernels at the workload's shapes
+# kernel rooflines: the hand-written kernels at the workload's shapes, L2-cold
 # ---------------------------------------------------------------------------------------------------
-def kernel_rooflines(pkg, dev, reps=20):
+L2_BYTES = 126 * 1024 * 1024
+
+
+def kernel_rooflines(pkg, dev, reps=10):
+    """Per-launch device time of each hand-written kernel with an L2-cold working set.
+
+    Method ("inputs larger than L2"): every kernel gets R independent tensor sets with R x bytes >= 4 x L2;
+    one CUDA graph launches the kernel once per set back to back, the graph is replayed `reps` times between
+    two CUDA events on the launching stream, and the per-launch time is total / (R x reps).  Each launch
+    therefore finds none of its inputs in L2 and no CPU launch latency is in the number; inter-kernel gaps
+    are (they are real cost in the training step as well).  `us_isolated` is the classic single launch
+    between two events after a 256 MB L2-flush memset (includes event/launch ramp, shown for context)."""
     ops = pkg.ops
+    L = pkg._lib.lib()
+    st = pkg._lib.stream
     peak, peak_src = peaks()
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev).manual_seed(3)
-
-    def timed(fn, cold=True):
-        ts = []
-        for i in range(reps + 3):
-            if cold:
-                flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            fn()
-            e.record()
-            e.synchronize()
-            if i >= 3:
-                ts.append(s.elapsed_time(e) * 1e-3)
-        return sum(ts) / len(ts)
-
+    side = torch.cuda.Stream(device=dev)
     res = []
 
-    def add(name, bytes_per_launch, fn, launches_per_iter, note):
-        t_cold, t_warm = timed(fn, True), timed(fn, False)
-        res.append({"kernel": name, "bytes": bytes_per_launch, "us_cold": t_cold * 1e6, "us_warm": t_warm * 1e6,
-                    "achieved": bytes_per_launch / t_cold / 1e9, "achieved_warm_l2": bytes_per_launch / t_warm / 1e9,
-                    "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / t_cold / 1e9 / peak,
+    def measure(name, bytes_per_launch, footprint, make_set, run, launches_per_iter, note):
+        R = max(2, min(64, -(-4 * L2_BYTES // footprint)))
+        sets = [make_set() for _ in range(R)]
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for sset in sets:
+                run(sset)                               # warm-up (lazy module load) outside capture
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for sset in sets:
+                run(sset)
+        for _ in range(3):
+            graph.replay()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(reps):
+            graph.replay()
+        e.record()
+        e.synchronize()
+        t = s.elapsed_time(e) * 1e-3 / (R * reps)
+        iso = []
+        for i in range(8):
+            flush.zero_()
+            s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s2.record()
+            run(sets[i % R])
+            e2.record()
+            e2.synchronize()
+            if i >= 3:
+                iso.append(s2.elapsed_time(e2) * 1e-3)
+        res.append({"kernel": name, "bytes": bytes_per_launch, "us": t * 1e6, "us_isolated": 1e6 * sum(iso) / len(iso),
+                    "achieved": bytes_per_launch / t / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": bytes_per_launch / t / 1e9 / peak, "rotating_sets": R,
                     "launches_per_iter": launches_per_iter, "note": note})
+        del graph, sets
 
     w = WORKLOAD
     n = w["batch_per_gpu"]
-    # the perturbed feature map of the workload and an L2-exceeding one (FRCNN config 4, B=8: 8x1024x38x63)
+    gm, ep = w["gamma"] / 255, w["eps"] / 255
     for tag, shape in (("cfg2 128x16x32x32", (n, 16, 32, 32)), ("cfg4 8x1024x38x63", (8, 1024, 38, 63))):
         E = 1
-        for s in shape:
-            E *= s
-        x = torch.relu(1.5 * torch.randn(shape, device=dev, generator=g))
-        grad = 1e-3 * torch.randn(shape, device=dev, generator=g)
-        xa, delta = x.clone(), torch.empty_like(x)
-        norms, ws = torch.zeros(2, shape[0], device=dev), ops.norms_workspace(shape[0], dev)
-        gm, ep = w["gamma"] / 255, w["eps"] / 255
-        add(f"pgd_linf_step clip [{tag}]", 16 * E, lambda: ops.pgd_linf_step_(grad, x, xa, gm, ep, True),
-            w["steps"] - 1 if tag.startswith("cfg2") else 0, "read g,x_adv,x + write x_adv = 16 B/elem")
-        add(f"pgd_linf_step clip+delta+norms [{tag}]", 20 * E,
-            lambda: ops.pgd_linf_step_(grad, x, xa, gm, ep, True, delta_out=delta, norms_out=norms, workspace=ws),
-            0, "+ write delta = 20 B/elem, per-sample norms fused")
-        add(f"pgd_linf_step clip+norms [{tag}]", 16 * E,
-            lambda: ops.pgd_linf_step_(grad, x, xa, gm, ep, True, norms_out=norms, workspace=ws),
-            1 if tag.startswith("cfg2") else 0, "16 B/elem, per-sample norms fused (last PGD step of the trainer)")
-        add(f"pgd_linf_step noclip [{tag}]", 12 * E, lambda: ops.pgd_linf_step_(grad, None, xa, gm, ep, False), 0,
-            "shipped recipe (no clip): 12 B/elem")
-        add(f"pgd_init philox [{tag}]", 8 * E, lambda: ops.pgd_init(x, ep, seed=1, out=xa),
-            1 if tag.startswith("cfg2") else 0, "8 B/elem")
-        del x, grad, xa, delta
-    # dual BN at the tail shapes of the workload (stage 2/3 of ResNet-56) and one large shape
+        for d in shape:
+            E *= d
+        in_step = tag.startswith("cfg2")
+
+        def mk():
+            x = torch.relu(1.5 * torch.randn(shape, device=dev, generator=g))
+            return dict(x=x, g=1e-3 * torch.randn(shape, device=dev, generator=g), xa=x.clone(), d=torch.empty_like(x),
+                        nrm=torch.zeros(2, shape[0], device=dev), ws=ops.norms_workspace(shape[0], dev))
+        measure(f"pgd_linf_step clip [{tag}]", 16 * E, 12 * E, mk,
+                lambda t: ops.pgd_linf_step_(t["g"], t["x"], t["xa"], gm, ep, True), w["steps"] - 1 if in_step else 0,
+                "read g,x_adv,x + write x_adv = 16 B/elem")
+        measure(f"pgd_linf_step clip+norms [{tag}]", 16 * E, 12 * E, mk,
+                lambda t: ops.pgd_linf_step_(t["g"], t["x"], t["xa"], gm, ep, True, norms_out=t["nrm"], workspace=t["ws"]),
+                1 if in_step else 0, "16 B/elem, per-sample L2/Linf norms fused (last PGD step of the trainer)")
+        measure(f"pgd_linf_step clip+delta+norms [{tag}]", 20 * E, 16 * E, mk,
+                lambda t: ops.pgd_linf_step_(t["g"], t["x"], t["xa"], gm, ep, True, delta_out=t["d"], norms_out=t["nrm"],
+                                             workspace=t["ws"]), 0, "+ write delta = 20 B/elem")
+        measure(f"pgd_linf_step noclip [{tag}]", 12 * E, 8 * E, mk,
+                lambda t: ops.pgd_linf_step_(t["g"], None, t["xa"], gm, ep, False), 0, "shipped recipe (no clip): 12 B/elem")
+        measure(f"pgd_init philox [{tag}]", 8 * E, 8 * E, mk, lambda t: ops.pgd_init(t["x"], ep, seed=1, out=t["xa"]),
+                1 if in_step else 0, "read x + write x_adv = 8 B/elem, noise generated in registers")
     for tag, (G, N, C, H, W), lpi in (("G2 128x32x16x16", (2, n, 32, 16, 16), 18), ("G2 128x64x8x8", (2, n, 64, 8, 8), 18),
                                       ("G1 128x32x16x16", (1, n, 32, 16, 16), 18 * w["steps"]),
+                                      ("G1 128x64x8x8", (1, n, 64, 8, 8), 18 * w["steps"]),
                                       ("G1 128x16x32x32", (1, n, 16, 32, 32), 19),
-                                      ("G2 256x64x56x56 (L2-exceeding)", (2, 256, 64, 56, 56), 0)):
-        x = torch.randn(G * N, C, H, W, device=dev, generator=g)
-        dy = torch.randn(G * N, C, H, W, device=dev, generator=g)
-        wt, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-        rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
-        wsb = ops.bn_workspace(G, C, dev)
-        L = pkg._lib.lib()
-        y = torch.empty_like(x)
-        dx = torch.empty_like(x)
-        sm, si = torch.empty(G, C, device=dev), torch.empty(G, C, device=dev)
-        dw, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
-        E = x.numel()
-        st = pkg._lib.stream
-        nb = wsb.numel() * 8
+                                      ("G2 256x64x56x56", (2, 256, 64, 56, 56), 0)):
+        E = G * N * C * H * W
+        nb = L.afan_bn_workspace_bytes(G, C)
 
-        def fwd():
-            pkg._lib.check(L.afan_bn_fwd_f32(x.data_ptr(), None, wt.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(),
-                                             y.data_ptr(), sm.data_ptr(), si.data_ptr(), wsb.data_ptr(), nb, G, N, C, H * W,
-                                             1e-5, 0.1, 1, 1, st()), "afan_bn_fwd_f32")
+        def mk():
+            return dict(x=torch.randn(G * N, C, H, W, device=dev, generator=g), dy=torch.randn(G * N, C, H, W, device=dev, generator=g),
+                        y=torch.empty(G * N, C, H, W, device=dev), dx=torch.empty(G * N, C, H, W, device=dev),
+                        w=torch.ones(C, device=dev), b=torch.zeros(C, device=dev), rm=torch.zeros(C, device=dev),
+                        rv=torch.ones(C, device=dev), sm=torch.empty(G, C, device=dev), si=torch.empty(G, C, device=dev),
+                        dw=torch.empty(C, device=dev), db=torch.empty(C, device=dev), ws=ops.bn_workspace(G, C, dev))
 
-        def bwd():
-            pkg._lib.check(L.afan_bn_bwd_f32(dy.data_ptr(), x.data_ptr(), y.data_ptr(), wt.data_ptr(), sm.data_ptr(),
-                                             si.data_ptr(), dx.data_ptr(), None, dw.data_ptr(), db.data_ptr(),
-                                             wsb.data_ptr(), nb, G, N, C, H * W, 1, st()), "afan_bn_bwd_f32")
-        add(f"dual_bn fwd+relu [{tag}]", 8 * E, fwd, lpi, "read x + write y = 8 B/elem (16 B per clean+adv pair); 2 launches")
-        fwd()
-        add(f"dual_bn bwd+relu [{tag}]", 16 * E, bwd, lpi, "read dy,x,y + write dx = 16 B/elem (12 without the ReLU mask); 2 launches")
-        del x, dy, y, dx
+        def fwd(t):
+            pkg._lib.check(L.afan_bn_fwd_f32(t["x"].data_ptr(), None, t["w"].data_ptr(), t["b"].data_ptr(), t["rm"].data_ptr(),
+                                             t["rv"].data_ptr(), t["y"].data_ptr(), t["sm"].data_ptr(), t["si"].data_ptr(),
+                                             t["ws"].data_ptr(), nb, G, N, C, H * W, 1e-5, 0.1, 1, 1, st()), "afan_bn_fwd_f32")
+
+        def bwd(t):
+            pkg._lib.check(L.afan_bn_bwd_f32(t["dy"].data_ptr(), t["x"].data_ptr(), t["y"].data_ptr(), t["w"].data_ptr(),
+                                             t["sm"].data_ptr(), t["si"].data_ptr(), t["dx"].data_ptr(), None, t["dw"].data_ptr(),
+                                             t["db"].data_ptr(), t["ws"].data_ptr(), nb, G, N, C, H * W, 1, st()), "afan_bn_bwd_f32")
+
+        def mk_bwd():
+            t = mk()
+            fwd(t)
+            return t
+        measure(f"dual_bn fwd+relu [{tag}]", 8 * E, 8 * E, mk, fwd, lpi,
+                "read x + write y = 8 B/elem (16 B per clean+adv pair)")
+        measure(f"dual_bn bwd+relu [{tag}]", 16 * E, 16 * E, mk_bwd, bwd, lpi,
+                "read dy,x,y + write dx = 16 B/elem (12 without the ReLU mask)")
     return res, peak_src
 
 
@@ -247,6 +279,8 @@ def main():
     ap.add_argument("--no-sync-bn", action="store_true", help="per-replica BN statistics (the reference's DataParallel behaviour)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-rooflines", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager iteration between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -303,9 +337,21 @@ def main():
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms) / 1e3, clk.summary()
 
+    if args.profile_step:
+        eager = pkg.trainer.AfanTrainer(model, perturb_idx=w["perturb_idx"], steps=w["steps"], gamma=w["gamma"],
+                                        eps=w["eps"], randinit=w["randinit"], clip=w["clip"], rng="philox", seed=3,
+                                        use_cuda_graph=False)
+        for i in range(3):
+            eager.step(dev_x[i], dev_y[i])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        eager.step(dev_x[3], dev_y[3])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_step": True, "afan_kernels_per_step": eager.kernel_launches_per_iter}))
+        return
+
     # (1) device-resident inputs
-    lib = pkg._lib
-    l0 = lib.launch_count
     trainer.step(dev_x[0], dev_y[0])                         # builds arena, captures the graph
     out = {}
 
@@ -342,10 +388,11 @@ def main():
     if rank == 0 and not args.skip_rooflines:
         ks, peak_src = kernel_rooflines(pkg, dev)
         in_step = [k for k in ks if k["launches_per_iter"] > 0]
-        dom = max(in_step, key=lambda k: k["us_warm"] * k["launches_per_iter"])
+        dom = max(in_step, key=lambda k: k["us"] * k["launches_per_iter"])
         line["roofline"] = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
                             "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
-                            "timing": "CUDA events around one launch, L2 flushed (256 MB memset) before each"}
+                            "timing": "CUDA events around a graph of back-to-back launches over rotating tensor sets (4x L2), per-launch average",
+                            "share_of_step": dom["us"] * dom["launches_per_iter"] / (1e3 * sec / args.steps) / 1e3}
         line["kernels"] = ks
     if world > 1:
         torch.distributed.barrier()

@@ -16,9 +16,13 @@
 //   pass 2 (bn_apply_kernel): flat streaming sweep, y = relu(x*scale + shift (+res)).
 // HBM bytes per element: fwd 8 algorithmic (read x, write y); the second read of x in pass 2 hits
 // the 126 MB L2 for every shape in BASELINE.json's configs.  bwd: 12 algorithmic (+4 for y if relu).
+#include <cooperative_groups.h>
+
 #include <type_traits>
 
 #include "afan_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace afan {
 
@@ -324,6 +328,332 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParam
     }
 }
 
+
+// =====================================================================================================
+// Cluster path (the one every BASELINE config takes): ONE launch per BatchNorm direction.
+//
+// A thread-block cluster of CS CTAs owns one channel (all statistic groups).  Each CTA streams its slice
+// of every group's domain once from HBM (128-bit loads), reduces with warp shuffles + a shared-memory
+// tree, and publishes one double2 partial per group in its shared memory.  After a cluster barrier every
+// CTA pulls the CS partials of each group over DISTRIBUTED SHARED MEMORY in rank order (deterministic),
+// finalises mean / invstd (rank 0 also updates the running statistics in pass order), and sweeps its slice
+// a second time -- now an L2 hit, the slice was touched microseconds ago -- to normalise + affine
+// (+ residual) + ReLU.  HBM traffic is the algorithmic 8 B/elem (fwd) / 16 B/elem (bwd with ReLU mask);
+// no global-memory partials, no atomics, no second launch.
+// =====================================================================================================
+constexpr int kClusterThreads = 512;
+constexpr int kMaxGroups = 8;
+constexpr int kMaxCluster = 8;                     // portable cluster size on sm_100a
+
+struct ClusterParams {
+    const float* a;          // fwd: x            bwd: dy
+    const float* b;          // fwd: residual     bwd: x
+    const float* y;          // bwd + relu: forward output
+    float* out;              // fwd: y            bwd: dx
+    float* out2;             // bwd: dresidual
+    const float* weight;
+    const float* bias;
+    float* running_mean;
+    float* running_var;
+    float* save_mean;        // fwd: written      bwd: read
+    float* save_invstd;
+    float* dweight;
+    float* dbias;
+    double count;
+    float eps, momentum;
+    int replay;
+    unsigned int groups, n, c, hwv;
+};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+
+// Gather the per-rank partials of every group over DSMEM into local shared memory, then fold them in
+// rank order: tot[g] valid in threads g < groups after the call.  Contains the cluster barrier.
+__device__ __forceinline__ double2 cluster_fold(cg::cluster_group& cluster, double2* s_part, double2 (*s_all)[kMaxCluster],
+                                                unsigned int groups) {
+    const unsigned int cs = cluster.num_blocks();
+    cluster.sync();                                                 // every CTA's s_part is published
+    if (threadIdx.x < groups * cs) {
+        const unsigned int g = threadIdx.x / cs, r = threadIdx.x - g * cs;
+        s_all[g][r] = *cluster.map_shared_rank(&s_part[g], r);      // parallel DSMEM reads: one latency, not G*CS
+    }
+    __syncthreads();
+    cluster_arrive();                                               // remote reads done: peers may exit later
+    double2 tot = make_double2(0.0, 0.0);
+    if (threadIdx.x < groups)
+        for (unsigned int r = 0; r < cs; ++r) { tot.x += s_all[threadIdx.x][r].x; tot.y += s_all[threadIdx.x][r].y; }
+    return tot;
+}
+
+template <int VEC, bool RELU, bool RES>
+__global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const ClusterParams p) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
+    __shared__ double2 s_part[kMaxGroups];
+    __shared__ double2 s_all[kMaxGroups][kMaxCluster];
+    __shared__ double2 s_stat[kMaxGroups];                          // (mean, unbiased var) for the running update
+    __shared__ float2 s_ss[kMaxGroups];
+    __shared__ double scratch[64];
+    const unsigned int J = p.n * p.hwv;
+    const unsigned int lo = static_cast<unsigned int>(static_cast<unsigned long long>(J) * rank / cs);
+    const unsigned int hi = static_cast<unsigned int>(static_cast<unsigned long long>(J) * (rank + 1) / cs);
+    const V* x_v = reinterpret_cast<const V*>(p.a);
+    const V* r_v = reinterpret_cast<const V*>(p.b);
+    V* y_v = reinterpret_cast<V*>(p.out);
+    const size_t plane_stride = static_cast<size_t>(p.c) * p.hwv;
+
+    // ---- sweep 1: per-group sum / sum of squares of this CTA's slice ----
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
+            V a[kBnUnroll] = {};
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const unsigned int j = j0 + u * kClusterThreads;
+                if (j < hi) {
+                    const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
+                    a[u] = x_v[plane0 + nn * plane_stride + off];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                if constexpr (VEC == 4) {
+                    acc0 += (a[u].x + a[u].y) + (a[u].z + a[u].w);
+                    acc1 = fmaf(a[u].x, a[u].x, fmaf(a[u].y, a[u].y, fmaf(a[u].z, a[u].z, fmaf(a[u].w, a[u].w, acc1))));
+                } else {
+                    acc0 += a[u];
+                    acc1 = fmaf(a[u], a[u], acc1);
+                }
+            }
+        }
+        double d0 = acc0, d1 = acc1;
+        block_sum2(d0, d1, scratch);
+        if (threadIdx.x == 0) s_part[g] = make_double2(d0, d1);
+    }
+
+    // ---- cluster-wide fold over DSMEM, finalise ----
+    const double2 tot = cluster_fold(cluster, s_part, s_all, p.groups);
+    if (threadIdx.x < p.groups) {
+        const unsigned int g = threadIdx.x, gc = g * p.c + ch;
+        const double mean = tot.x / p.count;
+        double var = tot.y / p.count - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const double invstd = rsqrt(var + static_cast<double>(p.eps));
+        const float w = p.weight ? p.weight[ch] : 1.f, b = p.bias ? p.bias[ch] : 0.f;
+        s_ss[g] = make_float2(static_cast<float>(w * invstd), static_cast<float>(b - mean * w * invstd));
+        s_stat[g] = make_double2(mean, p.count > 1.0 ? var * (p.count / (p.count - 1.0)) : var);
+        if (rank == 0) {
+            p.save_mean[gc] = static_cast<float>(mean);
+            p.save_invstd[gc] = static_cast<float>(invstd);
+        }
+    }
+    __syncthreads();
+    if (rank == 0 && threadIdx.x == 0 && p.running_mean && p.running_var) {
+        float rm = p.running_mean[ch], rv = p.running_var[ch];
+        for (unsigned int g = 0; g < p.groups; ++g)                  // pass order: adv group first, then clean
+            for (int r = 0; r < p.replay; ++r) {
+                rm = static_cast<float>((1.0 - p.momentum) * rm + p.momentum * s_stat[g].x);
+                rv = static_cast<float>((1.0 - p.momentum) * rv + p.momentum * s_stat[g].y);
+            }
+        p.running_mean[ch] = rm;
+        p.running_var[ch] = rv;
+    }
+
+    // ---- sweep 2 (L2-hot): normalise + affine (+ residual) + ReLU ----
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
+        const float2 ss = s_ss[g];
+        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
+            V a[kBnUnroll] = {}, r[kBnUnroll] = {};
+            size_t idx[kBnUnroll];
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const unsigned int j = j0 + u * kClusterThreads;
+                if (j < hi) {
+                    const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
+                    idx[u] = plane0 + nn * plane_stride + off;
+                    a[u] = ld_stream(x_v + idx[u]);
+                    if (RES) r[u] = ld_stream(r_v + idx[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const unsigned int j = j0 + u * kClusterThreads;
+                if (j < hi) {
+                    V o;
+                    if constexpr (VEC == 4) {
+                        o.x = fmaf(a[u].x, ss.x, ss.y); o.y = fmaf(a[u].y, ss.x, ss.y);
+                        o.z = fmaf(a[u].z, ss.x, ss.y); o.w = fmaf(a[u].w, ss.x, ss.y);
+                        if (RES) { o.x += r[u].x; o.y += r[u].y; o.z += r[u].z; o.w += r[u].w; }
+                        if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    } else {
+                        o = fmaf(a[u], ss.x, ss.y);
+                        if (RES) o += r[u];
+                        if (RELU) o = fmaxf(o, 0.f);
+                    }
+                    y_v[idx[u]] = o;
+                }
+            }
+        }
+    }
+    cluster_wait();                                                 // nobody exits while a peer may still read its smem
+}
+
+template <int VEC, bool RELU, bool DRES>
+__global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const ClusterParams p) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
+    __shared__ double2 s_part[kMaxGroups];
+    __shared__ double2 s_all[kMaxGroups][kMaxCluster];
+    __shared__ double2 s_sum[kMaxGroups];
+    __shared__ float4 s_cf[kMaxGroups];
+    __shared__ double scratch[64];
+    const unsigned int J = p.n * p.hwv;
+    const unsigned int lo = static_cast<unsigned int>(static_cast<unsigned long long>(J) * rank / cs);
+    const unsigned int hi = static_cast<unsigned int>(static_cast<unsigned long long>(J) * (rank + 1) / cs);
+    const V* dy_v = reinterpret_cast<const V*>(p.a);
+    const V* x_v = reinterpret_cast<const V*>(p.b);
+    const V* y_v = reinterpret_cast<const V*>(p.y);
+    V* dx_v = reinterpret_cast<V*>(p.out);
+    V* dr_v = reinterpret_cast<V*>(p.out2);
+    const size_t plane_stride = static_cast<size_t>(p.c) * p.hwv;
+
+    // ---- sweep 1: sum dy_eff, sum dy_eff * (x - mean) ----
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
+        const float mean = p.save_mean[g * p.c + ch];
+        float acc0 = 0.f, acc1 = 0.f;
+        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
+            V d[kBnUnroll] = {}, x[kBnUnroll] = {}, y[kBnUnroll] = {};
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const unsigned int j = j0 + u * kClusterThreads;
+                if (j < hi) {
+                    const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
+                    const size_t idx = plane0 + nn * plane_stride + off;
+                    d[u] = dy_v[idx];
+                    x[u] = x_v[idx];
+                    if (RELU) y[u] = y_v[idx];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const unsigned int j = j0 + u * kClusterThreads;
+                if (j < hi) {
+                    auto one = [&](float dv, float xv, float yv) {
+                        const float de = (RELU && !(yv > 0.f)) ? 0.f : dv;
+                        acc0 += de;
+                        acc1 = fmaf(de, xv - mean, acc1);
+                    };
+                    if constexpr (VEC == 4) {
+                        one(d[u].x, x[u].x, y[u].x); one(d[u].y, x[u].y, y[u].y);
+                        one(d[u].z, x[u].z, y[u].z); one(d[u].w, x[u].w, y[u].w);
+                    } else {
+                        one(d[u], x[u], y[u]);
+                    }
+                }
+            }
+        }
+        double d0 = acc0, d1 = acc1;
+        block_sum2(d0, d1, scratch);
+        if (threadIdx.x == 0) s_part[g] = make_double2(d0, d1);
+    }
+
+    const double2 tot = cluster_fold(cluster, s_part, s_all, p.groups);
+    if (threadIdx.x < p.groups) {
+        const unsigned int g = threadIdx.x, gc = g * p.c + ch;
+        const float invstd = p.save_invstd[gc], w = p.weight ? p.weight[ch] : 1.f;
+        const double s_dy = tot.x, s_dyxh = tot.y * static_cast<double>(invstd);
+        s_sum[g] = make_double2(s_dy, s_dyxh);
+        s_cf[g] = make_float4(w * invstd, static_cast<float>(s_dy / p.count),
+                              static_cast<float>(s_dyxh / p.count * invstd), p.save_mean[gc]);
+    }
+    __syncthreads();
+    if (rank == 0 && threadIdx.x == 0) {
+        double dw = 0.0, db = 0.0;
+        for (unsigned int g = 0; g < p.groups; ++g) { db += s_sum[g].x; dw += s_sum[g].y; }
+        if (p.dweight) p.dweight[ch] = static_cast<float>(dw);
+        if (p.dbias) p.dbias[ch] = static_cast<float>(db);
+    }
+
+    // ---- sweep 2 (L2-hot): dx = w*invstd * (dy_eff - mean(dy_eff) - xhat * mean(dy_eff*xhat)) ----
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
+        const float4 cf = s_cf[g];
+        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
+            V d[kBnUnroll] = {}, x[kBnUnroll] = {}, y[kBnUnroll] = {};
+            size_t idx[kBnUnroll];
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const unsigned int j = j0 + u * kClusterThreads;
+                if (j < hi) {
+                    const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
+                    idx[u] = plane0 + nn * plane_stride + off;
+                    d[u] = ld_stream(dy_v + idx[u]);
+                    x[u] = ld_stream(x_v + idx[u]);
+                    if (RELU) y[u] = ld_stream(y_v + idx[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const unsigned int j = j0 + u * kClusterThreads;
+                if (j < hi) {
+                    V dx, dr;
+                    auto one = [&](float dv, float xv, float yv, float& o, float& r) {
+                        const float de = (RELU && !(yv > 0.f)) ? 0.f : dv;
+                        r = de;
+                        o = cf.x * (de - cf.y - (xv - cf.w) * cf.z);
+                    };
+                    if constexpr (VEC == 4) {
+                        one(d[u].x, x[u].x, y[u].x, dx.x, dr.x); one(d[u].y, x[u].y, y[u].y, dx.y, dr.y);
+                        one(d[u].z, x[u].z, y[u].z, dx.z, dr.z); one(d[u].w, x[u].w, y[u].w, dx.w, dr.w);
+                    } else {
+                        one(d[u], x[u], y[u], dx, dr);
+                    }
+                    dx_v[idx[u]] = dx;
+                    if (DRES) dr_v[idx[u]] = dr;
+                }
+            }
+        }
+    }
+    cluster_wait();
+}
+
+// cluster size: enough CTAs to cover the chip (C * CS >= ~148), power of two, <= 8, and every CTA keeps
+// >= 512 vectors per group; 0 -> shape not suited (per-channel domain too large to stay L2-resident)
+__host__ inline int pick_cluster(int64_t groups, int64_t n, int64_t c, int64_t hw, bool vec) {
+    const int64_t v = vec ? 4 : 1;
+    const int64_t J = n * (hw / v);                                   // vectors per (group, channel)
+    const int64_t domain_bytes = groups * n * hw * 4;
+    int cs = 1;
+    while (cs < kMaxCluster && c * cs < sm_count() && J / (cs * 2) >= 512) cs *= 2;
+    // concurrently resident footprint must fit L2 for sweep 2 to hit: (CTAs resident) * slice <= ~48 MB
+    const int64_t resident = static_cast<int64_t>(sm_count()) * 4;   // 4 x 512 threads per SM
+    const int64_t slice = domain_bytes / cs;
+    const int64_t ctas = c * cs < resident ? c * cs : resident;
+    if (ctas * slice > (int64_t(48) << 20)) return 0;
+    return cs;
+}
+
+template <typename K>
+int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p.c * cs);
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, p) != cudaSuccess) { cudaGetLastError(); return AFAN_ERR_LAUNCH; }
+    return launch_status();
+}
+
 // ---- host helpers -------------------------------------------------------------------------------
 struct BnShape {
     bool ok, vec;
@@ -457,10 +787,31 @@ AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const flo
                                 float* save_invstd, void* workspace, int64_t workspace_bytes, int64_t groups,
                                 int64_t n, int64_t c, int64_t hw, float eps, float momentum, int relu, int replay,
                                 afan_stream_t stream) {
-    BnShape s{};   // (each pass picks its own vector/scalar path; partial and table formats do not depend on it)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool al = aligned16(x) && aligned16(y) && (!residual || aligned16(residual));
+    BnShape s = bn_shape(groups, n, c, hw, al);
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_OK;
+    if (!x || !y || !save_mean || !save_invstd) return AFAN_ERR_NULL;
+    const int cs = pick_cluster(groups, n, c, hw, s.vec);
+    if (cs > 0) {                                                    // single-launch cluster path
+        ClusterParams p{};
+        p.a = x; p.b = residual; p.out = y; p.weight = weight; p.bias = bias;
+        p.running_mean = running_mean; p.running_var = running_var; p.save_mean = save_mean; p.save_invstd = save_invstd;
+        p.count = static_cast<double>(n) * static_cast<double>(hw);
+        p.eps = eps; p.momentum = momentum; p.replay = replay;
+        p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
+        const bool r = relu != 0, rs = residual != nullptr;
+#define AFAN_CF(V, R, S) return launch_cluster(bn_fwd_cluster_kernel<V, R, S>, p, cs, st)
+        if (s.vec) { if (r) { if (rs) AFAN_CF(4, true, true); else AFAN_CF(4, true, false); }
+                     else   { if (rs) AFAN_CF(4, false, true); else AFAN_CF(4, false, false); } }
+        else       { if (r) { if (rs) AFAN_CF(1, true, true); else AFAN_CF(1, true, false); }
+                     else   { if (rs) AFAN_CF(1, false, true); else AFAN_CF(1, false, false); } }
+#undef AFAN_CF
+    }
+    // large per-channel domains: two-launch path (global partials + last-CTA finalise, then apply)
     int rc = bn_fwd_reduce_impl(x, nullptr, true, weight, bias, running_mean, running_var, save_mean, save_invstd,
-                                workspace, workspace_bytes, groups, n, c, hw, eps, momentum, replay,
-                                static_cast<cudaStream_t>(stream), &s);
+                                workspace, workspace_bytes, groups, n, c, hw, eps, momentum, replay, st, &s);
     if (rc != AFAN_OK || !s.ok) return rc;
     return afan_bn_fwd_apply_f32(x, residual, y, workspace, workspace_bytes, groups, n, c, hw, relu, stream);
 }
@@ -551,10 +902,32 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
                                 const float* save_mean, const float* save_invstd, float* dx, float* dresidual,
                                 float* dweight, float* dbias, void* workspace, int64_t workspace_bytes,
                                 int64_t groups, int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream) {
-    BnShape s{};
-    const bool al = aligned16(dy) && aligned16(x) && (!y || aligned16(y));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool al = aligned16(dy) && aligned16(x) && aligned16(dx) && (!y || aligned16(y)) &&
+                    (!dresidual || aligned16(dresidual));
+    BnShape s = bn_shape(groups, n, c, hw, al);
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_OK;
+    if (!dy || !x || !dx || !save_mean || !save_invstd || (relu && !y)) return AFAN_ERR_NULL;
+    const int cs = pick_cluster(groups * 3, n, c, hw, s.vec);        // three tensors are swept twice
+    if (cs > 0) {
+        ClusterParams p{};
+        p.a = dy; p.b = x; p.y = y; p.out = dx; p.out2 = dresidual; p.weight = weight;
+        p.save_mean = const_cast<float*>(save_mean); p.save_invstd = const_cast<float*>(save_invstd);
+        p.dweight = dweight; p.dbias = dbias;
+        p.count = static_cast<double>(n) * static_cast<double>(hw);
+        p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
+        const bool r = relu != 0, dr = dresidual != nullptr;
+#define AFAN_CB(V, R, S) return launch_cluster(bn_bwd_cluster_kernel<V, R, S>, p, cs, st)
+        if (s.vec) { if (r) { if (dr) AFAN_CB(4, true, true); else AFAN_CB(4, true, false); }
+                     else   { if (dr) AFAN_CB(4, false, true); else AFAN_CB(4, false, false); } }
+        else       { if (r) { if (dr) AFAN_CB(1, true, true); else AFAN_CB(1, true, false); }
+                     else   { if (dr) AFAN_CB(1, false, true); else AFAN_CB(1, false, false); } }
+#undef AFAN_CB
+    }
+    const bool al1 = aligned16(dy) && aligned16(x) && (!y || aligned16(y));
     int rc = bn_bwd_reduce_impl(dy, x, y, weight, save_mean, save_invstd, nullptr, true, dweight, dbias, workspace,
-                                workspace_bytes, groups, n, c, hw, relu, al, static_cast<cudaStream_t>(stream), &s);
+                                workspace_bytes, groups, n, c, hw, relu, al1, st, &s);
     if (rc != AFAN_OK || !s.ok) return rc;
     return afan_bn_bwd_apply_f32(dy, x, y, dx, dresidual, workspace, workspace_bytes, groups, n, c, hw, relu, stream);
 }

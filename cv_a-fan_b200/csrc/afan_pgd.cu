@@ -216,8 +216,9 @@ l2_apply_kernel(const float* __restrict__ src, const float* __restrict__ norm, f
         float d = __fsub_rn(tv, sv);
         d = __fdiv_rn(d, nrm);
         d = __fmul_rn(d, coef);
-        dlt = d;
-        return __fadd_rn(sv, d);
+        const float o = __fadd_rn(sv, d);
+        dlt = __fsub_rn(o, sv);                        // delta as the caller sees it: fl(t_new - center)
+        return o;
     };
     for (long long i0 = lo + threadIdx.x; i0 < hi; i0 += static_cast<long long>(kThreads) * kUnroll) {
         V a[kUnroll] = {}, b[kUnroll] = {};

@@ -137,7 +137,7 @@ def _ws_bytes(ws):
 
 
 def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1, eps=1e-5, momentum=0.1,
-           relu=False, replay=1, process_group=None):
+           relu=False, replay=1, process_group=None, split=False):
     """Train-mode grouped-statistics BN (+residual, +ReLU).  Returns (y, save_mean[G,C], save_invstd[G,C]).
     With a process group of size > 1 the per-(group, channel) sums are all-reduced over NCCL in ONE
     message for all groups between the statistics kernel and the apply kernel."""
@@ -147,7 +147,7 @@ def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1
     save_mean = torch.empty((groups, c), dtype=torch.float32, device=x.device)
     save_invstd = torch.empty_like(save_mean)
     world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
-    if world == 1:
+    if world == 1 and not split:
         check(L.afan_bn_fwd_f32(f32(x), f32(residual), f32(weight), f32(bias), f32(running_mean), f32(running_var),
                                 f32(y), f32(save_mean), f32(save_invstd), ptr(ws), _ws_bytes(ws), groups, n, c, hw,
                                 float(eps), float(momentum), int(bool(relu)), int(replay), stream()), "afan_bn_fwd_f32")
@@ -155,7 +155,8 @@ def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1
         sums = torch.empty((groups, c, 2), dtype=torch.float64, device=x.device)
         check(L.afan_bn_fwd_stats_f32(f32(x), ptr(sums), ptr(ws), _ws_bytes(ws), groups, n, c, hw, stream()),
               "afan_bn_fwd_stats_f32")
-        torch.distributed.all_reduce(sums, group=process_group)
+        if world > 1:
+            torch.distributed.all_reduce(sums, group=process_group)
         check(L.afan_bn_fwd_finalize_f32(ptr(sums), float(n * hw * world), f32(weight), f32(bias), f32(running_mean),
                                          f32(running_var), f32(save_mean), f32(save_invstd), ptr(ws), _ws_bytes(ws),
                                          groups, c, float(eps), float(momentum), int(replay), stream()),
@@ -166,7 +167,7 @@ def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1
 
 
 def bn_bwd(dy, x, y, weight, save_mean, save_invstd, ws, *, groups=1, relu=False, want_dresidual=False,
-           process_group=None):
+           process_group=None, split=False):
     """Backward of bn_fwd.  Returns (dx, dresidual|None, dweight[C], dbias[C]) (dweight/dbias are LOCAL sums;
     the data-parallel gradient all-reduce averages them with the other parameters)."""
     n, c, hw = _nchw(x, groups)
@@ -176,7 +177,7 @@ def bn_bwd(dy, x, y, weight, save_mean, save_invstd, ws, *, groups=1, relu=False
     dweight = torch.empty(c, dtype=torch.float32, device=x.device)
     dbias = torch.empty_like(dweight)
     world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
-    if world == 1:
+    if world == 1 and not split:
         check(L.afan_bn_bwd_f32(f32(dy), f32(x), f32(y) if relu else None, f32(weight), f32(save_mean),
                                 f32(save_invstd), f32(dx), f32(dres), f32(dweight), f32(dbias), ptr(ws), _ws_bytes(ws),
                                 groups, n, c, hw, int(bool(relu)), stream()), "afan_bn_bwd_f32")
@@ -185,7 +186,8 @@ def bn_bwd(dy, x, y, weight, save_mean, save_invstd, ws, *, groups=1, relu=False
         check(L.afan_bn_bwd_reduce_f32(f32(dy), f32(x), f32(y) if relu else None, f32(save_mean), f32(save_invstd),
                                        ptr(sums), f32(dweight), f32(dbias), ptr(ws), _ws_bytes(ws), groups, n, c, hw,
                                        int(bool(relu)), stream()), "afan_bn_bwd_reduce_f32")
-        torch.distributed.all_reduce(sums, group=process_group)
+        if world > 1:
+            torch.distributed.all_reduce(sums, group=process_group)
         check(L.afan_bn_bwd_finalize_f32(ptr(sums), float(n * hw * world), f32(weight), f32(save_mean),
                                          f32(save_invstd), ptr(ws), _ws_bytes(ws), groups, c, stream()),
               "afan_bn_bwd_finalize_f32")

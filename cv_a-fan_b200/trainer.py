@@ -203,21 +203,25 @@ class AfanTrainer:
         st["images"], st["target"] = images.clone(), target.clone()
         st["noise"] = noise.clone() if noise is not None else None
         snap = self._snapshot()
-        side = torch.cuda.Stream(device=self.device)
+        # warm-up and capture run on ONE private stream so that autograd's per-parameter AccumulateGrad
+        # nodes live on the stream that is later captured
+        side = self._stream = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):                      # warm-up: cuDNN autotune, NCCL communicator, lazy module load
                 loss, _ = self._iteration(st["images"], st["target"], st["noise"], st["norms"], st["ws"])
                 self._optimize(loss)
+            del loss
         torch.cuda.current_stream().wait_stream(side)
         self._restore(snap)
         pend0 = [m._pending_batches for m in self._bn]
         self._graph = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=side):
             loss, out_clean = self._iteration(st["images"], st["target"], st["noise"], st["norms"], st["ws"])
             self._optimize(loss)
             st["loss"], st["out_clean"] = loss.detach(), out_clean.detach()
+        del loss, out_clean
         self.kernel_launches_per_iter = _lib.launch_count - l0      # afan kernels replayed per iteration
         self._bn_per_iter = [m._pending_batches - p0 for m, p0 in zip(self._bn, pend0)]
         for m, p0 in zip(self._bn, pend0):

@@ -79,7 +79,8 @@ int afan_pgd_linf_step_f32(const float* grad, const float* x_clean, float* x_adv
  *   north-star item with NO reference implementation -- semantics defined in oracle/afan_oracle.c).
  * afan_l2ball_proj_f32:   replaces l2ball_proj, Classification/attack_algo.py:21-33, given
  *   dist[s] = ||t_s - center_s||_2:  d = t - c; d /= dist; d *= min(dist, radius); t = c + d
- *   (t == center gives 0/0 = NaN exactly like the reference).  delta_out (nullable) receives d. */
+ *   (t == center gives 0/0 = NaN exactly like the reference).  delta_out (nullable) receives
+ *   fl(t_new - center). */
 int afan_sample_l2norm_f32(const float* a, const float* b, float* out_norm, void* workspace,
                            int64_t workspace_bytes, int64_t n_samples, int64_t per_sample,
                            afan_stream_t stream);

@@ -17,7 +17,7 @@ CASES = [  # groups, n, c, h, w
     (1, 3, 5, 1, 1), (2, 1, 3, 2, 2), (1, 2, 1, 1, 7), (4, 2, 6, 4, 4)]
 
 
-def run_case(groups, n, c, h, w, relu, residual, replay=1, offset=0.0):
+def run_case(groups, n, c, h, w, relu, residual, replay=1, offset=0.0, split=False):
     g = torch.Generator().manual_seed(groups * 1000 + c + h)
     x = torch.randn(groups * n, c, h, w, generator=g) * 1.7 + 0.3 + offset
     res = torch.randn(x.shape, generator=g) if residual else None
@@ -28,9 +28,9 @@ def run_case(groups, n, c, h, w, relu, residual, replay=1, offset=0.0):
     rm_d, rv_d = rm.to(d), rv.to(d)
     ws = ops.bn_workspace(groups, c, d)
     y, sm, si = ops.bn_fwd(x.to(d), res.to(d) if residual else None, wt.to(d), b.to(d), rm_d, rv_d, ws,
-                           groups=groups, relu=relu, replay=replay)
+                           groups=groups, relu=relu, replay=replay, split=split)
     dx, dres, dw, db = ops.bn_bwd(dy.to(d), x.to(d), y, wt.to(d), sm, si, ws, groups=groups, relu=relu,
-                                  want_dresidual=residual)
+                                  want_dresidual=residual, split=split)
     rm_o, rv_o = rm.numpy().copy(), rv.numpy().copy()
     y_o, sm_o, si_o = orc.bn_fwd(x.numpy(), wt.numpy(), b.numpy(), rm_o, rv_o, groups=groups,
                                  residual=res.numpy() if residual else None, relu=relu, replay=replay)
@@ -58,6 +58,17 @@ def run_case(groups, n, c, h, w, relu, residual, replay=1, offset=0.0):
 @pytest.mark.parametrize("relu,residual", [(False, False), (True, False), (True, True)])
 def test_bn_fwd_bwd_vs_oracle(case, relu, residual):
     run_case(*case, relu=relu, residual=residual)
+
+
+@pytest.mark.parametrize("case", [(2, 128, 32, 16, 16), (2, 2, 256, 33, 33), (1, 3, 5, 1, 1), (4, 2, 6, 4, 4)])
+def test_split_stats_finalize_apply_path(case):
+    """The three-call form used under NCCL (stats -> all-reduce -> finalize -> apply), here with world 1."""
+    run_case(*case, relu=True, residual=True, split=True)
+
+
+def test_large_domain_takes_two_launch_path():
+    """Per-channel domain of 32 MB: too big to stay L2-resident per cluster -> global-partials path."""
+    run_case(1, 8, 4, 1024, 1024, relu=True, residual=False)
 
 
 def test_replay_and_large_mean():

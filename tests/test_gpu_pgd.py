@@ -133,7 +133,7 @@ def test_l2_step_vs_oracle(shape, clip):
     ops.pgd_l2_step_(grad.to(dev()), x.to(dev()), xa, 0.5, 0.3, clip, delta_out=delta)
     ref = orc.pgd_l2_step(grad.numpy(), x.numpy(), xa0.numpy(), 0.5, 0.3, clip)
     np.testing.assert_allclose(xa.cpu().numpy(), ref, rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(delta.cpu().numpy(), ref - x.numpy(), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(delta.cpu().numpy(), ref - x.numpy(), rtol=1e-4, atol=1e-6)   # 1-ulp x_adv differences
     n2 = ops.sample_l2norm(xa, x.to(dev())).cpu().numpy()
     assert ulp_diff(n2, orc.delta_norms(xa.cpu().numpy(), x.numpy())[1]) <= 4
     if clip:
