@@ -402,8 +402,11 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        trainer.close()                      # a live graph with captured NCCL ops blocks communicator teardown
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

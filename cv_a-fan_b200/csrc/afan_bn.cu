@@ -793,6 +793,7 @@ AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const flo
     if (s.err != AFAN_OK) return s.err;
     if (!s.ok) return AFAN_OK;
     if (!x || !y || !save_mean || !save_invstd) return AFAN_ERR_NULL;
+    if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;   // uniform contract on both paths
     const int cs = pick_cluster(groups, n, c, hw, s.vec);
     if (cs > 0) {                                                    // single-launch cluster path
         ClusterParams p{};
@@ -909,6 +910,7 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
     if (s.err != AFAN_OK) return s.err;
     if (!s.ok) return AFAN_OK;
     if (!dy || !x || !dx || !save_mean || !save_invstd || (relu && !y)) return AFAN_ERR_NULL;
+    if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
     const int cs = pick_cluster(groups * 3, n, c, hw, s.vec);        // three tensors are swept twice
     if (cs > 0) {
         ClusterParams p{};

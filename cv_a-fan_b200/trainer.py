@@ -227,6 +227,13 @@ class AfanTrainer:
         for m, p0 in zip(self._bn, pend0):
             m._pending_batches = p0                 # capture records launches, it does not run them
 
+    def close(self):
+        """Drop the captured graph (it pins NCCL communicator resources: destroy_process_group() blocks
+        while a graph holding captured collectives is alive)."""
+        torch.cuda.synchronize(self.device)
+        self._graph = None
+        self._static = {}
+
     # ---- evaluation (main_perturb.py:227-262) ---------------------------------------------------------
     @torch.no_grad()
     def evaluate(self, images, target):

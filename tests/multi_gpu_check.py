@@ -1,0 +1,94 @@
+"""Run under torchrun (world >= 2, one rank per GPU, NCCL):  the data-parallel A-FAN step with the batch
+sharded over ranks + NCCL-synchronised dual-BN statistics + one gradient all-reduce must reproduce the
+SINGLE-process step at the GLOBAL batch (the multi-GPU oracle of SURVEY.md F10 / 8e).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py [--graph]
+"""
+import importlib
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("AFAN_HANG_DUMP_S", "120")), exit=True)   # never hang a GPU box
+    use_graph = "--graph" in sys.argv
+    sync_bn = "--no-sync-bn" not in sys.argv
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pkg = importlib.import_module("cv_a-fan_b200")
+    per_rank, iters = 8, 3
+    kw = dict(perturb_idx=5, steps=2, gamma=1.0, eps=2.0, randinit=True, clip=True)
+    g = torch.Generator().manual_seed(21)
+    B = per_rank * world
+    images = [torch.rand(B, 3, 32, 32, generator=g) for _ in range(iters)]
+    targets = [torch.randint(0, 10, (B,), generator=g) for _ in range(iters)]
+    noises = [torch.rand(B, 16, 32, 32, generator=g) for _ in range(iters)]
+
+    torch.manual_seed(3)
+    model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    tr = pkg.trainer.AfanTrainer(model, process_group=dist.group.WORLD, sync_bn=sync_bn, use_cuda_graph=use_graph, **kw)
+    print(f'[rank {rank}] trainer built', flush=True)
+    sl = slice(rank * per_rank, (rank + 1) * per_rank)
+    losses = []
+    for i in range(iters):
+        out = tr.step(images[i][sl].to(dev), targets[i][sl].to(dev), noises[i][sl].to(dev))
+        torch.cuda.synchronize()
+        print(f'[rank {rank}] step {i} done', flush=True)
+        l = out["loss"].detach().clone()
+        dist.all_reduce(l)
+        losses.append(float(l) / world)                 # global-batch loss = mean of equal-sized shard means
+    sharded = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    # the oracle: ONE process, global batch, same initial weights
+    ref_model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
+    ref_model.load_state_dict(init)
+    ref = pkg.trainer.AfanTrainer(ref_model, use_cuda_graph=False, **kw)
+    ref_losses = [float(ref.step(images[i].to(dev), targets[i].to(dev), noises[i].to(dev))["loss"]) for i in range(iters)]
+    single = ref_model.state_dict()
+
+    ok = True
+    for a, b in zip(losses, ref_losses):
+        ok &= abs(a - b) <= 2e-4 * abs(b)
+    worst = ("", 0.0)
+    for k, v in single.items():
+        if not v.dtype.is_floating_point:
+            ok &= bool((sharded[k] == v).all())
+            continue
+        err = float((sharded[k] - v).abs().max())
+        tol = 1e-3 + 1e-2 * float(v.abs().max())
+        if err > worst[1]:
+            worst = (k, err)
+        ok &= err <= tol
+    # every rank must hold identical weights after the all-reduced update
+    flat = torch.cat([v.reshape(-1).float() for v in sharded.values()])
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok &= bool((lo == hi).all())
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"MULTI_GPU_CHECK world={world} graph={use_graph} losses={losses} ref={ref_losses} worst={worst} "
+              f"{'OK' if int(flag) else 'FAIL'}")
+    tr.close()
+    ref.close()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if int(flag) else 1)      # skip NCCL teardown: exit status is what the caller checks
+
+
+if __name__ == "__main__":
+    main()
