@@ -390,7 +390,9 @@ AFAN_EXPORT int afan_pgd_linf_step_f32(const float* grad, const float* x_clean, 
     const long long pv = vec ? per / 4 : per;
     // chunks per sample: enough CTAs to fill the chip (148 x 8), at most one CTA per 256*kUnroll vectors
     long long chunks = (pv + kThreads * kUnroll - 1) / (kThreads * kUnroll);
-    const long long cap = (static_cast<long long>(sm_count()) * kCtasPerSm + ns - 1) / ns;
+    const long long sms = sm_count();
+    const long long cap = (sms * kCtasPerSm + ns - 1) / ns;
+    if (ns == 1 && chunks > sms) chunks = (chunks + sms - 1) / sms * sms;   // whole waves: every SM gets the same CTA count
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     if (norms && chunks * ns > kMaxNormChunks + ns) chunks = (kMaxNormChunks + ns) / ns;

@@ -4,7 +4,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, sync
 from ._lib import AfanError, check, f32, ptr, stream
 
 
@@ -155,9 +155,8 @@ def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1
         sums = torch.empty((groups, c, 2), dtype=torch.float64, device=x.device)
         check(L.afan_bn_fwd_stats_f32(f32(x), ptr(sums), ptr(ws), _ws_bytes(ws), groups, n, c, hw, stream()),
               "afan_bn_fwd_stats_f32")
-        if world > 1:
-            torch.distributed.all_reduce(sums, group=process_group)
-        check(L.afan_bn_fwd_finalize_f32(ptr(sums), float(n * hw * world), f32(weight), f32(bias), f32(running_mean),
+        sync.allreduce_sums_(sums, process_group)             # ONE message: clean + adversarial statistics
+        check(L.afan_bn_fwd_finalize_f32(ptr(sums), sync.global_count(n, hw, world), f32(weight), f32(bias), f32(running_mean),
                                          f32(running_var), f32(save_mean), f32(save_invstd), ptr(ws), _ws_bytes(ws),
                                          groups, c, float(eps), float(momentum), int(replay), stream()),
               "afan_bn_fwd_finalize_f32")
@@ -186,9 +185,8 @@ def bn_bwd(dy, x, y, weight, save_mean, save_invstd, ws, *, groups=1, relu=False
         check(L.afan_bn_bwd_reduce_f32(f32(dy), f32(x), f32(y) if relu else None, f32(save_mean), f32(save_invstd),
                                        ptr(sums), f32(dweight), f32(dbias), ptr(ws), _ws_bytes(ws), groups, n, c, hw,
                                        int(bool(relu)), stream()), "afan_bn_bwd_reduce_f32")
-        if world > 1:
-            torch.distributed.all_reduce(sums, group=process_group)
-        check(L.afan_bn_bwd_finalize_f32(ptr(sums), float(n * hw * world), f32(weight), f32(save_mean),
+        sync.allreduce_sums_(sums, process_group)
+        check(L.afan_bn_bwd_finalize_f32(ptr(sums), sync.global_count(n, hw, world), f32(weight), f32(save_mean),
                                          f32(save_invstd), ptr(ws), _ws_bytes(ws), groups, c, stream()),
               "afan_bn_bwd_finalize_f32")
         check(L.afan_bn_bwd_apply_f32(f32(dy), f32(x), f32(y) if relu else None, f32(dx), f32(dres), ptr(ws),

@@ -23,7 +23,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import _lib, attack_algo, ops
+from . import _lib, attack_algo, ops, sync
 from ._lib import AfanError
 from .dual_bn import DualBatchNorm2d
 
@@ -133,10 +133,9 @@ class AfanTrainer:
     def _optimize(self, loss):
         self.flat_grad.zero_()                                                       # :199
         loss.backward()                                                              # :200
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad, group=self.pg)              # one NCCL message / iteration
+        scale = sync.allreduce_grad_arena_(self.flat_grad, self.pg)                  # one NCCL message / iteration
         ops.sgd_momentum_(self.flat_param, self.flat_grad, self.flat_buf, self.lr_dev, momentum=self.momentum,
-                          weight_decay=self.weight_decay, grad_scale=1.0 / self.world)        # :201
+                          weight_decay=self.weight_decay, grad_scale=scale)                   # :201
 
     def _discover_arena(self, images, target, noise, norms_out, ws):
         """First iteration: find the parameters that actually receive gradients (torch.optim.SGD skips

@@ -1,0 +1,123 @@
+"""CPU: host-side logic -- CLI parity with the reference flags, LR schedule, data-parallel protocol over
+gloo (world_size 2), model/state-dict compatibility with the reference."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as orc
+from oracle import ref_shim
+
+PKG = importlib.import_module("cv_a-fan_b200")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cli_flags_and_defaults_match_reference():
+    ours = PKG.main_perturb.build_parser()
+    d = vars(ours.parse_args([]))
+    expected = dict(steps=5, perturb_idx=13, gamma=1.5, eps=2, randinit=False, clip=False, batch_size=128, lr=0.1,
+                    momentum=0.9, weight_decay=5e-4, epochs=200, decreasing_lr="50,150", print_freq=50, gpu=0,
+                    seed=None, resume=False, save_dir="res56s_adv_aug", data="../data")     # main_perturb.py:28-49
+    for k, v in expected.items():
+        assert d[k] == v, k
+    if ref_shim.available():
+        ref = ref_shim.load("Classification", "main_perturb").parser
+        rd = vars(ref.parse_args([]))
+        for k, v in rd.items():
+            assert d[k] == v, f"default of --{k} differs from the reference"
+        args = ["--steps", "3", "--perturb_idx", "10", "--gamma", "0.5", "--eps", "4", "--randinit", "--clip", "--seed", "3"]
+        a, b = vars(ours.parse_args(args)), vars(ref.parse_args(args))
+        for k, v in b.items():
+            assert a[k] == v, k
+
+
+def test_lr_schedule_matches_reference():
+    mpf = PKG.main_perturb
+    for step in (0, 1, 175, 349, 350, 1000):
+        assert mpf.warmup_lr(step, 351, 0.1) == pytest.approx(min(step * 0.1 / 350, 0.1))
+    sched_model = torch.nn.Linear(1, 1)
+    opt = torch.optim.SGD(sched_model.parameters(), 0.1)
+    sch = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[50, 150], gamma=0.1)     # main_perturb.py:75
+    for epoch in range(200):
+        assert mpf.multistep_lr(epoch, 0.1, [50, 150]) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-9)
+        opt.step(); sch.step()
+
+
+def test_model_layout_matches_reference_indexing():
+    m = PKG.resnet_s.resnet56(num_classes=100)
+    assert len(m.sequential_model) == 34                      # main_perturb.py:65
+    assert len(PKG.resnet_s.resnet20().sequential_model) == 16   # attack_algo.py:38 default layer_number
+    names = [type(l).__name__ for l in m.sequential_model]
+    assert names[:4] == ["NormalizeByChannelMeanStd", "Conv2d", "DualBatchNorm2d", "ReLU"]
+    assert names[4:31] == ["BasicBlock"] * 27 and names[31:] == ["AdaptiveAvgPool2d", "Flatten", "Linear"]
+    assert len(m.bn_layers()) == 55
+    if ref_shim.available():
+        rs = ref_shim.load("Classification", "resnet_s")
+        torch.manual_seed(3)
+        ref = rs.ResNet(rs.BasicBlock, [9, 9, 9], num_classes=100)
+        torch.manual_seed(3)
+        ours = PKG.resnet_s.resnet56(num_classes=100)
+        rsd, osd = ref.state_dict(), ours.state_dict()
+        assert list(rsd) == list(osd)
+        assert all(torch.equal(rsd[k], osd[k]) for k in rsd)          # same init stream under the same seed
+        ours.load_state_dict(rsd)
+
+
+def test_shard_range_and_errors():
+    s = PKG.sync
+    assert [s.shard_range(1024, r, 8) for r in (0, 7)] == [(0, 128), (896, 1024)]
+    with pytest.raises(ValueError):
+        s.shard_range(10, 0, 4)
+    with pytest.raises(TypeError):
+        s.allreduce_sums_(torch.zeros(2, 3, 2))                         # must be float64
+
+
+def test_cuda_only_paths_fail_loudly_on_cpu():
+    with pytest.raises(PKG.AfanError):
+        PKG.attack_algo.PGD(torch.zeros(2, 3, 4, 4), lambda o, y: o.sum(), model=lambda x, **k: x, steps=1, gamma=0.1)
+    with pytest.raises(PKG.AfanError):
+        PKG.segmentation.mix_feature(torch.zeros(1, 4, 2, 2), torch.zeros(1, 4, 2, 2))
+    with pytest.raises(PKG.AfanError):
+        PKG.trainer.AfanTrainer(PKG.resnet_s.resnet20())
+
+
+def _dp_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("cv_a-fan_b200")
+    g = torch.Generator().manual_seed(0)
+    G, N, C, H, W = 2, 8, 6, 5, 5                        # global [adv; clean] batch: G*N samples
+    x = torch.randn(G * N, C, H, W, generator=g) * 1.5 + 0.4
+    lo, hi = pkg.sync.shard_range(N, rank, world)
+    local = torch.cat([x[gi * N + lo: gi * N + hi] for gi in range(G)])       # this rank's shard of EACH group
+    n_loc = hi - lo
+    xs = local.view(G, n_loc, C, H * W).double()
+    sums = torch.stack([xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))], dim=-1).contiguous()    # [G, C, 2] local sums
+    pkg.sync.allreduce_sums_(sums, dist.group.WORLD)                     # ONE message for both groups
+    mean, var, unb, invstd = pkg.sync.stats_from_sums(sums, pkg.sync.global_count(n_loc, H * W, world), 1e-5)
+    # gradient arena protocol: SUM all-reduce, 1/world folded into the update
+    arena = torch.full((10,), float(rank + 1))
+    scale = pkg.sync.allreduce_grad_arena_(arena, dist.group.WORLD)
+    torch.save({"mean": mean, "invstd": invstd, "unb": unb, "arena": arena * scale, "x": x}, os.path.join(tmp, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_protocol_reproduces_global_batch_statistics(tmp_path):
+    world, port = 2, 29600 + os.getpid() % 300
+    mp.spawn(_dp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (torch.load(tmp_path / f"r{r}.pt") for r in range(2))
+    for k in ("mean", "invstd", "unb", "arena"):
+        assert torch.equal(r0[k], r1[k]), k                              # every rank ends with identical values
+    assert torch.allclose(r0["arena"], torch.full((10,), 1.5))           # mean of rank grads (1 and 2)
+    x = r0["x"].numpy()
+    rm, rv = np.zeros(6, np.float32), np.ones(6, np.float32)
+    _, sm, si = orc.bn_fwd(x, np.ones(6, np.float32), np.zeros(6, np.float32), rm, rv, groups=2)    # single process, global batch
+    np.testing.assert_allclose(r0["mean"].numpy(), sm, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(r0["invstd"].numpy(), si, rtol=1e-6)
