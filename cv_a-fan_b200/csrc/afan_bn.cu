@@ -623,6 +623,254 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
     cluster_wait();
 }
 
+
+// -----------------------------------------------------------------------------------------------------
+// Register-resident cluster kernels: when a CTA's slice fits in registers (<= 8 float4 per thread per
+// group, G <= 2) every element is read from HBM exactly once, ALL loads are issued up front (one DRAM
+// round trip), the statistics are folded over DSMEM, and the second sweep runs out of registers.
+// These are the kernels the ResNet-56 tail (BASELINE config 2) runs.
+// -----------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void block_reduce_k(const float (&v)[K], double* s_out, double (*s_warp)[K]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float w[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) w[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) s_warp[warp][k] = static_cast<double>(w[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double t = 0.0;
+        for (int ww = 0; ww < kClusterThreads / 32; ++ww) t += s_warp[ww][threadIdx.x];   // fixed order
+        s_out[threadIdx.x] = t;
+    }
+}
+
+template <int G, int NV, bool RELU, bool RES>
+__global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_reg_kernel(const ClusterParams p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
+    __shared__ double2 s_part[kMaxGroups];
+    __shared__ double2 s_all[kMaxGroups][kMaxCluster];
+    __shared__ double2 s_stat[kMaxGroups];
+    __shared__ float2 s_ss[kMaxGroups];
+    __shared__ double s_warp[kClusterThreads / 32][2 * G];
+    constexpr bool RES_EARLY = RES && (G * NV <= 8);
+    const unsigned int J = p.n * p.hwv;
+    const unsigned int lo = static_cast<unsigned int>(static_cast<unsigned long long>(J) * rank / cs);
+    const unsigned int hi = static_cast<unsigned int>(static_cast<unsigned long long>(J) * (rank + 1) / cs);
+    const float4* x_v = reinterpret_cast<const float4*>(p.a);
+    const float4* r_v = reinterpret_cast<const float4*>(p.b);
+    float4* y_v = reinterpret_cast<float4*>(p.out);
+    const unsigned int plane_stride = p.c * p.hwv;
+    const unsigned int group_stride = p.n * plane_stride;            // total vectors < 2^32 (checked on the host)
+
+    unsigned int rel[NV];
+    float4 a[G][NV], r[RES_EARLY ? G : 1][RES_EARLY ? NV : 1];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const unsigned int j = lo + threadIdx.x + i * kClusterThreads;
+        if (j < hi) {
+            const unsigned int nn = j / p.hwv;
+            rel[i] = ch * p.hwv + nn * plane_stride + (j - nn * p.hwv);
+        } else {
+            rel[i] = 0xffffffffu;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            a[g][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rel[i] != 0xffffffffu) {
+                a[g][i] = ld_stream(x_v + (g * group_stride + rel[i]));       // read exactly once
+                if (RES_EARLY) r[g][i] = ld_stream(r_v + (g * group_stride + rel[i]));
+            }
+        }
+    float acc[2 * G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            s0 += (a[g][i].x + a[g][i].y) + (a[g][i].z + a[g][i].w);
+            s1 = fmaf(a[g][i].x, a[g][i].x, fmaf(a[g][i].y, a[g][i].y, fmaf(a[g][i].z, a[g][i].z, fmaf(a[g][i].w, a[g][i].w, s1))));
+        }
+        acc[2 * g] = s0;
+        acc[2 * g + 1] = s1;
+    }
+    block_reduce_k<2 * G>(acc, reinterpret_cast<double*>(s_part), s_warp);
+
+    const double2 tot = cluster_fold(cluster, s_part, s_all, G);
+    if (threadIdx.x < G) {
+        const unsigned int g = threadIdx.x, gc = g * p.c + ch;
+        const double mean = tot.x / p.count;
+        double var = tot.y / p.count - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const double invstd = rsqrt(var + static_cast<double>(p.eps));
+        const float w = p.weight ? p.weight[ch] : 1.f, b = p.bias ? p.bias[ch] : 0.f;
+        s_ss[g] = make_float2(static_cast<float>(w * invstd), static_cast<float>(b - mean * w * invstd));
+        s_stat[g] = make_double2(mean, p.count > 1.0 ? var * (p.count / (p.count - 1.0)) : var);
+        if (rank == 0) {
+            p.save_mean[gc] = static_cast<float>(mean);
+            p.save_invstd[gc] = static_cast<float>(invstd);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float2 ss = s_ss[g];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (rel[i] != 0xffffffffu) {
+                float4 o;
+                o.x = fmaf(a[g][i].x, ss.x, ss.y); o.y = fmaf(a[g][i].y, ss.x, ss.y);
+                o.z = fmaf(a[g][i].z, ss.x, ss.y); o.w = fmaf(a[g][i].w, ss.x, ss.y);
+                if (RES) {
+                    const float4 rr = RES_EARLY ? r[RES_EARLY ? g : 0][RES_EARLY ? i : 0] : ld_stream(r_v + (g * group_stride + rel[i]));
+                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                }
+                if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                y_v[g * group_stride + rel[i]] = o;
+            }
+        }
+    }
+    if (rank == 0 && threadIdx.x == 0 && p.running_mean && p.running_var) {
+        float rm = p.running_mean[ch], rv = p.running_var[ch];
+        for (int g = 0; g < G; ++g)
+            for (int rr = 0; rr < p.replay; ++rr) {
+                rm = static_cast<float>((1.0 - p.momentum) * rm + p.momentum * s_stat[g].x);
+                rv = static_cast<float>((1.0 - p.momentum) * rv + p.momentum * s_stat[g].y);
+            }
+        p.running_mean[ch] = rm;
+        p.running_var[ch] = rv;
+    }
+    cluster_wait();
+}
+
+template <int G, int NV, bool RELU, bool DRES>
+__global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_reg_kernel(const ClusterParams p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
+    __shared__ double2 s_part[kMaxGroups];
+    __shared__ double2 s_all[kMaxGroups][kMaxCluster];
+    __shared__ double2 s_sum[kMaxGroups];
+    __shared__ float4 s_cf[kMaxGroups];
+    __shared__ double s_warp[kClusterThreads / 32][2 * G];
+    const unsigned int J = p.n * p.hwv;
+    const unsigned int lo = static_cast<unsigned int>(static_cast<unsigned long long>(J) * rank / cs);
+    const unsigned int hi = static_cast<unsigned int>(static_cast<unsigned long long>(J) * (rank + 1) / cs);
+    const float4* dy_v = reinterpret_cast<const float4*>(p.a);
+    const float4* x_v = reinterpret_cast<const float4*>(p.b);
+    const float4* y_v = reinterpret_cast<const float4*>(p.y);
+    float4* dx_v = reinterpret_cast<float4*>(p.out);
+    float4* dr_v = reinterpret_cast<float4*>(p.out2);
+    const unsigned int plane_stride = p.c * p.hwv;
+    const unsigned int group_stride = p.n * plane_stride;
+
+    unsigned int rel[NV];
+    float4 d[G][NV], x[G][NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const unsigned int j = lo + threadIdx.x + i * kClusterThreads;
+        if (j < hi) {
+            const unsigned int nn = j / p.hwv;
+            rel[i] = ch * p.hwv + nn * plane_stride + (j - nn * p.hwv);
+        } else {
+            rel[i] = 0xffffffffu;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            d[g][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            x[g][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rel[i] != 0xffffffffu) {
+                d[g][i] = ld_stream(dy_v + (g * group_stride + rel[i]));
+                x[g][i] = ld_stream(x_v + (g * group_stride + rel[i]));
+                if (RELU) {                                         // fold the ReLU mask into dy right away
+                    const float4 yy = ld_stream(y_v + (g * group_stride + rel[i]));
+                    if (!(yy.x > 0.f)) d[g][i].x = 0.f;
+                    if (!(yy.y > 0.f)) d[g][i].y = 0.f;
+                    if (!(yy.z > 0.f)) d[g][i].z = 0.f;
+                    if (!(yy.w > 0.f)) d[g][i].w = 0.f;
+                }
+            }
+        }
+    float acc[2 * G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float mean = p.save_mean[g * p.c + ch];
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            s0 += (d[g][i].x + d[g][i].y) + (d[g][i].z + d[g][i].w);
+            s1 = fmaf(d[g][i].x, x[g][i].x - mean, fmaf(d[g][i].y, x[g][i].y - mean,
+                 fmaf(d[g][i].z, x[g][i].z - mean, fmaf(d[g][i].w, x[g][i].w - mean, s1))));
+        }
+        acc[2 * g] = s0;
+        acc[2 * g + 1] = s1;
+    }
+    block_reduce_k<2 * G>(acc, reinterpret_cast<double*>(s_part), s_warp);
+
+    const double2 tot = cluster_fold(cluster, s_part, s_all, G);
+    if (threadIdx.x < G) {
+        const unsigned int g = threadIdx.x, gc = g * p.c + ch;
+        const float invstd = p.save_invstd[gc], w = p.weight ? p.weight[ch] : 1.f;
+        const double s_dy = tot.x, s_dyxh = tot.y * static_cast<double>(invstd);
+        s_sum[g] = make_double2(s_dy, s_dyxh);
+        s_cf[g] = make_float4(w * invstd, static_cast<float>(s_dy / p.count),
+                              static_cast<float>(s_dyxh / p.count * invstd), p.save_mean[gc]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float4 cf = s_cf[g];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (rel[i] != 0xffffffffu) {
+                float4 o;
+                o.x = cf.x * (d[g][i].x - cf.y - (x[g][i].x - cf.w) * cf.z);
+                o.y = cf.x * (d[g][i].y - cf.y - (x[g][i].y - cf.w) * cf.z);
+                o.z = cf.x * (d[g][i].z - cf.y - (x[g][i].z - cf.w) * cf.z);
+                o.w = cf.x * (d[g][i].w - cf.y - (x[g][i].w - cf.w) * cf.z);
+                dx_v[g * group_stride + rel[i]] = o;
+                if (DRES) dr_v[g * group_stride + rel[i]] = d[g][i];
+            }
+        }
+    }
+    if (rank == 0 && threadIdx.x == 0) {
+        double dw = 0.0, db = 0.0;
+        for (int g = 0; g < G; ++g) { db += s_sum[g].x; dw += s_sum[g].y; }
+        if (p.dweight) p.dweight[ch] = static_cast<float>(dw);
+        if (p.dbias) p.dbias[ch] = static_cast<float>(db);
+    }
+    cluster_wait();
+}
+
+// (cluster size, vectors per thread) for the register-resident kernels; nv == 0 -> not applicable
+struct RegPlan { int cs, nv; };
+__host__ inline RegPlan pick_reg_plan(int64_t groups, int64_t n, int64_t c, int64_t hw, bool vec, int max_gnv) {
+    RegPlan r{0, 0};
+    if (!vec || groups > 2) return r;
+    const int64_t J = n * (hw / 4);
+    int cs = 1;
+    while (cs < kMaxCluster && c * cs * 2 <= sm_count()) cs *= 2;    // whole chip in ONE wave of 1 CTA / SM
+    for (int nv = 1; nv <= 8; nv *= 2) {
+        if (static_cast<int64_t>(cs) * kClusterThreads * nv >= J) {
+            if (groups * nv > max_gnv) return r;
+            // do not spread a tiny domain over more CTAs than it can feed with >= 1 vector per thread
+            while (cs > 1 && static_cast<int64_t>(cs / 2) * kClusterThreads * nv >= J) cs /= 2;
+            r.cs = cs; r.nv = nv;
+            return r;
+        }
+    }
+    return r;
+}
+
 // cluster size: enough CTAs to cover the chip (C * CS >= ~148), power of two, <= 8, and every CTA keeps
 // >= 512 vectors per group; 0 -> shape not suited (per-channel domain too large to stay L2-resident)
 __host__ inline int pick_cluster(int64_t groups, int64_t n, int64_t c, int64_t hw, bool vec) {
@@ -795,7 +1043,8 @@ AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const flo
     if (!x || !y || !save_mean || !save_invstd) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;   // uniform contract on both paths
     const int cs = pick_cluster(groups, n, c, hw, s.vec);
-    if (cs > 0) {                                                    // single-launch cluster path
+    const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 16);
+    if (cs > 0 || rp.nv > 0) {                                       // single-launch cluster paths
         ClusterParams p{};
         p.a = x; p.b = residual; p.out = y; p.weight = weight; p.bias = bias;
         p.running_mean = running_mean; p.running_var = running_var; p.save_mean = save_mean; p.save_invstd = save_invstd;
@@ -803,13 +1052,25 @@ AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const flo
         p.eps = eps; p.momentum = momentum; p.replay = replay;
         p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
         const bool r = relu != 0, rs = residual != nullptr;
+        if (rp.nv > 0) {                                             // register-resident: x read from HBM exactly once
+#define AFAN_RF4(G_, NV_) { if (r) { if (rs) return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, true, true>, p, rp.cs, st);   \
+                                     return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, true, false>, p, rp.cs, st); }        \
+                            if (rs) return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, false, true>, p, rp.cs, st);           \
+                            return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, false, false>, p, rp.cs, st); }
+#define AFAN_RFN(G_) { switch (rp.nv) { case 1: AFAN_RF4(G_, 1) case 2: AFAN_RF4(G_, 2) case 4: AFAN_RF4(G_, 4) default: AFAN_RF4(G_, 8) } }
+            if (groups == 1) AFAN_RFN(1) else AFAN_RFN(2)
+#undef AFAN_RFN
+#undef AFAN_RF4
+        }
 #define AFAN_CF(V, R, S) return launch_cluster(bn_fwd_cluster_kernel<V, R, S>, p, cs, st)
+        if (cs <= 0) goto two_launch_fwd;
         if (s.vec) { if (r) { if (rs) AFAN_CF(4, true, true); else AFAN_CF(4, true, false); }
                      else   { if (rs) AFAN_CF(4, false, true); else AFAN_CF(4, false, false); } }
         else       { if (r) { if (rs) AFAN_CF(1, true, true); else AFAN_CF(1, true, false); }
                      else   { if (rs) AFAN_CF(1, false, true); else AFAN_CF(1, false, false); } }
 #undef AFAN_CF
     }
+two_launch_fwd:
     // large per-channel domains: two-launch path (global partials + last-CTA finalise, then apply)
     int rc = bn_fwd_reduce_impl(x, nullptr, true, weight, bias, running_mean, running_var, save_mean, save_invstd,
                                 workspace, workspace_bytes, groups, n, c, hw, eps, momentum, replay, st, &s);
@@ -912,7 +1173,8 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
     if (!dy || !x || !dx || !save_mean || !save_invstd || (relu && !y)) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
     const int cs = pick_cluster(groups * 3, n, c, hw, s.vec);        // three tensors are swept twice
-    if (cs > 0) {
+    const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 8);    // dy and x are both held: G*NV <= 8
+    if (cs > 0 || rp.nv > 0) {
         ClusterParams p{};
         p.a = dy; p.b = x; p.y = y; p.out = dx; p.out2 = dresidual; p.weight = weight;
         p.save_mean = const_cast<float*>(save_mean); p.save_invstd = const_cast<float*>(save_invstd);
@@ -920,13 +1182,24 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
         p.count = static_cast<double>(n) * static_cast<double>(hw);
         p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
         const bool r = relu != 0, dr = dresidual != nullptr;
+        if (rp.nv > 0) {
+#define AFAN_RB4(G_, NV_) { if (r) { if (dr) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, true>, p, rp.cs, st);   \
+                                     return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, false>, p, rp.cs, st); }        \
+                            if (dr) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, false, true>, p, rp.cs, st);           \
+                            return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, false, false>, p, rp.cs, st); }
+            if (groups == 1) { switch (rp.nv) { case 1: AFAN_RB4(1, 1) case 2: AFAN_RB4(1, 2) case 4: AFAN_RB4(1, 4) default: AFAN_RB4(1, 8) } }
+            else             { switch (rp.nv) { case 1: AFAN_RB4(2, 1) case 2: AFAN_RB4(2, 2) default: AFAN_RB4(2, 4) } }
+#undef AFAN_RB4
+        }
 #define AFAN_CB(V, R, S) return launch_cluster(bn_bwd_cluster_kernel<V, R, S>, p, cs, st)
+        if (cs <= 0) goto two_launch_bwd;
         if (s.vec) { if (r) { if (dr) AFAN_CB(4, true, true); else AFAN_CB(4, true, false); }
                      else   { if (dr) AFAN_CB(4, false, true); else AFAN_CB(4, false, false); } }
         else       { if (r) { if (dr) AFAN_CB(1, true, true); else AFAN_CB(1, true, false); }
                      else   { if (dr) AFAN_CB(1, false, true); else AFAN_CB(1, false, false); } }
 #undef AFAN_CB
     }
+two_launch_bwd:
     const bool al1 = aligned16(dy) && aligned16(x) && (!y || aligned16(y));
     int rc = bn_bwd_reduce_impl(dy, x, y, weight, save_mean, save_invstd, nullptr, true, dweight, dbias, workspace,
                                 workspace_bytes, groups, n, c, hw, relu, al1, st, &s);
