@@ -265,6 +265,17 @@ def kernel_rooflines(pkg, dev, reps=10):
                 "read x + write y = 8 B/elem (16 B per clean+adv pair)")
         measure(f"dual_bn bwd+relu [{tag}]", 16 * E, 16 * E, mk_bwd, bwd, lpi,
                 "read dy,x,y + write dx = 16 B/elem (12 without the ReLU mask)")
+    for tag, shape in (("cfg5 4x2048x33x33", (4, 2048, 33, 33)), ("cfg4 8x1024x38x63", (8, 1024, 38, 63)),
+                       ("4x256x128x128", (4, 256, 128, 128))):
+        E = 1
+        for d in shape:
+            E *= d
+
+        def mk():
+            cl = torch.relu(torch.randn(shape, device=dev, generator=g))
+            return dict(cl=cl, ad=cl + 0.01 * torch.randn(shape, device=dev, generator=g), out=torch.empty_like(cl))
+        measure(f"mix_feature [{tag}]", 12 * E, 12 * E, mk, lambda t: ops.mix_feature(t["cl"], t["ad"], out=t["out"]), 0,
+                "read clean, adv + write out = 12 B/elem (Seg/Det normalisation; not in the Classification step)")
     return res, peak_src
 
 

@@ -648,8 +648,10 @@ __device__ __forceinline__ void block_reduce_k(const float (&v)[K], double* s_ou
     }
 }
 
+// minBlocks = 2 (<= 64 registers) whenever the data fits: clusters of 8 only pack 16-per-chip when two CTAs
+// can share an SM (ncu: launch__cluster_max_active = 15 at one CTA per SM -> a second wave).
 template <int G, int NV, bool RELU, bool RES>
-__global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_reg_kernel(const ClusterParams p) {
+__global__ void __launch_bounds__(kClusterThreads, (G * NV <= 8) ? 2 : 1) bn_fwd_cluster_reg_kernel(const ClusterParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
     __shared__ double2 s_part[kMaxGroups];
@@ -657,7 +659,7 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_reg_kernel(con
     __shared__ double2 s_stat[kMaxGroups];
     __shared__ float2 s_ss[kMaxGroups];
     __shared__ double s_warp[kClusterThreads / 32][2 * G];
-    constexpr bool RES_EARLY = RES && (G * NV <= 8);
+    constexpr bool RES_EARLY = RES && (G * NV <= 4);   // residual prefetched with x only while it fits in 64 registers
     const unsigned int J = p.n * p.hwv;
     const unsigned int lo = static_cast<unsigned int>(static_cast<unsigned long long>(J) * rank / cs);
     const unsigned int hi = static_cast<unsigned int>(static_cast<unsigned long long>(J) * (rank + 1) / cs);
@@ -751,7 +753,7 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_reg_kernel(con
 }
 
 template <int G, int NV, bool RELU, bool DRES>
-__global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_reg_kernel(const ClusterParams p) {
+__global__ void __launch_bounds__(kClusterThreads, (G * NV <= 4) ? 2 : 1) bn_bwd_cluster_reg_kernel(const ClusterParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
     __shared__ double2 s_part[kMaxGroups];
@@ -862,6 +864,7 @@ __host__ inline RegPlan pick_reg_plan(int64_t groups, int64_t n, int64_t c, int6
     for (int nv = 1; nv <= 8; nv *= 2) {
         if (static_cast<int64_t>(cs) * kClusterThreads * nv >= J) {
             if (groups * nv > max_gnv) return r;
+            if (cs == kMaxCluster && groups * nv > max_gnv / 2) return r;   // 8-CTA clusters need 2 CTAs/SM (<= 64 regs) to pack
             // do not spread a tiny domain over more CTAs than it can feed with >= 1 vector per thread
             while (cs > 1 && static_cast<int64_t>(cs / 2) * kClusterThreads * nv >= J) cs /= 2;
             r.cs = cs; r.nv = nv;

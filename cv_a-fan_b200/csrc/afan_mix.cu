@@ -6,7 +6,7 @@
 //
 // NCHW makes the reduction dim (C) the strided one (stride H*W) while coalescing wants threads along
 // W, so a CTA owns a tile of 32*VEC consecutive pixels of one sample: lanes run along pixels (128-bit
-// loads when H*W % 4 == 0), the 16 warps split the channels.  Sweep 1 keeps one Welford state per
+// loads when H*W % 4 == 0), the 16-32 warps split the channels.  Sweep 1 keeps one Welford state per
 // (pixel, tensor) in registers -- clean and adversarial statistics in the SAME sweep -- then the warps'
 // states are merged through shared memory in a fixed order (Chan).  Sweep 2 re-reads the tile (L1/L2
 // hot: it was touched microseconds ago) and writes the mixed feature: 12 B/elem of HBM traffic.
@@ -16,9 +16,8 @@
 
 namespace afan {
 
-constexpr int kMixThreads = 512;
-constexpr int kMixWarps = kMixThreads / 32;
-constexpr int kMixUnroll = 4;                 // channels in flight per thread per tensor
+// scalar path (H*W % 4 != 0, e.g. 33x33): 1024 threads x 8 channels x 2 tensors x 4 B = 64 KB in flight per SM
+// vector path: 512 threads x 4 channels x 2 tensors x 16 B = 64 KB in flight per SM
 
 struct Welford {
     float mean = 0.f, m2 = 0.f;
@@ -29,12 +28,13 @@ struct Welford {
     }
 };
 
-template <int VEC>
+template <int VEC, int kMixThreads, int kMixUnroll>
 __global__ void __launch_bounds__(kMixThreads)
 mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ adv, float* __restrict__ out,
                    unsigned int c, unsigned int hw, unsigned int tiles_per_sample) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
     constexpr int PT = 32 * VEC;                                     // pixels per CTA tile
+    constexpr int kMixWarps = kMixThreads / 32;
     __shared__ float s_mean[2][kMixWarps][PT], s_m2[2][kMixWarps][PT];
     __shared__ float s_stat[4][PT];                                  // mean_cl, std_cl, mean_ad, std_ad
 
@@ -152,10 +152,10 @@ AFAN_EXPORT int afan_mix_feature_f32(const float* clean, const float* adv, float
     if (n * tiles >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
     const unsigned int grid = static_cast<unsigned int>(n * tiles);
     if (vec)
-        mix_feature_kernel<4><<<grid, kMixThreads, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
+        mix_feature_kernel<4, 512, 4><<<grid, 512, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
                                                            static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
     else
-        mix_feature_kernel<1><<<grid, kMixThreads, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
-                                                           static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
+        mix_feature_kernel<1, 1024, 8><<<grid, 1024, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
+                                                             static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
     return launch_status();
 }
