@@ -288,6 +288,8 @@ def main():
     ap.add_argument("--impl", default="afan_b200", choices=["afan_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--no-sync-bn", action="store_true", help="per-replica BN statistics (the reference's DataParallel behaviour)")
+    ap.add_argument("--bn-exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU dual-BN statistics: fused NVLink peer-memory exchange inside the kernel, or NCCL all-reduce")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-rooflines", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
@@ -320,7 +322,8 @@ def main():
     model = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)
     trainer = pkg.trainer.AfanTrainer(model, perturb_idx=w["perturb_idx"], steps=w["steps"], gamma=w["gamma"],
                                       eps=w["eps"], randinit=w["randinit"], clip=w["clip"], rng="philox", seed=3 + rank,
-                                      process_group=pg, sync_bn=not args.no_sync_bn, use_cuda_graph=not args.no_graph)
+                                      process_group=pg, sync_bn=not args.no_sync_bn, use_cuda_graph=not args.no_graph,
+                                      bn_exchange=args.bn_exchange)
     n = w["batch_per_gpu"]
     g = torch.Generator().manual_seed(3 + rank)              # per-rank data
     host_x = [torch.rand(n, *w["image"], generator=g).pin_memory() for _ in range(4)]
@@ -394,7 +397,8 @@ def main():
                     "h2d_bytes_per_step": (host_x[0].numel() * 4 + host_y[0].numel() * 8) * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * sec_e2e / args.steps},
             "gpu_launches": per_iter * args.steps, "afan_kernels_per_step": per_iter,
-            "cuda_graph": not args.no_graph, "sync_bn": (not args.no_sync_bn) and world > 1, "final_loss": loss_dev}
+            "cuda_graph": not args.no_graph, "sync_bn": (not args.no_sync_bn) and world > 1,
+            "bn_exchange": args.bn_exchange if ((not args.no_sync_bn) and world > 1) else None, "final_loss": loss_dev}
 
     if rank == 0 and not args.skip_rooflines:
         ks, peak_src = kernel_rooflines(pkg, dev)

@@ -36,10 +36,19 @@ SIGNATURES = {
     "afan_bn_bwd_reduce_f32": (_int, [_vp] * 8 + [_vp, _i64] + [_i64] * 4 + [_int, _vp]),
     "afan_bn_bwd_finalize_f32": (_int, [_vp, _f64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "afan_bn_bwd_apply_f32": (_int, [_vp] * 5 + [_vp, _i64] + [_i64] * 4 + [_int, _vp]),
+    "afan_bn_mailbox_bytes": (_i64, [_int, _i64]),
+    "afan_bn_fwd_p2p_f32": (_int, [_vp] * 9 + [_i64] * 4 + [_f32, _f32, _int, _int, _int, _int, _vp, _i64, _vp, _vp]),
+    "afan_bn_bwd_p2p_f32": (_int, [_vp] * 10 + [_i64] * 4 + [_int, _int, _int, _vp, _i64, _vp, _vp]),
+    "afan_p2p_alloc": (_int, [ctypes.POINTER(_vp), _i64]),
+    "afan_p2p_free": (_int, [_vp]),
+    "afan_p2p_get_handle": (_int, [_vp, _vp]),
+    "afan_p2p_open_handle": (_int, [_vp, ctypes.POINTER(_vp)]),
+    "afan_p2p_close_handle": (_int, [_vp]),
     "afan_bn_affine_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "afan_sgd_momentum_f32": (_int, [_vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp]),
 }
 
+AFAN_ERR_UNSUPPORTED = -5
 _lib = None
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); bumped by check() on success
 KERNELS_PER_CALL = {"afan_bn_fwd_f32": 2, "afan_bn_bwd_f32": 2}

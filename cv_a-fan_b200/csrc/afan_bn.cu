@@ -624,6 +624,129 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
 }
 
 
+
+// -----------------------------------------------------------------------------------------------------
+// Fused statistics exchange over NVLink peer memory (multi-GPU, one process per GPU).
+//
+// Instead of  [stats kernel] -> NCCL all-reduce -> [finalize kernel] -> [apply kernel]  the register-
+// resident cluster kernel itself exchanges the per-(group, channel) sums with the other GPUs: the rank-0
+// CTA of each cluster stores its LOCAL sums into every peer's mailbox (P2P stores over NVLink/NVSwitch),
+// publishes a per-(source rank, channel) flag with st.release.sys, spins (bounded) with ld.acquire.sys
+// until all `world` flags of its channel carry this call's sequence number, and folds the `world`
+// contributions in rank order -- every GPU adds the same numbers in the same order, so the global
+// statistics are bit-identical on all ranks.  One launch per BatchNorm direction, no NCCL call, clean and
+// adversarial statistics travel together.
+//
+// Mailbox (one per GPU, peer-mapped by cudaIpc): RING slots x [world][cmax] x {double2 data[2 groups], u64 flag}.
+// `state` (local device memory): {seq, ticket, error}.  seq counts BN calls; slot = seq % RING; the last CTA
+// of every launch increments seq.  RING >= 2 suffices: a GPU can run ahead of a peer by at most one exchange
+// (it cannot pass exchange k+1 before the peer has published k+1, i.e. finished reading k).
+// -----------------------------------------------------------------------------------------------------
+constexpr int kP2PMaxWorld = 8;
+constexpr int kP2PRing = 4;
+constexpr long long kP2PTimeoutCycles = 4000000000LL;      // ~2 s: a lost peer sets state[2] instead of hanging the GPU
+
+struct P2PParams {
+    void* peers[kP2PMaxWorld];        // peer-mapped mailbox base of every rank (peers[rank] = own mailbox)
+    unsigned long long* state;        // local: {seq, ticket, error}
+    int world, rank;
+    unsigned int cmax;
+};
+
+__host__ __device__ inline size_t p2p_data_off(unsigned int slot, unsigned int src, unsigned int ch, unsigned int g, int world,
+                                                unsigned int cmax) {
+    return (((static_cast<size_t>(slot) * world + src) * cmax + ch) * 2 + g) * sizeof(double2);
+}
+__host__ __device__ inline size_t p2p_flag_off(unsigned int slot, unsigned int src, unsigned int ch, int world, unsigned int cmax) {
+    return static_cast<size_t>(kP2PRing) * world * cmax * 2 * sizeof(double2) +
+           ((static_cast<size_t>(slot) * world + src) * cmax + ch) * sizeof(unsigned long long);
+}
+__host__ inline int64_t p2p_mailbox_bytes(int world, int64_t cmax) {
+    return static_cast<int64_t>(kP2PRing) * world * cmax * (2 * sizeof(double2) + sizeof(unsigned long long));
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_f64x2(double2* p, double2 v) {
+    asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double2 ld_sys_f64x2(const double2* p) {
+    double2 v;
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+// Cluster fold + cross-GPU fold.  Returns the GLOBAL totals in threads g < groups of EVERY CTA; the rank-0
+// CTA additionally keeps the LOCAL totals in s_loc (the backward needs them for dweight / dbias).
+__device__ __forceinline__ double2 cluster_fold_p2p(cg::cluster_group& cluster, double2* s_part,
+                                                    double2 (*s_all)[kMaxCluster], double2* s_loc, double2* s_glob,
+                                                    unsigned int groups, unsigned int ch, const P2PParams& q) {
+    const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), t = threadIdx.x;
+    cluster.sync();                                                 // #1: every CTA's s_part is published
+    if (rank == 0) {
+        if (t < groups * cs) {
+            const unsigned int g = t / cs, r = t - g * cs;
+            s_all[g][r] = *cluster.map_shared_rank(&s_part[g], r);
+        }
+        __syncthreads();
+        if (t < groups) {
+            double2 loc = make_double2(0.0, 0.0);
+            for (unsigned int r = 0; r < cs; ++r) { loc.x += s_all[t][r].x; loc.y += s_all[t][r].y; }
+            s_loc[t] = loc;
+        }
+        __syncthreads();
+        const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(q.state);
+        const unsigned int slot = static_cast<unsigned int>(seq % kP2PRing);
+        if (t < static_cast<unsigned int>(q.world) * groups) {       // P2P stores: my sums -> every GPU's mailbox
+            const unsigned int peer = t / groups, g = t - peer * groups;
+            char* base = static_cast<char*>(q.peers[peer]);
+            st_sys_f64x2(reinterpret_cast<double2*>(base + p2p_data_off(slot, q.rank, ch, g, q.world, q.cmax)), s_loc[g]);
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (t < static_cast<unsigned int>(q.world)) {
+            char* base = static_cast<char*>(q.peers[t]);
+            st_release_sys(reinterpret_cast<unsigned long long*>(base + p2p_flag_off(slot, q.rank, ch, q.world, q.cmax)), seq + 1);
+            const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(
+                static_cast<char*>(q.peers[q.rank]) + p2p_flag_off(slot, t, ch, q.world, q.cmax));
+            const long long t0 = clock64();
+            while (ld_acquire_sys(mine) != seq + 1) {
+                if (clock64() - t0 > kP2PTimeoutCycles) { q.state[2] = 1ULL; break; }     // peer lost: flag, do not hang
+                __nanosleep(20);
+            }
+        }
+        __syncthreads();
+        if (t < groups) {
+            double2 tot = make_double2(0.0, 0.0);
+            const char* base = static_cast<const char*>(q.peers[q.rank]);
+            for (int r = 0; r < q.world; ++r) {                      // rank order on every GPU -> identical totals
+                const double2 v = ld_sys_f64x2(reinterpret_cast<const double2*>(base + p2p_data_off(slot, r, ch, t, q.world, q.cmax)));
+                tot.x += v.x; tot.y += v.y;
+            }
+            s_glob[t] = tot;
+        }
+    }
+    cluster.sync();                                                 // #2: rank 0's s_glob is published
+    double2 tot = make_double2(0.0, 0.0);
+    if (t < groups) tot = *cluster.map_shared_rank(&s_glob[t], 0);
+    __syncthreads();
+    cluster_arrive();
+    return tot;
+}
+
+// the last CTA of the launch advances the call sequence (stream order makes it visible to the next BN launch)
+__device__ __forceinline__ void p2p_advance_seq(const P2PParams& q) {
+    __shared__ int s_last;
+    if (last_cta_arrives(reinterpret_cast<unsigned int*>(q.state + 1), gridDim.x, &s_last) && threadIdx.x == 0)
+        q.state[0] = q.state[0] + 1ULL;
+}
+
 // -----------------------------------------------------------------------------------------------------
 // Register-resident cluster kernels: when a CTA's slice fits in registers (<= 8 float4 per thread per
 // group, G <= 2) every element is read from HBM exactly once, ALL loads are issued up front (one DRAM
@@ -650,8 +773,9 @@ __device__ __forceinline__ void block_reduce_k(const float (&v)[K], double* s_ou
 
 // minBlocks = 2 (<= 64 registers) whenever the data fits: clusters of 8 only pack 16-per-chip when two CTAs
 // can share an SM (ncu: launch__cluster_max_active = 15 at one CTA per SM -> a second wave).
-template <int G, int NV, bool RELU, bool RES>
-__global__ void __launch_bounds__(kClusterThreads, (G * NV <= 8) ? 2 : 1) bn_fwd_cluster_reg_kernel(const ClusterParams p) {
+template <int G, int NV, bool RELU, bool RES, bool P2P = false>
+__global__ void __launch_bounds__(kClusterThreads, (G * NV <= 8) ? 2 : 1)
+bn_fwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
     __shared__ double2 s_part[kMaxGroups];
@@ -705,7 +829,9 @@ __global__ void __launch_bounds__(kClusterThreads, (G * NV <= 8) ? 2 : 1) bn_fwd
     }
     block_reduce_k<2 * G>(acc, reinterpret_cast<double*>(s_part), s_warp);
 
-    const double2 tot = cluster_fold(cluster, s_part, s_all, G);
+    __shared__ double2 s_loc[kMaxGroups], s_glob[kMaxGroups];
+    const double2 tot = P2P ? cluster_fold_p2p(cluster, s_part, s_all, s_loc, s_glob, G, ch, q)
+                            : cluster_fold(cluster, s_part, s_all, G);
     if (threadIdx.x < G) {
         const unsigned int g = threadIdx.x, gc = g * p.c + ch;
         const double mean = tot.x / p.count;
@@ -750,10 +876,12 @@ __global__ void __launch_bounds__(kClusterThreads, (G * NV <= 8) ? 2 : 1) bn_fwd
         p.running_var[ch] = rv;
     }
     cluster_wait();
+    if (P2P) p2p_advance_seq(q);
 }
 
-template <int G, int NV, bool RELU, bool DRES>
-__global__ void __launch_bounds__(kClusterThreads, (G * NV <= 4) ? 2 : 1) bn_bwd_cluster_reg_kernel(const ClusterParams p) {
+template <int G, int NV, bool RELU, bool DRES, bool P2P = false>
+__global__ void __launch_bounds__(kClusterThreads, (G * NV <= 4) ? 2 : 1)
+bn_bwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
     __shared__ double2 s_part[kMaxGroups];
@@ -818,12 +946,16 @@ __global__ void __launch_bounds__(kClusterThreads, (G * NV <= 4) ? 2 : 1) bn_bwd
     }
     block_reduce_k<2 * G>(acc, reinterpret_cast<double*>(s_part), s_warp);
 
-    const double2 tot = cluster_fold(cluster, s_part, s_all, G);
+    __shared__ double2 s_loc[kMaxGroups], s_glob[kMaxGroups];
+    const double2 tot = P2P ? cluster_fold_p2p(cluster, s_part, s_all, s_loc, s_glob, G, ch, q)
+                            : cluster_fold(cluster, s_part, s_all, G);
     if (threadIdx.x < G) {
         const unsigned int g = threadIdx.x, gc = g * p.c + ch;
         const float invstd = p.save_invstd[gc], w = p.weight ? p.weight[ch] : 1.f;
         const double s_dy = tot.x, s_dyxh = tot.y * static_cast<double>(invstd);
-        s_sum[g] = make_double2(s_dy, s_dyxh);
+        // dweight / dbias come from the LOCAL sums (the gradient all-reduce averages them with the other parameters)
+        s_sum[g] = (P2P && rank == 0) ? make_double2(s_loc[g].x, s_loc[g].y * static_cast<double>(invstd))
+                                      : make_double2(s_dy, s_dyxh);
         s_cf[g] = make_float4(w * invstd, static_cast<float>(s_dy / p.count),
                               static_cast<float>(s_dyxh / p.count * invstd), p.save_mean[gc]);
     }
@@ -851,6 +983,7 @@ __global__ void __launch_bounds__(kClusterThreads, (G * NV <= 4) ? 2 : 1) bn_bwd
         if (p.dbias) p.dbias[ch] = static_cast<float>(db);
     }
     cluster_wait();
+    if (P2P) p2p_advance_seq(q);
 }
 
 // (cluster size, vectors per thread) for the register-resident kernels; nv == 0 -> not applicable
@@ -890,8 +1023,8 @@ __host__ inline int pick_cluster(int64_t groups, int64_t n, int64_t c, int64_t h
     return cs;
 }
 
-template <typename K>
-int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st) {
+template <typename K, typename... Extra>
+int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st, const Extra&... extra) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.c * cs);
     cfg.blockDim = dim3(kClusterThreads);
@@ -901,7 +1034,7 @@ int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st) {
     attr.val.clusterDim.x = cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kernel, p) != cudaSuccess) { cudaGetLastError(); return AFAN_ERR_LAUNCH; }
+    if (cudaLaunchKernelEx(&cfg, kernel, p, extra...) != cudaSuccess) { cudaGetLastError(); return AFAN_ERR_LAUNCH; }
     return launch_status();
 }
 
@@ -1056,10 +1189,11 @@ AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const flo
         p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
         const bool r = relu != 0, rs = residual != nullptr;
         if (rp.nv > 0) {                                             // register-resident: x read from HBM exactly once
-#define AFAN_RF4(G_, NV_) { if (r) { if (rs) return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, true, true>, p, rp.cs, st);   \
-                                     return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, true, false>, p, rp.cs, st); }        \
-                            if (rs) return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, false, true>, p, rp.cs, st);           \
-                            return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, false, false>, p, rp.cs, st); }
+            const P2PParams noq{};
+#define AFAN_RF4(G_, NV_) { if (r) { if (rs) return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, true, true, false>, p, rp.cs, st, noq);   \
+                                     return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, true, false, false>, p, rp.cs, st, noq); }        \
+                            if (rs) return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, false, true, false>, p, rp.cs, st, noq);           \
+                            return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, false, false, false>, p, rp.cs, st, noq); }
 #define AFAN_RFN(G_) { switch (rp.nv) { case 1: AFAN_RF4(G_, 1) case 2: AFAN_RF4(G_, 2) case 4: AFAN_RF4(G_, 4) default: AFAN_RF4(G_, 8) } }
             if (groups == 1) AFAN_RFN(1) else AFAN_RFN(2)
 #undef AFAN_RFN
@@ -1186,10 +1320,11 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
         p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
         const bool r = relu != 0, dr = dresidual != nullptr;
         if (rp.nv > 0) {
-#define AFAN_RB4(G_, NV_) { if (r) { if (dr) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, true>, p, rp.cs, st);   \
-                                     return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, false>, p, rp.cs, st); }        \
-                            if (dr) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, false, true>, p, rp.cs, st);           \
-                            return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, false, false>, p, rp.cs, st); }
+            const P2PParams noq{};
+#define AFAN_RB4(G_, NV_) { if (r) { if (dr) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, true, false>, p, rp.cs, st, noq);   \
+                                     return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, false, false>, p, rp.cs, st, noq); }        \
+                            if (dr) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, false, true, false>, p, rp.cs, st, noq);           \
+                            return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, false, false, false>, p, rp.cs, st, noq); }
             if (groups == 1) { switch (rp.nv) { case 1: AFAN_RB4(1, 1) case 2: AFAN_RB4(1, 2) case 4: AFAN_RB4(1, 4) default: AFAN_RB4(1, 8) } }
             else             { switch (rp.nv) { case 1: AFAN_RB4(2, 1) case 2: AFAN_RB4(2, 2) default: AFAN_RB4(2, 4) } }
 #undef AFAN_RB4
@@ -1236,4 +1371,88 @@ AFAN_EXPORT int afan_bn_bwd_finalize_f32(const double* sums, double count, const
     p.groups = static_cast<unsigned int>(groups); p.c = static_cast<unsigned int>(c);
     bn_bwd_finalize_kernel<<<static_cast<unsigned int>((c + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p, sums);
     return launch_status();
+}
+
+// ---- fused multi-GPU entry points (statistics exchanged over NVLink peer memory inside the kernel) -------------
+static int fill_p2p(P2PParams& q, int world, int rank, void* const* peer_mailboxes, int64_t cmax, void* state, int64_t c) {
+    if (world < 2 || world > kP2PMaxWorld || rank < 0 || rank >= world || cmax < c) return AFAN_ERR_UNSUPPORTED;
+    if (!peer_mailboxes || !state) return AFAN_ERR_NULL;
+    for (int i = 0; i < world; ++i) {
+        if (!peer_mailboxes[i]) return AFAN_ERR_NULL;
+        q.peers[i] = peer_mailboxes[i];
+    }
+    q.state = static_cast<unsigned long long*>(state);
+    q.world = world; q.rank = rank; q.cmax = static_cast<unsigned int>(cmax);
+    return AFAN_OK;
+}
+
+AFAN_EXPORT int64_t afan_bn_mailbox_bytes(int world, int64_t cmax) {
+    if (world < 1 || world > kP2PMaxWorld || cmax < 1) return AFAN_ERR_SIZE;
+    return p2p_mailbox_bytes(world, cmax);
+}
+
+AFAN_EXPORT int afan_bn_fwd_p2p_f32(const float* x, const float* residual, const float* weight, const float* bias,
+                                    float* running_mean, float* running_var, float* y, float* save_mean,
+                                    float* save_invstd, int64_t groups, int64_t n, int64_t c, int64_t hw, float eps,
+                                    float momentum, int relu, int replay, int world, int rank,
+                                    void* const* peer_mailboxes, int64_t cmax, void* state, afan_stream_t stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool al = aligned16(x) && aligned16(y) && (!residual || aligned16(residual));
+    BnShape s = bn_shape(groups, n, c, hw, al);
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_ERR_UNSUPPORTED;                          // every rank must take part in every exchange
+    if (!x || !y || !save_mean || !save_invstd) return AFAN_ERR_NULL;
+    const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 16);
+    if (rp.nv == 0) return AFAN_ERR_UNSUPPORTED;                     // caller falls back to stats -> NCCL -> finalize -> apply
+    P2PParams q{};
+    int rc = fill_p2p(q, world, rank, peer_mailboxes, cmax, state, c);
+    if (rc != AFAN_OK) return rc;
+    ClusterParams p{};
+    p.a = x; p.b = residual; p.out = y; p.weight = weight; p.bias = bias;
+    p.running_mean = running_mean; p.running_var = running_var; p.save_mean = save_mean; p.save_invstd = save_invstd;
+    p.count = static_cast<double>(n) * static_cast<double>(hw) * world;   // GLOBAL count
+    p.eps = eps; p.momentum = momentum; p.replay = replay;
+    p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
+    const bool r = relu != 0, rs = residual != nullptr;
+#define AFAN_PF4(G_, NV_) { if (r) { if (rs) return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, true, true, true>, p, rp.cs, st, q);   \
+                                     return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, true, false, true>, p, rp.cs, st, q); }        \
+                            if (rs) return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, false, true, true>, p, rp.cs, st, q);           \
+                            return launch_cluster(bn_fwd_cluster_reg_kernel<G_, NV_, false, false, true>, p, rp.cs, st, q); }
+#define AFAN_PFN(G_) { switch (rp.nv) { case 1: AFAN_PF4(G_, 1) case 2: AFAN_PF4(G_, 2) case 4: AFAN_PF4(G_, 4) default: AFAN_PF4(G_, 8) } }
+    if (groups == 1) AFAN_PFN(1) else AFAN_PFN(2)
+#undef AFAN_PFN
+#undef AFAN_PF4
+}
+
+AFAN_EXPORT int afan_bn_bwd_p2p_f32(const float* dy, const float* x, const float* y, const float* weight,
+                                    const float* save_mean, const float* save_invstd, float* dx, float* dresidual,
+                                    float* dweight, float* dbias, int64_t groups, int64_t n, int64_t c, int64_t hw,
+                                    int relu, int world, int rank, void* const* peer_mailboxes, int64_t cmax,
+                                    void* state, afan_stream_t stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool al = aligned16(dy) && aligned16(x) && aligned16(dx) && (!y || aligned16(y)) &&
+                    (!dresidual || aligned16(dresidual));
+    BnShape s = bn_shape(groups, n, c, hw, al);
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_ERR_UNSUPPORTED;
+    if (!dy || !x || !dx || !save_mean || !save_invstd || (relu && !y)) return AFAN_ERR_NULL;
+    const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 8);
+    if (rp.nv == 0) return AFAN_ERR_UNSUPPORTED;
+    P2PParams q{};
+    int rc = fill_p2p(q, world, rank, peer_mailboxes, cmax, state, c);
+    if (rc != AFAN_OK) return rc;
+    ClusterParams p{};
+    p.a = dy; p.b = x; p.y = y; p.out = dx; p.out2 = dresidual; p.weight = weight;
+    p.save_mean = const_cast<float*>(save_mean); p.save_invstd = const_cast<float*>(save_invstd);
+    p.dweight = dweight; p.dbias = dbias;
+    p.count = static_cast<double>(n) * static_cast<double>(hw) * world;
+    p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
+    const bool r = relu != 0, dr = dresidual != nullptr;
+#define AFAN_PB4(G_, NV_) { if (r) { if (dr) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, true, true>, p, rp.cs, st, q);   \
+                                     return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, false, true>, p, rp.cs, st, q); }        \
+                            if (dr) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, false, true, true>, p, rp.cs, st, q);           \
+                            return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, false, false, true>, p, rp.cs, st, q); }
+    if (groups == 1) { switch (rp.nv) { case 1: AFAN_PB4(1, 1) case 2: AFAN_PB4(1, 2) case 4: AFAN_PB4(1, 4) default: AFAN_PB4(1, 8) } }
+    else             { switch (rp.nv) { case 1: AFAN_PB4(2, 1) case 2: AFAN_PB4(2, 2) default: AFAN_PB4(2, 4) } }
+#undef AFAN_PB4
 }

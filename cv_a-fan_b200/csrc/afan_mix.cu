@@ -154,8 +154,11 @@ AFAN_EXPORT int afan_mix_feature_f32(const float* clean, const float* adv, float
     if (vec)
         mix_feature_kernel<4, 512, 4><<<grid, 512, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
                                                            static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
-    else
+    else if (grid < 2u * static_cast<unsigned int>(sm_count()))        // few tiles: one fat CTA per SM keeps 64 KB in flight
         mix_feature_kernel<1, 1024, 8><<<grid, 1024, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
                                                              static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
+    else                                                             // many tiles: 3 x 512-thread CTAs per SM
+        mix_feature_kernel<1, 512, 8><<<grid, 512, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
+                                                           static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
     return launch_status();
 }

@@ -19,14 +19,14 @@ from ._lib import AfanError
 class _DualBNTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, ws, groups, eps, momentum, relu, replay,
-                process_group):
+                process_group, mailbox):
         x = x.contiguous()
         res = residual.contiguous() if residual is not None else None
         y, save_mean, save_invstd = ops.bn_fwd(x, res, weight, bias, running_mean, running_var, ws, groups=groups,
                                                eps=eps, momentum=momentum, relu=relu, replay=replay,
-                                               process_group=process_group)
+                                               process_group=process_group, mailbox=mailbox)
         ctx.save_for_backward(x, y if relu else None, weight, save_mean, save_invstd)
-        ctx.ws, ctx.groups, ctx.relu, ctx.has_res, ctx.pg = ws, groups, relu, residual is not None, process_group
+        ctx.ws, ctx.groups, ctx.relu, ctx.has_res, ctx.pg, ctx.mailbox = ws, groups, relu, residual is not None, process_group, mailbox
         return y
 
     @staticmethod
@@ -35,9 +35,9 @@ class _DualBNTrainFn(torch.autograd.Function):
         want_res = ctx.has_res and ctx.needs_input_grad[1]
         dx, dres, dw, db = ops.bn_bwd(dy.contiguous(), x, y, weight, save_mean, save_invstd, ctx.ws,
                                       groups=ctx.groups, relu=ctx.relu, want_dresidual=want_res,
-                                      process_group=ctx.pg)
+                                      process_group=ctx.pg, mailbox=ctx.mailbox)
         return (dx, dres, dw if ctx.needs_input_grad[2] else None, db if ctx.needs_input_grad[3] else None,
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None)
 
 
 class _AffineEvalFn(torch.autograd.Function):
@@ -73,6 +73,7 @@ class DualBatchNorm2d(nn.Module):
         self._ws = {}                  # groups -> workspace tensor (device scratch owned by this module)
         self._pending_batches = 0      # host-side count, folded into num_batches_tracked lazily (no launch per pass)
         self.process_group = None      # set by the trainer for NCCL-synchronised statistics
+        self.mailbox = None            # p2p.PeerMailbox: statistics exchanged over NVLink inside the kernel instead
         self._register_state_dict_hook(_flush_hook)
 
     def _workspace(self, groups: int, device):
@@ -94,7 +95,7 @@ class DualBatchNorm2d(nn.Module):
             self._pending_batches += groups * replay
             return _DualBNTrainFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                                         self._workspace(groups, x.device), groups, self.eps, self.momentum, relu,
-                                        replay, self.process_group)
+                                        replay, self.process_group, self.mailbox)
         invstd = torch.rsqrt(self.running_var + self.eps)
         scale = self.weight.detach() * invstd
         scale_shift = torch.stack((scale, self.bias.detach() - self.running_mean * scale), dim=1).contiguous()

@@ -137,7 +137,7 @@ def _ws_bytes(ws):
 
 
 def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1, eps=1e-5, momentum=0.1,
-           relu=False, replay=1, process_group=None, split=False):
+           relu=False, replay=1, process_group=None, split=False, mailbox=None):
     """Train-mode grouped-statistics BN (+residual, +ReLU).  Returns (y, save_mean[G,C], save_invstd[G,C]).
     With a process group of size > 1 the per-(group, channel) sums are all-reduced over NCCL in ONE
     message for all groups between the statistics kernel and the apply kernel."""
@@ -147,6 +147,15 @@ def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1
     save_mean = torch.empty((groups, c), dtype=torch.float32, device=x.device)
     save_invstd = torch.empty_like(save_mean)
     world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    if mailbox is not None and not split:                    # fused: statistics exchanged over NVLink inside the kernel
+        rc = L.afan_bn_fwd_p2p_f32(f32(x), f32(residual), f32(weight), f32(bias), f32(running_mean), f32(running_var),
+                                   f32(y), f32(save_mean), f32(save_invstd), groups, n, c, hw, float(eps), float(momentum),
+                                   int(bool(relu)), int(replay), mailbox.world, mailbox.rank, mailbox.peer_ptrs,
+                                   mailbox.cmax, ptr(mailbox.state), stream())
+        if rc != _lib.AFAN_ERR_UNSUPPORTED:
+            check(rc, "afan_bn_fwd_p2p_f32")
+            return y, save_mean, save_invstd
+        world = mailbox.world                                # shape not cluster-resident: same decision on every rank
     if world == 1 and not split:
         check(L.afan_bn_fwd_f32(f32(x), f32(residual), f32(weight), f32(bias), f32(running_mean), f32(running_var),
                                 f32(y), f32(save_mean), f32(save_invstd), ptr(ws), _ws_bytes(ws), groups, n, c, hw,
@@ -166,7 +175,7 @@ def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1
 
 
 def bn_bwd(dy, x, y, weight, save_mean, save_invstd, ws, *, groups=1, relu=False, want_dresidual=False,
-           process_group=None, split=False):
+           process_group=None, split=False, mailbox=None):
     """Backward of bn_fwd.  Returns (dx, dresidual|None, dweight[C], dbias[C]) (dweight/dbias are LOCAL sums;
     the data-parallel gradient all-reduce averages them with the other parameters)."""
     n, c, hw = _nchw(x, groups)
@@ -176,6 +185,14 @@ def bn_bwd(dy, x, y, weight, save_mean, save_invstd, ws, *, groups=1, relu=False
     dweight = torch.empty(c, dtype=torch.float32, device=x.device)
     dbias = torch.empty_like(dweight)
     world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    if mailbox is not None and not split:
+        rc = L.afan_bn_bwd_p2p_f32(f32(dy), f32(x), f32(y) if relu else None, f32(weight), f32(save_mean), f32(save_invstd),
+                                   f32(dx), f32(dres), f32(dweight), f32(dbias), groups, n, c, hw, int(bool(relu)),
+                                   mailbox.world, mailbox.rank, mailbox.peer_ptrs, mailbox.cmax, ptr(mailbox.state), stream())
+        if rc != _lib.AFAN_ERR_UNSUPPORTED:
+            check(rc, "afan_bn_bwd_p2p_f32")
+            return dx, dres, dweight, dbias
+        world = mailbox.world
     if world == 1 and not split:
         check(L.afan_bn_bwd_f32(f32(dy), f32(x), f32(y) if relu else None, f32(weight), f32(save_mean),
                                 f32(save_invstd), f32(dx), f32(dres), f32(dweight), f32(dbias), ptr(ws), _ws_bytes(ws),

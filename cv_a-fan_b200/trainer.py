@@ -33,7 +33,7 @@ class AfanTrainer:
                  eps: float = 2.0, randinit: bool = False, clip: bool = False, lr: float = 0.1,
                  momentum: float = 0.9, weight_decay: float = 5e-4, norm: str = "linf", rng: str = "philox",
                  seed: int = 0, criterion: Optional[nn.Module] = None, process_group=None, sync_bn: bool = True,
-                 head_cache: bool = True, use_cuda_graph: bool = True):
+                 head_cache: bool = True, use_cuda_graph: bool = True, bn_exchange: str = "p2p"):
         """gamma / eps are in 1/255 units like the reference flags (main_perturb.py:180,183)."""
         self.model, self.k, self.L = model, int(perturb_idx), len(model.sequential_model)
         self.steps, self.gamma, self.eps = int(steps), gamma / 255.0, eps / 255.0
@@ -46,10 +46,18 @@ class AfanTrainer:
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise AfanError("AfanTrainer needs the model on a CUDA device: there is no CPU path")
+        self.mailbox = None
         if sync_bn and self.world > 1:
+            if bn_exchange == "p2p":                 # fused exchange over NVLink peer memory inside the BN kernels
+                from .p2p import PeerMailbox
+                cmax = max(m.num_features for m in model.modules() if isinstance(m, DualBatchNorm2d))
+                self.mailbox = PeerMailbox(process_group, self.device, cmax=cmax)
+            elif bn_exchange != "nccl":
+                raise AfanError(f"bn_exchange must be 'p2p' or 'nccl', got {bn_exchange!r}")
             for m in model.modules():
                 if isinstance(m, DualBatchNorm2d):
                     m.process_group = process_group
+                    m.mailbox = self.mailbox
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
         self._lr = float(lr)
         self.rng_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
@@ -232,6 +240,8 @@ class AfanTrainer:
         torch.cuda.synchronize(self.device)
         self._graph = None
         self._static = {}
+        if self.mailbox is not None:
+            self.mailbox.check()
 
     # ---- evaluation (main_perturb.py:227-262) ---------------------------------------------------------
     @torch.no_grad()

@@ -140,6 +140,35 @@ int afan_bn_bwd_finalize_f32(const double* sums, double count, const float* weig
 int afan_bn_bwd_apply_f32(const float* dy, const float* x, const float* y, float* dx, float* dresidual,
                           const void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n,
                           int64_t c, int64_t hw, int relu, afan_stream_t stream);
+/* Fused multi-GPU form (one process per GPU): the kernel itself exchanges the per-(group, channel) sums with the
+ * other GPUs over NVLink peer memory -- P2P stores into every peer's mailbox, st.release.sys flag, bounded
+ * ld.acquire.sys spin, fold in rank order (bit-identical statistics on all ranks) -- and then normalises.  ONE
+ * launch per BatchNorm direction and no NCCL call; replaces stats -> all-reduce -> finalize -> apply.
+ *   peer_mailboxes: HOST array of `world` device pointers, [i] = rank i's mailbox mapped into this process
+ *                   (afan_p2p_* below); each mailbox is afan_bn_mailbox_bytes(world, cmax) bytes, zeroed.
+ *   state:          LOCAL device memory, 3 x uint64 {call sequence, ticket, error}, zeroed once.  error != 0
+ *                   after a launch means a peer did not arrive within ~2 s (the kernel never hangs).
+ * Every rank must issue the same sequence of calls.  AFAN_ERR_UNSUPPORTED (shape does not fit the
+ * register-resident cluster kernel) is returned identically on all ranks: fall back to the split form. */
+int64_t afan_bn_mailbox_bytes(int world, int64_t cmax);
+int afan_bn_fwd_p2p_f32(const float* x, const float* residual, const float* weight, const float* bias,
+                        float* running_mean, float* running_var, float* y, float* save_mean,
+                        float* save_invstd, int64_t groups, int64_t n, int64_t c, int64_t hw, float eps,
+                        float momentum, int relu, int replay, int world, int rank,
+                        void* const* peer_mailboxes, int64_t cmax, void* state, afan_stream_t stream);
+int afan_bn_bwd_p2p_f32(const float* dy, const float* x, const float* y, const float* weight,
+                        const float* save_mean, const float* save_invstd, float* dx, float* dresidual,
+                        float* dweight, float* dbias, int64_t groups, int64_t n, int64_t c, int64_t hw,
+                        int relu, int world, int rank, void* const* peer_mailboxes, int64_t cmax,
+                        void* state, afan_stream_t stream);
+/* Peer-mapped device memory (cudaMalloc + cudaIpc): alloc zeroes the buffer; handles are 64 opaque bytes that the
+ * host exchanges between the processes of one node; open maps a peer's buffer (NVLink P2P enabled lazily). */
+int afan_p2p_alloc(void** ptr, int64_t bytes);
+int afan_p2p_free(void* ptr);
+int afan_p2p_get_handle(void* ptr, void* handle_out_64);
+int afan_p2p_open_handle(const void* handle_64, void** ptr_out);
+int afan_p2p_close_handle(void* ptr);
+
 /* Inference-mode affine (+residual, +relu) with a caller-supplied per-channel scale/shift table
  * (float [c][2]); used for model.eval() (main_perturb.py:232-246). */
 int afan_bn_affine_f32(const float* x, const float* residual, const float* scale_shift, float* y,

@@ -20,6 +20,7 @@ def main():
     faulthandler.dump_traceback_later(int(os.environ.get("AFAN_HANG_DUMP_S", "120")), exit=True)   # never hang a GPU box
     use_graph = "--graph" in sys.argv
     sync_bn = "--no-sync-bn" not in sys.argv
+    exchange = "nccl" if "--nccl" in sys.argv else "p2p"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -38,7 +39,8 @@ def main():
     torch.manual_seed(3)
     model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
     init = {k: v.clone() for k, v in model.state_dict().items()}
-    tr = pkg.trainer.AfanTrainer(model, process_group=dist.group.WORLD, sync_bn=sync_bn, use_cuda_graph=use_graph, **kw)
+    tr = pkg.trainer.AfanTrainer(model, process_group=dist.group.WORLD, sync_bn=sync_bn, use_cuda_graph=use_graph,
+                                 bn_exchange=exchange, **kw)
     print(f'[rank {rank}] trainer built', flush=True)
     sl = slice(rank * per_rank, (rank + 1) * per_rank)
     losses = []
@@ -80,7 +82,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"MULTI_GPU_CHECK world={world} graph={use_graph} losses={losses} ref={ref_losses} worst={worst} "
+        print(f"MULTI_GPU_CHECK world={world} graph={use_graph} exchange={exchange} losses={losses} ref={ref_losses} worst={worst} "
               f"{'OK' if int(flag) else 'FAIL'}")
     tr.close()
     ref.close()

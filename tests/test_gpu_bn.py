@@ -116,3 +116,53 @@ def test_bn_rejects_bad_inputs():
     with pytest.raises(PKG.AfanError):      # workspace too small
         ops.bn_fwd(torch.zeros(4, 4, 2, 2, device=d), None, None, None, None, None,
                    torch.zeros(2, dtype=torch.int64, device=d), groups=2)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 32, 16, 16), (1, 32, 64, 8, 8), (2, 8, 64, 8, 8)])
+def test_fused_p2p_exchange_loopback_two_virtual_ranks(case):
+    """The fused statistics exchange (P2P stores + release/acquire flags inside the BN kernel), exercised on ONE GPU:
+    two virtual ranks on two streams with mailboxes in local memory.  Each rank normalises its shard with the
+    statistics of the GLOBAL batch; the oracle is single-process BN over the global batch."""
+    G, n_loc, C, H, W = case
+    world, d = 2, dev()
+    g = torch.Generator().manual_seed(17)
+    n_glob = n_loc * world
+    x = torch.randn(G * n_glob, C, H, W, generator=g) * 1.3 + 0.2
+    dy = torch.randn(x.shape, generator=g)
+    wt, b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    shard = lambda t, r: torch.cat([t[gi * n_glob + r * n_loc: gi * n_glob + (r + 1) * n_loc] for gi in range(G)]).contiguous()
+    boxes = PKG.p2p.PeerMailbox.loopback(world, d, cmax=C)
+    streams = [torch.cuda.Stream(device=d) for _ in range(world)]
+    outs = [None] * world
+    xs = [shard(x, r).to(d) for r in range(world)]
+    dys = [shard(dy, r).to(d) for r in range(world)]
+    rms = [torch.zeros(C, device=d) for _ in range(world)]
+    rvs = [torch.ones(C, device=d) for _ in range(world)]
+    wss = [ops.bn_workspace(G, C, d) for _ in range(world)]
+    torch.cuda.synchronize()
+    for rep in range(3):                                    # several calls: exercises the sequence / ring logic
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                y, sm, si = ops.bn_fwd(xs[r], None, wt.to(d), b.to(d), rms[r], rvs[r], wss[r], groups=G, relu=True, mailbox=boxes[r])
+                outs[r] = (y, sm, si) + ops.bn_bwd(dys[r], xs[r], y, wt.to(d), sm, si, wss[r], groups=G, relu=True, mailbox=boxes[r])
+        torch.cuda.synchronize()
+        for bx in boxes:
+            bx.check()
+    assert int(boxes[0].state[0]) == 6 and int(boxes[1].state[0]) == 6          # 3 x (fwd + bwd) calls counted
+    rm_o, rv_o = np.zeros(C, np.float32), np.ones(C, np.float32)
+    for _ in range(3):
+        y_o, sm_o, si_o = orc.bn_fwd(x.numpy(), wt.numpy(), b.numpy(), rm_o, rv_o, groups=G, relu=True)
+    dx_o, _, dw_o, db_o = orc.bn_bwd(dy.numpy(), x.numpy(), y_o, wt.numpy(), sm_o, si_o, groups=G, relu=True)
+    dw_sum, db_sum = 0, 0
+    for r in range(world):
+        y, sm, si, dx, _, dw, db = outs[r]
+        np.testing.assert_allclose(y.cpu().numpy(), shard(torch.from_numpy(y_o), r).numpy(), rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(sm.cpu().numpy(), sm_o, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(dx.cpu().numpy(), shard(torch.from_numpy(dx_o), r).numpy(), rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(rvs[r].cpu().numpy(), rv_o, rtol=1e-5, atol=1e-6)
+        dw_sum, db_sum = dw_sum + dw.cpu().numpy(), db_sum + db.cpu().numpy()
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])   # bit-identical statistics on all ranks
+    np.testing.assert_allclose(dw_sum, dw_o, rtol=1e-4, atol=1e-3)              # local dweight/dbias sum to the global ones
+    np.testing.assert_allclose(db_sum, db_o, rtol=1e-4, atol=1e-3)
+    for bx in boxes:
+        bx.close()
