@@ -279,6 +279,46 @@ def kernel_rooflines(pkg, dev, reps=10):
     return res, peak_src
 
 
+def exchange_microbench(pkg, dev, mailbox, pg, calls=100):
+    """N>1 only, every rank: per-call device time of the dual-BN forward at a tail shape (G1 128x32x16x16) with the
+    fused NVLink exchange, with the NCCL split form, and without any exchange (graph of `calls` back-to-back launches)."""
+    ops = pkg.ops
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(128, 32, 16, 16, device=dev, generator=g)
+    w, b = torch.ones(32, device=dev), torch.zeros(32, device=dev)
+    rm, rv = torch.zeros(32, device=dev), torch.ones(32, device=dev)
+    ws = ops.bn_workspace(1, 32, dev)
+    side = torch.cuda.Stream(device=dev)
+    out = {}
+    for name, kw in (("local_no_exchange", {}), ("fused_nvlink_p2p", dict(mailbox=mailbox)), ("nccl_split", dict(process_group=pg))):
+        if name == "fused_nvlink_p2p" and mailbox is None:
+            continue
+        run = lambda: ops.bn_fwd(x, None, w, b, rm, rv, ws, groups=1, relu=True, **kw)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.distributed.barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(calls):
+                run()
+        graph.replay()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(5):
+            graph.replay()
+        e0.record()
+        e0.synchronize()
+        out[name] = s0.elapsed_time(e0) * 1e3 / (5 * calls)
+        torch.distributed.barrier()
+        del graph
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -411,6 +451,8 @@ def main():
         line["kernels"] = ks
     if world > 1:
         torch.distributed.barrier()
+        if not args.no_sync_bn:
+            line["bn_fwd_us_per_call_G1_128x32x16x16"] = exchange_microbench(pkg, dev, trainer.mailbox, pg)
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         cb = cpu_reference(steps=4, warmup=1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

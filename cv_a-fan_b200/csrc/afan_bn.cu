@@ -630,14 +630,13 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
 //
 // Instead of  [stats kernel] -> NCCL all-reduce -> [finalize kernel] -> [apply kernel]  the register-
 // resident cluster kernel itself exchanges the per-(group, channel) sums with the other GPUs: the rank-0
-// CTA of each cluster stores its LOCAL sums into every peer's mailbox (P2P stores over NVLink/NVSwitch),
-// publishes a per-(source rank, channel) flag with st.release.sys, spins (bounded) with ld.acquire.sys
-// until all `world` flags of its channel carry this call's sequence number, and folds the `world`
-// contributions in rank order -- every GPU adds the same numbers in the same order, so the global
+// CTA of each cluster stores its LOCAL sums into every peer's mailbox (P2P stores over NVLink/NVSwitch)
+// as self-validating words with in-band tags, spins (bounded) until the `world` contributions of its
+// channel carry this call's tag, and folds them in rank order -- every GPU adds the same numbers in the same order, so the global
 // statistics are bit-identical on all ranks.  One launch per BatchNorm direction, no NCCL call, clean and
 // adversarial statistics travel together.
 //
-// Mailbox (one per GPU, peer-mapped by cudaIpc): RING slots x [world][cmax] x {double2 data[2 groups], u64 flag}.
+// Mailbox (one per GPU, peer-mapped by cudaIpc): RING slots x [world][cmax] x [2 groups][2 sums] 16-byte words.
 // `state` (local device memory): {seq, ticket, error}.  seq counts BN calls; slot = seq % RING; the last CTA
 // of every launch increments seq.  RING >= 2 suffices: a GPU can run ahead of a peer by at most one exchange
 // (it cannot pass exchange k+1 before the peer has published k+1, i.e. finished reading k).
@@ -653,32 +652,23 @@ struct P2PParams {
     unsigned int cmax;
 };
 
-__host__ __device__ inline size_t p2p_data_off(unsigned int slot, unsigned int src, unsigned int ch, unsigned int g, int world,
-                                                unsigned int cmax) {
-    return (((static_cast<size_t>(slot) * world + src) * cmax + ch) * 2 + g) * sizeof(double2);
-}
-__host__ __device__ inline size_t p2p_flag_off(unsigned int slot, unsigned int src, unsigned int ch, int world, unsigned int cmax) {
-    return static_cast<size_t>(kP2PRing) * world * cmax * 2 * sizeof(double2) +
-           ((static_cast<size_t>(slot) * world + src) * cmax + ch) * sizeof(unsigned long long);
+// LL-style in-band flags (the idea of NCCL's low-latency protocol): every double travels as one 16-byte word
+// {lo32, tag, hi32, tag}; each 8-byte half carries its own tag, so the word is self-validating however the
+// fabric splits the store -- no fence, no separate flag, ONE one-way NVLink latency per exchange.
+// word index: ((((slot * world + src) * cmax + ch) * 2 + g) * 2 + k),  k = 0: first sum, 1: second sum.
+__host__ __device__ inline size_t p2p_word_off(unsigned int slot, unsigned int src, unsigned int ch, unsigned int g, unsigned int k,
+                                               int world, unsigned int cmax) {
+    return ((((static_cast<size_t>(slot) * world + src) * cmax + ch) * 2 + g) * 2 + k) * sizeof(uint4);
 }
 __host__ inline int64_t p2p_mailbox_bytes(int world, int64_t cmax) {
-    return static_cast<int64_t>(kP2PRing) * world * cmax * (2 * sizeof(double2) + sizeof(unsigned long long));
+    return static_cast<int64_t>(kP2PRing) * world * cmax * 4 * sizeof(uint4);
 }
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_sys_u32x4(uint4* p, uint4 v) {
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_sys_f64x2(double2* p, double2 v) {
-    asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ double2 ld_sys_f64x2(const double2* p) {
-    double2 v;
-    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_sys_u32x4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 
@@ -687,6 +677,7 @@ __device__ __forceinline__ double2 ld_sys_f64x2(const double2* p) {
 __device__ __forceinline__ double2 cluster_fold_p2p(cg::cluster_group& cluster, double2* s_part,
                                                     double2 (*s_all)[kMaxCluster], double2* s_loc, double2* s_glob,
                                                     unsigned int groups, unsigned int ch, const P2PParams& q) {
+    __shared__ double s_recv[kP2PMaxWorld][2][2];                   // [src rank][group][k]
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), t = threadIdx.x;
     cluster.sync();                                                 // #1: every CTA's s_part is published
     if (rank == 0) {
@@ -703,32 +694,31 @@ __device__ __forceinline__ double2 cluster_fold_p2p(cg::cluster_group& cluster, 
         __syncthreads();
         const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(q.state);
         const unsigned int slot = static_cast<unsigned int>(seq % kP2PRing);
-        if (t < static_cast<unsigned int>(q.world) * groups) {       // P2P stores: my sums -> every GPU's mailbox
-            const unsigned int peer = t / groups, g = t - peer * groups;
-            char* base = static_cast<char*>(q.peers[peer]);
-            st_sys_f64x2(reinterpret_cast<double2*>(base + p2p_data_off(slot, q.rank, ch, g, q.world, q.cmax)), s_loc[g]);
-            __threadfence_system();
-        }
-        __syncthreads();
-        if (t < static_cast<unsigned int>(q.world)) {
-            char* base = static_cast<char*>(q.peers[t]);
-            st_release_sys(reinterpret_cast<unsigned long long*>(base + p2p_flag_off(slot, q.rank, ch, q.world, q.cmax)), seq + 1);
-            const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(
-                static_cast<char*>(q.peers[q.rank]) + p2p_flag_off(slot, t, ch, q.world, q.cmax));
+        const unsigned int tag = static_cast<unsigned int>(seq % 0xfffffffeULL) + 1u;     // never 0 (mailboxes start zeroed)
+        const unsigned int words = static_cast<unsigned int>(q.world) * groups * 2;
+        if (t < words) {
+            const unsigned int peer = t / (groups * 2), rem = t - peer * groups * 2, g = rem >> 1, k = rem & 1;
+            // publish: my local sums -> every GPU's mailbox (P2P store over NVLink; peer == my rank is a local store)
+            const double v = k ? s_loc[g].y : s_loc[g].x;
+            const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+            uint4 w;
+            w.x = static_cast<unsigned int>(bits); w.y = tag; w.z = static_cast<unsigned int>(bits >> 32); w.w = tag;
+            st_sys_u32x4(reinterpret_cast<uint4*>(static_cast<char*>(q.peers[peer]) + p2p_word_off(slot, q.rank, ch, g, k, q.world, q.cmax)), w);
+            // collect: rank `peer`'s sums from MY mailbox (bounded spin on the in-band tags)
+            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const char*>(q.peers[q.rank]) +
+                                                             p2p_word_off(slot, peer, ch, g, k, q.world, q.cmax));
             const long long t0 = clock64();
-            while (ld_acquire_sys(mine) != seq + 1) {
-                if (clock64() - t0 > kP2PTimeoutCycles) { q.state[2] = 1ULL; break; }     // peer lost: flag, do not hang
-                __nanosleep(20);
+            uint4 r = ld_sys_u32x4(src);
+            while (r.y != tag || r.w != tag) {
+                if (clock64() - t0 > kP2PTimeoutCycles) { q.state[2] = 1ULL; break; }     // peer lost: flag it, never hang
+                r = ld_sys_u32x4(src);
             }
+            s_recv[peer][g][k] = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(r.z) << 32) | r.x));
         }
         __syncthreads();
         if (t < groups) {
             double2 tot = make_double2(0.0, 0.0);
-            const char* base = static_cast<const char*>(q.peers[q.rank]);
-            for (int r = 0; r < q.world; ++r) {                      // rank order on every GPU -> identical totals
-                const double2 v = ld_sys_f64x2(reinterpret_cast<const double2*>(base + p2p_data_off(slot, r, ch, t, q.world, q.cmax)));
-                tot.x += v.x; tot.y += v.y;
-            }
+            for (int r = 0; r < q.world; ++r) { tot.x += s_recv[r][t][0]; tot.y += s_recv[r][t][1]; }   // rank order everywhere
             s_glob[t] = tot;
         }
     }

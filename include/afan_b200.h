@@ -141,8 +141,9 @@ int afan_bn_bwd_apply_f32(const float* dy, const float* x, const float* y, float
                           const void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n,
                           int64_t c, int64_t hw, int relu, afan_stream_t stream);
 /* Fused multi-GPU form (one process per GPU): the kernel itself exchanges the per-(group, channel) sums with the
- * other GPUs over NVLink peer memory -- P2P stores into every peer's mailbox, st.release.sys flag, bounded
- * ld.acquire.sys spin, fold in rank order (bit-identical statistics on all ranks) -- and then normalises.  ONE
+ * other GPUs over NVLink peer memory -- P2P stores of self-validating {lo, tag, hi, tag} words into every peer's
+ * mailbox (no fence, one one-way NVLink latency), bounded spin on the in-band tags, fold in rank order
+ * (bit-identical statistics on all ranks) -- and then normalises.  ONE
  * launch per BatchNorm direction and no NCCL call; replaces stats -> all-reduce -> finalize -> apply.
  *   peer_mailboxes: HOST array of `world` device pointers, [i] = rank i's mailbox mapped into this process
  *                   (afan_p2p_* below); each mailbox is afan_bn_mailbox_bytes(world, cmax) bytes, zeroed.
