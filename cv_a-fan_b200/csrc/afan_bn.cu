@@ -676,7 +676,8 @@ __device__ __forceinline__ uint4 ld_sys_u32x4(const uint4* p) {
 // CTA additionally keeps the LOCAL totals in s_loc (the backward needs them for dweight / dbias).
 __device__ __forceinline__ double2 cluster_fold_p2p(cg::cluster_group& cluster, double2* s_part,
                                                     double2 (*s_all)[kMaxCluster], double2* s_loc, double2* s_glob,
-                                                    unsigned int groups, unsigned int ch, const P2PParams& q) {
+                                                    unsigned int groups, unsigned int ch, const P2PParams& q,
+                                                    unsigned long long seq) {
     __shared__ double s_recv[kP2PMaxWorld][2][2];                   // [src rank][group][k]
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), t = threadIdx.x;
     cluster.sync();                                                 // #1: every CTA's s_part is published
@@ -692,7 +693,6 @@ __device__ __forceinline__ double2 cluster_fold_p2p(cg::cluster_group& cluster, 
             s_loc[t] = loc;
         }
         __syncthreads();
-        const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(q.state);
         const unsigned int slot = static_cast<unsigned int>(seq % kP2PRing);
         const unsigned int tag = static_cast<unsigned int>(seq % 0xfffffffeULL) + 1u;     // never 0 (mailboxes start zeroed)
         const unsigned int words = static_cast<unsigned int>(q.world) * groups * 2;
@@ -782,6 +782,8 @@ bn_fwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
     float4* y_v = reinterpret_cast<float4*>(p.out);
     const unsigned int plane_stride = p.c * p.hwv;
     const unsigned int group_stride = p.n * plane_stride;            // total vectors < 2^32 (checked on the host)
+    // call sequence number of the exchange: stable for the whole launch, fetched early so its latency hides under the loads
+    const unsigned long long seq = P2P ? *reinterpret_cast<const volatile unsigned long long*>(q.state) : 0ULL;
 
     unsigned int rel[NV];
     float4 a[G][NV], r[RES_EARLY ? G : 1][RES_EARLY ? NV : 1];
@@ -820,7 +822,7 @@ bn_fwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
     block_reduce_k<2 * G>(acc, reinterpret_cast<double*>(s_part), s_warp);
 
     __shared__ double2 s_loc[kMaxGroups], s_glob[kMaxGroups];
-    const double2 tot = P2P ? cluster_fold_p2p(cluster, s_part, s_all, s_loc, s_glob, G, ch, q)
+    const double2 tot = P2P ? cluster_fold_p2p(cluster, s_part, s_all, s_loc, s_glob, G, ch, q, seq)
                             : cluster_fold(cluster, s_part, s_all, G);
     if (threadIdx.x < G) {
         const unsigned int g = threadIdx.x, gc = g * p.c + ch;
@@ -889,6 +891,7 @@ bn_bwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
     float4* dr_v = reinterpret_cast<float4*>(p.out2);
     const unsigned int plane_stride = p.c * p.hwv;
     const unsigned int group_stride = p.n * plane_stride;
+    const unsigned long long seq = P2P ? *reinterpret_cast<const volatile unsigned long long*>(q.state) : 0ULL;
 
     unsigned int rel[NV];
     float4 d[G][NV], x[G][NV];
@@ -937,7 +940,7 @@ bn_bwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
     block_reduce_k<2 * G>(acc, reinterpret_cast<double*>(s_part), s_warp);
 
     __shared__ double2 s_loc[kMaxGroups], s_glob[kMaxGroups];
-    const double2 tot = P2P ? cluster_fold_p2p(cluster, s_part, s_all, s_loc, s_glob, G, ch, q)
+    const double2 tot = P2P ? cluster_fold_p2p(cluster, s_part, s_all, s_loc, s_glob, G, ch, q, seq)
                             : cluster_fold(cluster, s_part, s_all, G);
     if (threadIdx.x < G) {
         const unsigned int g = threadIdx.x, gc = g * p.c + ch;

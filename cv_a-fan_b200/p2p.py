@@ -56,7 +56,8 @@ class PeerMailbox:
                 check(L.afan_p2p_open_handle(buf, ctypes.byref(p)), "afan_p2p_open_handle")
             self._opened.append(p.value)
             self.peer_ptrs[r] = p.value
-        dist.barrier(group=self.pg)
+        # no collective here: the caller agrees on success across ranks (trainer: all-reduce of an ok flag), which also
+        # guarantees every peer finished opening before anyone can free its mailbox
 
     # ---- single-process loopback (tests): all "ranks" live on one GPU, peers are plain local pointers ----
     @classmethod

@@ -51,7 +51,18 @@ class AfanTrainer:
             if bn_exchange == "p2p":                 # fused exchange over NVLink peer memory inside the BN kernels
                 from .p2p import PeerMailbox
                 cmax = max(m.num_features for m in model.modules() if isinstance(m, DualBatchNorm2d))
-                self.mailbox = PeerMailbox(process_group, self.device, cmax=cmax)
+                ok = torch.ones(1, device=self.device)
+                try:
+                    self.mailbox = PeerMailbox(process_group, self.device, cmax=cmax)
+                except AfanError as e:               # e.g. no peer access between the GPUs: all ranks must agree
+                    ok.zero_()
+                    err = e
+                torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=process_group)
+                if not bool(ok.item()):
+                    import warnings
+                    warnings.warn("afan_b200: peer-mapped mailboxes unavailable on some rank; dual-BN statistics fall "
+                                  "back to NCCL all-reduce (stats -> all-reduce -> finalize -> apply)")
+                    self.mailbox = None
             elif bn_exchange != "nccl":
                 raise AfanError(f"bn_exchange must be 'p2p' or 'nccl', got {bn_exchange!r}")
             for m in model.modules():
