@@ -117,14 +117,14 @@ def cpu_reference(steps, warmup, batch=None):
             "ms_per_step": 1e3 * dt / steps}
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, conv_math="fp32"):
     w = WORKLOAD
     return {"workload": "BASELINE configs[1]: ResNet-56 CIFAR-100-shaped synthetic 32x32, A-FAN PGD-5 with dual BN",
             "global_batch": w["batch_per_gpu"] * n_gpus, "batch_per_gpu": w["batch_per_gpu"],
             "perturb_idx": w["perturb_idx"], "perturbed_feature": "128x16x32x32 fp32 per GPU",
             "pgd_steps": w["steps"], "gamma_255": w["gamma"], "eps_255": w["eps"], "randinit": w["randinit"],
             "clip": w["clip"], "parallelism": f"dp{n_gpus} (one process per GPU, NCCL)",
-            "conv_math": "fp32 (TF32 off)",
+            "conv_math": "fp32 (TF32 off)" if conv_math == "fp32" else "tf32 tensor cores (cuDNN), fp32 accumulate",
             "l2": "no flush between steps: per-step working set (saved activations ~0.9 GB) exceeds the 126 MB L2; "
                   "kernel rooflines are measured separately with an L2 flush between launches"}
 
@@ -330,6 +330,8 @@ def main():
     ap.add_argument("--no-sync-bn", action="store_true", help="per-replica BN statistics (the reference's DataParallel behaviour)")
     ap.add_argument("--bn-exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU dual-BN statistics: fused NVLink peer-memory exchange inside the kernel, or NCCL all-reduce")
+    ap.add_argument("--conv-math", default="fp32", choices=["fp32", "tf32"],
+                    help="cuDNN/cuBLAS math of the (library) convolutions / fc: strict fp32 (headline) or TF32 tensor cores")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-rooflines", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
@@ -352,8 +354,8 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
         pg = torch.distributed.group.WORLD
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = args.conv_math == "tf32"
+    torch.backends.cuda.matmul.allow_tf32 = args.conv_math == "tf32"
     torch.backends.cudnn.benchmark = True
 
     pkg = importlib.import_module("cv_a-fan_b200")
@@ -432,7 +434,7 @@ def main():
     line = {"metric": "A-FAN train img/s", "value": global_batch * args.steps / sec, "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(world), "clocks": clocks,
+            "config": config_dict(world, args.conv_math), "clocks": clocks,
             "e2e": {"value": global_batch * args.steps / sec_e2e, "unit": "img/s",
                     "h2d_bytes_per_step": (host_x[0].numel() * 4 + host_y[0].numel() * 8) * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * sec_e2e / args.steps},

@@ -135,6 +135,153 @@ mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ ad
     }
 }
 
+
+// ---- a9 + a8 fused: SAT sample points on the clean->adv segment with optional mix_feature per point -------------
+// Replaces get_sample_points + the per-point `adv_list[i] = mix_feature(clean, adv_list[i])` lines,
+// Segmentation/attack_algo.py:108-118 + main_aug_final.py:206-210 (n = 3), Detection/attack_algo.py:236-245 +
+// train_aug_final.py:117-126 (n = 5): up to 4 points p_j = lerp(clean, adv, w_j); for flagged points the output is
+// mix_feature(clean, p_j).  clean and adv are read once per sweep for ALL points (8 + 4m B/elem instead of
+// (m-1) lerp launches + ~10 passes per mix): the lerps are recomputed in registers, never materialised.
+constexpr int kSatMax = 4;
+struct SatParams {
+    const float* clean;
+    const float* adv;
+    float* out[kSatMax];
+    float w[kSatMax];
+    unsigned int mix_mask, m, c, hw, tiles_per_sample;
+};
+
+__device__ __forceinline__ float torch_lerp(float x, float y, float w) {
+    const float diff = __fsub_rn(y, x);                                  // ATen lerp: w < 0.5 ? x + w*diff : y - diff*(1-w)
+    return (fabsf(w) < 0.5f) ? fmaf(w, diff, x) : fmaf(-diff, __fsub_rn(1.0f, w), y);
+}
+
+template <int VEC, int kMixThreads, int kMixUnroll>
+__global__ void __launch_bounds__(kMixThreads) sat_mix_kernel(const SatParams p) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    constexpr int PT = 32 * VEC;
+    constexpr int kMixWarps = kMixThreads / 32;
+    __shared__ float s_mean[kMixWarps][PT], s_m2[kMixWarps][PT];
+    __shared__ float s_stat[1 + kSatMax][2][PT];                         // [clean, p_0..p_3][mean, std][pixel]
+    const unsigned int c = p.c, hw = p.hw;
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int n = blockIdx.x / p.tiles_per_sample, tile = blockIdx.x - n * p.tiles_per_sample;
+    const unsigned int p0 = tile * PT + lane * VEC;
+    const bool active = p0 < hw;
+    const size_t base = static_cast<size_t>(n) * c * hw + p0;
+
+    // ---- sweep 1: Welford of clean and of every flagged point, lerps formed in registers ----
+    Welford wc[VEC], wp[kSatMax][VEC];
+    unsigned int count = 0;
+    if (active && p.mix_mask) {
+        for (unsigned int k0 = warp; k0 < c; k0 += kMixWarps * kMixUnroll) {
+            V xc[kMixUnroll] = {}, xa[kMixUnroll] = {};
+#pragma unroll
+            for (int u = 0; u < kMixUnroll; ++u) {
+                const unsigned int k = k0 + u * kMixWarps;
+                if (k < c) {
+                    xc[u] = *reinterpret_cast<const V*>(p.clean + base + static_cast<size_t>(k) * hw);
+                    xa[u] = *reinterpret_cast<const V*>(p.adv + base + static_cast<size_t>(k) * hw);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kMixUnroll; ++u) {
+                const unsigned int k = k0 + u * kMixWarps;
+                if (k < c) {
+                    const float r = 1.0f / static_cast<float>(++count);
+                    float cv[VEC], av[VEC];
+                    if constexpr (VEC == 4) {
+                        cv[0] = xc[u].x; cv[1] = xc[u].y; cv[2] = xc[u].z; cv[3] = xc[u].w;
+                        av[0] = xa[u].x; av[1] = xa[u].y; av[2] = xa[u].z; av[3] = xa[u].w;
+                    } else {
+                        cv[0] = xc[u]; av[0] = xa[u];
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        wc[v].push(cv[v], r);
+#pragma unroll
+                        for (int j = 0; j < kSatMax; ++j)
+                            if (p.mix_mask & (1u << j)) wp[j][v].push(torch_lerp(cv[v], av[v], p.w[j]), r);
+                    }
+                }
+            }
+        }
+    }
+    // ---- merge the warps' states, one tensor at a time through the same shared buffers ----
+    if (p.mix_mask) {
+        for (int tsr = 0; tsr <= kSatMax; ++tsr) {
+            if (tsr > 0 && !(p.mix_mask & (1u << (tsr - 1)))) continue;   // uniform across the CTA
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const Welford& w = tsr == 0 ? wc[v] : wp[tsr - 1][v];
+                s_mean[warp][lane * VEC + v] = w.mean;
+                s_m2[warp][lane * VEC + v] = w.m2;
+            }
+            __syncthreads();
+            if (threadIdx.x < PT) {
+                const unsigned int px = threadIdx.x;
+                float mean = 0.f, m2 = 0.f, cnt = 0.f;
+                for (unsigned int w = 0; w < kMixWarps; ++w) {
+                    const float nb = w < c ? static_cast<float>((c - w + kMixWarps - 1) / kMixWarps) : 0.f;
+                    if (nb == 0.f) continue;
+                    const float mb = s_mean[w][px], qb = s_m2[w][px];
+                    const float tot = cnt + nb, d = mb - mean;
+                    mean = fmaf(d, nb / tot, mean);
+                    m2 = m2 + qb + d * d * (cnt * nb / tot);
+                    cnt = tot;
+                }
+                s_stat[tsr][0][px] = mean;
+                s_stat[tsr][1][px] = sqrtf(m2 / (static_cast<float>(c) - 1.0f) + 1e-5f);
+            }
+            __syncthreads();
+        }
+    }
+    if (!active) return;
+
+    // ---- sweep 2 (cache-hot): write every point ----
+    for (unsigned int k0 = warp; k0 < c; k0 += kMixWarps * kMixUnroll) {
+        V xc[kMixUnroll] = {}, xa[kMixUnroll] = {};
+#pragma unroll
+        for (int u = 0; u < kMixUnroll; ++u) {
+            const unsigned int k = k0 + u * kMixWarps;
+            if (k < c) {
+                xc[u] = *reinterpret_cast<const V*>(p.clean + base + static_cast<size_t>(k) * hw);
+                xa[u] = *reinterpret_cast<const V*>(p.adv + base + static_cast<size_t>(k) * hw);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kMixUnroll; ++u) {
+            const unsigned int k = k0 + u * kMixWarps;
+            if (k < c) {
+                float cv[VEC], av[VEC];
+                if constexpr (VEC == 4) {
+                    cv[0] = xc[u].x; cv[1] = xc[u].y; cv[2] = xc[u].z; cv[3] = xc[u].w;
+                    av[0] = xa[u].x; av[1] = xa[u].y; av[2] = xa[u].z; av[3] = xa[u].w;
+                } else {
+                    cv[0] = xc[u]; av[0] = xa[u];
+                }
+                for (unsigned int j = 0; j < p.m; ++j) {
+                    float o[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const float pt = torch_lerp(cv[v], av[v], p.w[j]);
+                        if (p.mix_mask & (1u << j)) {
+                            const unsigned int px = lane * VEC + v;
+                            o[v] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(cv[v], s_stat[0][0][px]), s_stat[0][1][px]),
+                                                       s_stat[1 + j][1][px]), s_stat[1 + j][0][px]);
+                        } else {
+                            o[v] = pt;
+                        }
+                    }
+                    V ov;
+                    if constexpr (VEC == 4) { ov.x = o[0]; ov.y = o[1]; ov.z = o[2]; ov.w = o[3]; } else { ov = o[0]; }
+                    st_stream(reinterpret_cast<V*>(p.out[j] + base + static_cast<size_t>(k) * hw), ov);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace afan
 
 using namespace afan;
@@ -160,5 +307,33 @@ AFAN_EXPORT int afan_mix_feature_f32(const float* clean, const float* adv, float
     else                                                             // many tiles: 3 x 512-thread CTAs per SM
         mix_feature_kernel<1, 512, 8><<<grid, 512, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
                                                            static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_sat_mix_f32(const float* clean, const float* adv, float* const* outs, const float* weights,
+                                 const int* mix_flags, int m, int64_t n, int64_t c, int64_t hw, afan_stream_t stream) {
+    if (n < 0 || c < 0 || hw < 0 || m < 0) return AFAN_ERR_SIZE;
+    if (m > kSatMax) return AFAN_ERR_UNSUPPORTED;
+    if (n == 0 || c == 0 || hw == 0 || m == 0) return AFAN_OK;
+    if (!clean || !adv || !outs || !weights || !mix_flags) return AFAN_ERR_NULL;
+    if (c >= (int64_t(1) << 31) || hw >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
+    SatParams p{};
+    p.clean = clean; p.adv = adv; p.m = static_cast<unsigned int>(m);
+    bool vec = (hw % 4 == 0) && aligned16(clean) && aligned16(adv);
+    for (int j = 0; j < m; ++j) {
+        if (!outs[j]) return AFAN_ERR_NULL;
+        p.out[j] = outs[j];
+        p.w[j] = weights[j];
+        if (mix_flags[j]) p.mix_mask |= 1u << j;
+        vec = vec && aligned16(outs[j]);
+    }
+    const int64_t pt = vec ? 128 : 32;
+    const int64_t tiles = (hw + pt - 1) / pt;
+    if (n * tiles >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
+    p.c = static_cast<unsigned int>(c); p.hw = static_cast<unsigned int>(hw); p.tiles_per_sample = static_cast<unsigned int>(tiles);
+    const unsigned int grid = static_cast<unsigned int>(n * tiles);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec) sat_mix_kernel<4, 512, 2><<<grid, 512, 0, st>>>(p);
+    else     sat_mix_kernel<1, 512, 8><<<grid, 512, 0, st>>>(p);
     return launch_status();
 }

@@ -6,7 +6,7 @@
 The model contract is the reference's: model.train().forward({'x','adv','out_idx','flag'}, bb, lb) -> 4 losses.
 """
 from .attack_algo import linfball_proj, l2ball_proj, pgd_loop  # noqa: F401
-from .segmentation import get_sample_points, mix_feature  # noqa: F401  (identical maths in both reference files)
+from .segmentation import get_sample_points, mix_feature, sat_sample_points  # noqa: F401  (identical maths in both reference files)
 
 
 def compute_loss(loss1, loss2, loss3, loss4):

@@ -113,6 +113,26 @@ def mix_feature(clean: torch.Tensor, adv: torch.Tensor, out: Optional[torch.Tens
     return out
 
 
+def sat_mix(clean: torch.Tensor, adv: torch.Tensor, weights, mix_flags):
+    """Fused SAT points: out_j = mix_flags[j] ? mix_feature(clean, lerp(clean, adv, w_j)) : lerp(clean, adv, w_j)
+    for up to 4 points in ONE launch (get_sample_points + per-point mix_feature of the reference)."""
+    import ctypes
+    m = len(weights)
+    if m != len(mix_flags) or not 1 <= m <= 4:
+        raise AfanError("sat_mix takes 1..4 points with one mix flag each")
+    if clean.shape != adv.shape or clean.dim() < 2:
+        raise AfanError("sat_mix needs two [N, C, ...] tensors of the same shape")
+    outs = [torch.empty_like(clean) for _ in range(m)]
+    n, c = clean.shape[0], clean.shape[1]
+    hw = clean.numel() // max(n * c, 1)
+    optr = (ctypes.c_void_p * m)(*[f32(o) for o in outs])
+    wts = (ctypes.c_float * m)(*[float(w) for w in weights])
+    flg = (ctypes.c_int * m)(*[int(bool(f)) for f in mix_flags])
+    check(_lib.lib().afan_sat_mix_f32(f32(clean, "clean"), f32(adv, "adv"), optr, wts, flg, m, n, c, hw, stream()),
+          "afan_sat_mix_f32")
+    return outs
+
+
 # ------------------------------------------------------------------------------------------------
 # dual BatchNorm (a10)
 # ------------------------------------------------------------------------------------------------

@@ -32,6 +32,30 @@ def mix_feature(clean_feature, adv_feature):
     return ops.mix_feature(clean_feature.contiguous(), adv_feature.contiguous())
 
 
+def sat_sample_points(pointx, pointy, number, mix=None):
+    """get_sample_points followed by the reference's per-point `adv_list[i] = mix_feature(clean, adv_list[i])`
+    (main_aug_final.py:206-210 / train_aug_final.py:117-126) in ONE fused launch.  mix[i-1] selects point i
+    (i = 1 .. number-1; the last point is pointy itself).  Returns [pointx, p_1', ..., p_{number-1}']."""
+    m = number - 1
+    mix = [False] * m if mix is None else [bool(f) for f in mix]
+    if len(mix) != m:
+        raise AfanError(f"mix must have {m} flags (points 1..{m})")
+    if pointx.requires_grad or pointy.requires_grad:
+        pointx, pointy = pointx.detach(), pointy.detach()
+    percent = 1.0 / (number - 1)
+    weights = [i * percent for i in range(1, number - 1)] + [1.0]
+    if not mix[-1]:                                   # un-mixed last point is pointy itself (no copy), like the reference
+        weights, flags = weights[:-1], mix[:-1]
+    else:
+        flags = mix
+    pts = []
+    for s in range(0, len(weights), 4):                # 4 points per launch
+        pts += ops.sat_mix(pointx.contiguous(), pointy.contiguous(), weights[s:s + 4], flags[s:s + 4])
+    if not mix[-1]:
+        pts.append(pointy)
+    return [pointx] + pts
+
+
 def get_sample_points(pointx, pointy, number):
     """[x, lerp(x, y, i/(number-1)) for i in 1..number-2, y] (SAT points on the clean->adv segment)."""
     percent = 1.0 / (number - 1)

@@ -97,6 +97,15 @@ int afan_l2ball_proj_f32(const float* center, const float* dist, float* t, float
 int afan_mix_feature_f32(const float* clean, const float* adv, float* out, int64_t n, int64_t c,
                          int64_t hw, afan_stream_t stream);
 
+/* ---- a9 (+ a8): SAT sample points with optional per-point mix_feature, fused ------------------------------
+ * Replaces get_sample_points (Segmentation/attack_algo.py:108-118, Detection/attack_algo.py:236-245) followed by
+ * `adv_list[i] = mix_feature(clean, adv_list[i])` (Segmentation/main_aug_final.py:206-210, Detection/
+ * train_aug_final.py:117-126):  for j < m (m <= 4):  p_j = lerp(clean, adv, weights[j]);
+ * outs[j] = mix_flags[j] ? mix_feature(clean, p_j) : p_j.   outs / weights / mix_flags are HOST arrays of length m
+ * (outs holds device pointers).  clean and adv are read once per sweep for all points: 8 + 4m B/elem. */
+int afan_sat_mix_f32(const float* clean, const float* adv, float* const* outs, const float* weights,
+                     const int* mix_flags, int m, int64_t n, int64_t c, int64_t hw, afan_stream_t stream);
+
 /* ---- a10: dual (grouped-statistics) train-mode BatchNorm2d ---------------------------------------
  * Replaces nn.BatchNorm2d (+ the F.relu / residual add that follow it) in the tail as seen by the
  * adversarial and the clean batch, Classification/resnet_s.py:54,56,70-76,89 driven by

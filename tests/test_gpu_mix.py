@@ -53,3 +53,30 @@ def test_mix_identity_property_full_size():
     x = feature_like((4, 2048, 33, 33), g).to(dev())
     out = PKG.ops.mix_feature(x, x)
     torch.testing.assert_close(out, x, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 33, 33), (2, 64, 16, 16), (1, 5, 3, 7)])
+@pytest.mark.parametrize("number,mix", [(3, (True, True)), (3, (False, True)), (5, (True, False, True, False)),
+                                        (5, (False, False, False, False)), (5, (True, True, True, True))])
+def test_fused_sat_points_vs_oracle(shape, number, mix):
+    """get_sample_points + per-point mix_feature (main_aug_final.py:206-210, train_aug_final.py:117-126) in one launch."""
+    g = torch.Generator().manual_seed(number + sum(shape))
+    cl = feature_like(shape, g)
+    ad = cl + (2 / 255) * torch.sign(torch.randn(shape, generator=g))
+    cl_d, ad_d = cl.to(dev()), ad.to(dev())
+    got = PKG.segmentation.sat_sample_points(cl_d, ad_d, number, mix)
+    ref_pts = orc.get_sample_points(cl.numpy(), ad.numpy(), number)
+    assert len(got) == number and got[0] is cl_d
+    for i in range(1, number):
+        exp = orc.mix_feature(cl.numpy(), ref_pts[i]) if mix[i - 1] else ref_pts[i]
+        if mix[i - 1]:
+            np.testing.assert_allclose(got[i].cpu().numpy(), exp, rtol=2e-5, atol=2e-6, err_msg=f"point {i}")
+        else:
+            np.testing.assert_allclose(got[i].cpu().numpy(), exp, rtol=0, atol=1.2e-7, err_msg=f"point {i}")
+    if not mix[-1]:
+        assert got[-1] is ad_d                       # the reference returns pointy itself
+    # the un-fused interface gives the same points
+    plain = PKG.segmentation.get_sample_points(cl_d, ad_d, number)
+    for i in range(1, number - 1):
+        if not mix[i - 1]:
+            np.testing.assert_allclose(got[i].cpu().numpy(), plain[i].cpu().numpy(), rtol=0, atol=1.2e-7)
