@@ -23,6 +23,9 @@ SIGNATURES = {
     "afan_pgd_init_philox_f32": (_int, [_vp, _vp, _i64, _f32, _u64, _u64, _vp, _vp]),
     "afan_pgd_norms_workspace_bytes": (_i64, [_i64]),
     "afan_pgd_linf_step_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _int, _vp]),
+    "afan_pgd_linf_step_bf16": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _int, _vp]),
+    "afan_pgd_init_noise_bf16": (_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
+    "afan_pgd_init_philox_bf16": (_int, [_vp, _vp, _i64, _f32, _u64, _u64, _vp, _vp]),
     "afan_sample_l2norm_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "afan_pgd_l2_step_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _vp]),
     "afan_l2ball_proj_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp]),
@@ -96,6 +99,12 @@ def ptr(t):
 def f32(t, name="tensor"):
     if t is not None and t.dtype != torch.float32:
         raise AfanError(f"{name} must be float32, got {t.dtype}")
+    return ptr(t)
+
+
+def dev_ptr(t, dtype, name="tensor"):
+    if t is not None and t.dtype != dtype:
+        raise AfanError(f"{name} must be {dtype}, got {t.dtype}")
     return ptr(t)
 
 

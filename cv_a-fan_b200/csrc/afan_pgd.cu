@@ -11,6 +11,8 @@
 // 13 un-fused launches and 4 host syncs.  Arithmetic is ordered exactly like the reference's op
 // sequence so x_adv is bit-identical: every fp32 op below is an explicit
 // round-to-nearest intrinsic, so nvcc cannot contract or reassociate it.
+#include <cuda_bf16.h>
+
 #include "afan_common.cuh"
 
 namespace afan {
@@ -314,6 +316,101 @@ pgd_init_philox_kernel(const float* __restrict__ x, float* __restrict__ x_adv, l
     }
 }
 
+
+// ---- bf16 I/O twins (BASELINE config 3: bf16 feature maps; fp32 math in registers) -----------------------------
+// Storage is bf16 (8 elements per 128-bit access: half the bytes of the fp32 kernels), arithmetic is the SAME fp32
+// sequence as above on the widened values, results rounded to nearest-even on store.  delta / norms are formed from
+// the ROUNDED x_adv, i.e. what the caller would see by subtracting the stored tensors.  No reference exists for
+// this dtype ("parity unpinned"); the oracle twin is orc_pgd_linf_step_bf16 and the contract is bit-equality with it.
+struct Bf16x8 { uint4 raw; };
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 v = __bfloat1622float2(h[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return r;
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+template <bool VEC8, bool STEP, bool CLIP, bool DELTA, bool NORMS>
+__global__ void __launch_bounds__(kThreads)
+pgd_linf_step_bf16_kernel(const __nv_bfloat16* __restrict__ grad, const __nv_bfloat16* __restrict__ x_clean,
+                          __nv_bfloat16* x_adv, __nv_bfloat16* __restrict__ delta_out, float* __restrict__ norms_out,
+                          float* partials, unsigned int* counters, long long pv, int n_samples, float gamma, float eps) {
+    constexpr int NE = VEC8 ? 8 : 1;
+    constexpr bool NEED_CLEAN = CLIP || DELTA || NORMS;
+    const int chunks = gridDim.x, k = blockIdx.x, s = blockIdx.y;
+    const long long lo = pv * k / chunks, hi = pv * (k + 1) / chunks, base = static_cast<long long>(s) * pv * NE;
+    NormAcc acc;
+    for (long long i0 = lo + threadIdx.x; i0 < hi; i0 += static_cast<long long>(kThreads) * kUnroll) {
+        float g[kUnroll][NE] = {}, a[kUnroll][NE] = {}, c[kUnroll][NE] = {};
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = i0 + static_cast<long long>(u) * kThreads;
+            if (i < hi) {
+                if constexpr (VEC8) {
+                    if (STEP) unpack8(__ldcs(reinterpret_cast<const uint4*>(grad + base) + i), g[u]);
+                    unpack8(reinterpret_cast<const uint4*>(x_adv + base)[i], a[u]);
+                    if (NEED_CLEAN) unpack8(__ldg(reinterpret_cast<const uint4*>(x_clean + base) + i), c[u]);
+                } else {
+                    if (STEP) g[u][0] = __bfloat162float(grad[base + i]);
+                    a[u][0] = __bfloat162float(x_adv[base + i]);
+                    if (NEED_CLEAN) c[u][0] = __bfloat162float(x_clean[base + i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = i0 + static_cast<long long>(u) * kThreads;
+            if (i < hi) {
+                float d[NE];
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    a[u][e] = bf16_round(linf_update<STEP, CLIP>(g[u][e], a[u][e], c[u][e], gamma, eps));
+                    if (DELTA || NORMS) {
+                        d[e] = __fsub_rn(a[u][e], c[u][e]);
+                        if (NORMS) acc.add(d[e]);
+                    }
+                }
+                if constexpr (VEC8) {
+                    reinterpret_cast<uint4*>(x_adv + base)[i] = pack8(a[u]);
+                    if (DELTA) __stcs(reinterpret_cast<uint4*>(delta_out + base) + i, pack8(d));
+                } else {
+                    x_adv[base + i] = __float2bfloat16_rn(a[u][0]);
+                    if (DELTA) delta_out[base + i] = __float2bfloat16_rn(d[0]);
+                }
+            }
+        }
+    }
+    if constexpr (NORMS) finish_sample_norms(acc, partials, counters, s, k, chunks, norms_out, norms_out + n_samples);
+}
+
+// random start, bf16 storage: u is either the caller's fp32 torch.rand draw or Philox (same stream as the fp32 kernel)
+template <bool PHILOX>
+__global__ void __launch_bounds__(kThreads)
+pgd_init_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ u, __nv_bfloat16* __restrict__ x_adv,
+                     long long n, float eps, unsigned long long seed, unsigned long long offset,
+                     const unsigned long long* __restrict__ offset_device) {
+    if (PHILOX && offset_device) offset += __ldg(offset_device);
+    const long long n4 = (n + 3) / 4, stride = static_cast<long long>(gridDim.x) * kThreads;
+    for (long long q = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; q < n4; q += stride) {
+        float r[4];
+        if (PHILOX) {
+            const uint4 b = Philox::draw(static_cast<unsigned long long>(q) + offset, seed);
+            r[0] = Philox::uniform(b.x); r[1] = Philox::uniform(b.y); r[2] = Philox::uniform(b.z); r[3] = Philox::uniform(b.w);
+        }
+        for (int j = 0; j < 4 && q * 4 + j < n; ++j) {
+            const float uu = PHILOX ? r[j] : __ldcs(u + q * 4 + j);
+            x_adv[q * 4 + j] = __float2bfloat16_rn(init_elem(__bfloat162float(x[q * 4 + j]), uu, eps));
+        }
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------
 inline int flat_grid(long long n_vec, int per_cta) {
     const long long want = (n_vec + per_cta - 1) / per_cta;
@@ -505,5 +602,89 @@ AFAN_EXPORT int afan_l2ball_proj_f32(const float* center, const float* dist, flo
                  else           l2_apply_kernel<4, 1, false><<<grid, kThreads, 0, st>>>(center, dist, t, nullptr, g.pv, radius, 0.f); }
     else       { if (delta_out) l2_apply_kernel<1, 1, true><<<grid, kThreads, 0, st>>>(center, dist, t, delta_out, g.pv, radius, 0.f);
                  else           l2_apply_kernel<1, 1, false><<<grid, kThreads, 0, st>>>(center, dist, t, nullptr, g.pv, radius, 0.f); }
+    return launch_status();
+}
+
+// ---- bf16 entry points -------------------------------------------------------------------------------------------
+namespace afan {
+template <bool VEC8>
+int dispatch_step_bf16(bool step, bool clip, bool delta, bool norms, const __nv_bfloat16* g, const __nv_bfloat16* xc,
+                       __nv_bfloat16* xa, __nv_bfloat16* d, float* norms_out, float* partials, unsigned int* counters,
+                       long long ns, long long pv, int chunks, float gamma, float eps, cudaStream_t st) {
+    dim3 grid(chunks, static_cast<unsigned int>(ns));
+#define AFAN_B16(S, C, D, N)                                                                                          \
+    if (step == S && clip == C && delta == D && norms == N) {                                                         \
+        pgd_linf_step_bf16_kernel<VEC8, S, C, D, N><<<grid, kThreads, 0, st>>>(g, xc, xa, d, norms_out, partials, counters, \
+                                                                              pv, static_cast<int>(ns), gamma, eps); \
+        return launch_status();                                                                                       \
+    }
+    AFAN_B16(true, false, false, false) AFAN_B16(true, false, false, true) AFAN_B16(true, false, true, false)
+    AFAN_B16(true, false, true, true) AFAN_B16(true, true, false, false) AFAN_B16(true, true, false, true)
+    AFAN_B16(true, true, true, false) AFAN_B16(true, true, true, true) AFAN_B16(false, false, false, false)
+    AFAN_B16(false, false, false, true) AFAN_B16(false, false, true, false) AFAN_B16(false, false, true, true)
+    AFAN_B16(false, true, false, false) AFAN_B16(false, true, false, true) AFAN_B16(false, true, true, false)
+    AFAN_B16(false, true, true, true)
+#undef AFAN_B16
+    return AFAN_ERR_UNSUPPORTED;
+}
+}  // namespace afan
+
+AFAN_EXPORT int afan_pgd_linf_step_bf16(const void* grad, const void* x_clean, void* x_adv, void* delta_out,
+                                        float* norms_out, void* workspace, int64_t workspace_bytes, int64_t n_samples,
+                                        int64_t per_sample, float gamma, float eps, int clip, afan_stream_t stream) {
+    if (n_samples < 0 || per_sample < 0) return AFAN_ERR_SIZE;
+    if (n_samples == 0 || per_sample == 0) return AFAN_OK;
+    const bool delta = delta_out != nullptr, norms = norms_out != nullptr, step = grad != nullptr;
+    if (!x_adv || ((clip || delta || norms) && !x_clean)) return AFAN_ERR_NULL;
+    long long ns = n_samples, per = per_sample;
+    float* partials = nullptr;
+    unsigned int* counters = nullptr;
+    if (norms) {
+        if (ns > 65535) return AFAN_ERR_UNSUPPORTED;
+        if (!workspace || workspace_bytes < afan_pgd_norms_workspace_bytes(n_samples)) return AFAN_ERR_WORKSPACE;
+        counters = static_cast<unsigned int*>(workspace);
+        partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((ns * 4 + 15) / 16) * 16);
+    } else {
+        per = ns * per;
+        ns = 1;
+    }
+    const bool vec = (per % 8 == 0) && (!grad || aligned16(grad)) && aligned16(x_adv) && (!x_clean || aligned16(x_clean)) &&
+                     (!delta_out || aligned16(delta_out));
+    const long long pv = vec ? per / 8 : per;
+    long long chunks = (pv + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+    const long long sms = sm_count(), cap = (sms * kCtasPerSm + ns - 1) / ns;
+    if (ns == 1 && chunks > sms) chunks = (chunks + sms - 1) / sms * sms;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    if (norms && chunks * ns > kMaxNormChunks + ns) chunks = (kMaxNormChunks + ns) / ns;
+    const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(grad);
+    const __nv_bfloat16* xc = static_cast<const __nv_bfloat16*>(x_clean);
+    __nv_bfloat16* xa = static_cast<__nv_bfloat16*>(x_adv);
+    __nv_bfloat16* d = static_cast<__nv_bfloat16*>(delta_out);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return vec ? dispatch_step_bf16<true>(step, clip != 0, delta, norms, g, xc, xa, d, norms_out, partials, counters, ns, pv,
+                                          static_cast<int>(chunks), gamma, eps, st)
+               : dispatch_step_bf16<false>(step, clip != 0, delta, norms, g, xc, xa, d, norms_out, partials, counters, ns, pv,
+                                           static_cast<int>(chunks), gamma, eps, st);
+}
+
+AFAN_EXPORT int afan_pgd_init_noise_bf16(const void* x, const float* u, void* x_adv, int64_t n_elem, float eps,
+                                         afan_stream_t stream) {
+    if (n_elem < 0) return AFAN_ERR_SIZE;
+    if (n_elem == 0) return AFAN_OK;
+    if (!x || !u || !x_adv) return AFAN_ERR_NULL;
+    pgd_init_bf16_kernel<false><<<flat_grid((n_elem + 3) / 4, kThreads * 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), u, static_cast<__nv_bfloat16*>(x_adv), n_elem, eps, 0ULL, 0ULL, nullptr);
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_pgd_init_philox_bf16(const void* x, void* x_adv, int64_t n_elem, float eps, uint64_t seed,
+                                          uint64_t offset, const uint64_t* offset_device, afan_stream_t stream) {
+    if (n_elem < 0) return AFAN_ERR_SIZE;
+    if (n_elem == 0) return AFAN_OK;
+    if (!x || !x_adv) return AFAN_ERR_NULL;
+    pgd_init_bf16_kernel<true><<<flat_grid((n_elem + 3) / 4, kThreads * 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), nullptr, static_cast<__nv_bfloat16*>(x_adv), n_elem, eps, seed, offset,
+        reinterpret_cast<const unsigned long long*>(offset_device));
     return launch_status();
 }

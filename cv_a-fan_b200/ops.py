@@ -22,6 +22,20 @@ def pgd_init(x: torch.Tensor, eps: float, *, noise: Optional[torch.Tensor] = Non
     """Random start x + (2u-1)*eps (Classification/attack_algo.py:42-44).  `noise` = u drawn by the
     caller (bitwise parity with the reference's CPU torch.rand); otherwise on-device Philox(seed, offset)."""
     out = torch.empty_like(x) if out is None else out
+    if x.dtype == torch.bfloat16:                            # bf16-storage twin (config 3); noise stays fp32
+        bp = lambda t, nm: _lib.dev_ptr(t, torch.bfloat16, nm)
+        if noise is not None:
+            if noise.shape != x.shape:
+                raise AfanError("noise must have the shape of x")
+            check(_lib.lib().afan_pgd_init_noise_bf16(bp(x, "x"), f32(noise.float().contiguous(), "noise"), bp(out, "out"),
+                                                      x.numel(), float(eps), stream()), "afan_pgd_init_noise_bf16")
+        else:
+            if seed is None:
+                raise AfanError("pgd_init needs either noise= or seed=")
+            check(_lib.lib().afan_pgd_init_philox_bf16(bp(x, "x"), bp(out, "out"), x.numel(), float(eps),
+                                                       int(seed) & (2 ** 64 - 1), int(offset), ptr(offset_device),
+                                                       stream()), "afan_pgd_init_philox_bf16")
+        return out
     if noise is not None:
         if noise.shape != x.shape:
             raise AfanError("noise must have the shape of x")
@@ -56,6 +70,13 @@ def pgd_linf_step_(grad: torch.Tensor, x_clean: Optional[torch.Tensor], x_adv: t
             workspace = norms_workspace(n, x_adv.device)
         if norms_out.numel() != 2 * n:
             raise AfanError("norms_out must hold 2*N floats")
+    if x_adv.dtype == torch.bfloat16:
+        bp = lambda t, nm: _lib.dev_ptr(t, torch.bfloat16, nm)
+        check(_lib.lib().afan_pgd_linf_step_bf16(
+            bp(grad, "grad"), bp(x_clean, "x_clean"), bp(x_adv, "x_adv"), bp(delta_out, "delta_out"),
+            f32(norms_out, "norms_out"), ptr(workspace), workspace.numel() * workspace.element_size() if workspace is not None else 0,
+            n, per, float(gamma), float(eps), int(bool(clip)), stream()), "afan_pgd_linf_step_bf16")
+        return x_adv
     check(_lib.lib().afan_pgd_linf_step_f32(
         f32(grad, "grad"), f32(x_clean, "x_clean"), f32(x_adv, "x_adv"), f32(delta_out, "delta_out"),
         f32(norms_out, "norms_out"), ptr(workspace), workspace.numel() * workspace.element_size() if workspace is not None else 0,

@@ -72,6 +72,18 @@ int afan_pgd_linf_step_f32(const float* grad, const float* x_clean, float* x_adv
                            int64_t n_samples, int64_t per_sample, float gamma, float eps, int clip,
                            afan_stream_t stream);
 
+/* bf16-storage twins (BASELINE config 3): tensors are bf16 (void* = __nv_bfloat16*), arithmetic is the same fp32
+ * sequence on the widened values, stores round to nearest even; delta / norms are formed from the ROUNDED x_adv.
+ * `u` stays fp32.  No reference exists for this dtype: the contract is bit-equality with oracle/afan_oracle.c's
+ * orc_pgd_linf_step_bf16 and <= 1e-2 relative distance of delta from the fp32 path (north star). */
+int afan_pgd_linf_step_bf16(const void* grad, const void* x_clean, void* x_adv, void* delta_out,
+                            float* norms_out, void* workspace, int64_t workspace_bytes, int64_t n_samples,
+                            int64_t per_sample, float gamma, float eps, int clip, afan_stream_t stream);
+int afan_pgd_init_noise_bf16(const void* x, const float* u, void* x_adv, int64_t n_elem, float eps,
+                             afan_stream_t stream);
+int afan_pgd_init_philox_bf16(const void* x, void* x_adv, int64_t n_elem, float eps, uint64_t seed,
+                              uint64_t offset, const uint64_t* offset_device, afan_stream_t stream);
+
 /* ---- a5 / a5b: L2 mode ---------------------------------------------------------------------------
  * afan_sample_l2norm_f32: out_norm[s] = ||a_s - b_s||_2 (b nullable -> ||a_s||_2), deterministic
  *   two-level reduction (replaces `.view(N,-1).norm(p=2, dim=1)`, Classification/attack_algo.py:28).

@@ -57,6 +57,40 @@ ORC_API void orc_pgd_linf_step_f32(const float *grad, const float *x_clean, floa
     }
 }
 
+/* ---- bf16-storage twin of the update (BASELINE config 3; NO reference exists for this dtype: unpinned) ----
+ * tensors are bf16 bit patterns (uint16); the arithmetic is the fp32 sequence above on the widened values; the
+ * result is rounded to nearest-even; delta = bf16(fl(widen(x_adv_new_bf16) - widen(x))). */
+static inline float orc_bf16_to_f32(uint16_t h) { uint32_t b = (uint32_t)h << 16; float f; memcpy(&f, &b, 4); return f; }
+static inline uint16_t orc_f32_to_bf16(float f) {
+    uint32_t b; memcpy(&b, &f, 4);
+    if ((b & 0x7fffffffu) > 0x7f800000u) return 0x7fff;                 /* NaN -> canonical (CUDA __float2bfloat16_rn) */
+    b += 0x7fffu + ((b >> 16) & 1u);
+    return (uint16_t)(b >> 16);
+}
+ORC_API void orc_pgd_linf_step_bf16(const uint16_t *grad, const uint16_t *x_clean, uint16_t *x_adv,
+                                    uint16_t *delta /*nullable*/, int64_t n, float gamma, float eps, int clip) {
+    for (int64_t i = 0; i < n; ++i) {
+        float v = gamma * orc_sign(orc_bf16_to_f32(grad[i]));
+        float t = orc_bf16_to_f32(x_adv[i]) + v;
+        float xc = x_clean ? orc_bf16_to_f32(x_clean[i]) : 0.0f;
+        if (clip) {
+            float lo = xc - eps, hi = xc + eps;
+            if (t < lo) t = lo;
+            if (t > hi) t = hi;
+        }
+        x_adv[i] = orc_f32_to_bf16(t);
+        if (delta) delta[i] = orc_f32_to_bf16(orc_bf16_to_f32(x_adv[i]) - xc);
+    }
+}
+ORC_API void orc_pgd_init_noise_bf16(const uint16_t *x, const float *u, uint16_t *x_adv, int64_t n, float eps) {
+    for (int64_t i = 0; i < n; ++i) {
+        float t = 2.0f * u[i];
+        t = t - 1.0f;
+        t = t * eps;
+        x_adv[i] = orc_f32_to_bf16(orc_bf16_to_f32(x[i]) + t);
+    }
+}
+
 /* ---- a11: perturbation norms, Classification/main_perturb.py:188-192 -------------
  * perturbation = (adv - clean); per-sample torch.norm(p=2) and torch.norm(p=inf).
  * L2 accumulates in double and rounds once (torch's own reduction order is not

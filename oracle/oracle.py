@@ -66,6 +66,35 @@ def pgd_linf_step(grad, x_clean, x_adv, gamma, eps, clip):
     return x_adv
 
 
+def _u16(a):
+    a = np.ascontiguousarray(a)
+    assert a.dtype == np.uint16
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16))
+
+
+def pgd_linf_step_bf16(grad_u16, x_clean_u16, x_adv_u16, gamma, eps, clip, want_delta=False):
+    """bf16-storage twin of pgd_linf_step on uint16 bit patterns (no reference for this dtype: unpinned).
+    Returns (x_adv_new_u16, delta_u16 | None)."""
+    g, gp = _u16(grad_u16)
+    xa, xap = _u16(np.array(x_adv_u16, copy=True))
+    xcp = ctypes.cast(None, ctypes.POINTER(ctypes.c_uint16))
+    if x_clean_u16 is not None:
+        xc, xcp = _u16(x_clean_u16)
+    d, dp = (None, ctypes.cast(None, ctypes.POINTER(ctypes.c_uint16)))
+    if want_delta:
+        d, dp = _u16(np.empty_like(xa))
+    lib().orc_pgd_linf_step_bf16(gp, xcp, xap, dp, _i64(xa.size), ctypes.c_float(gamma), ctypes.c_float(eps), int(bool(clip)))
+    return xa, d
+
+
+def pgd_init_noise_bf16(x_u16, u, eps):
+    x, xp = _u16(x_u16)
+    u = _f32(u)
+    out, outp = _u16(np.empty_like(x))
+    lib().orc_pgd_init_noise_bf16(xp, _p(u), outp, _i64(x.size), ctypes.c_float(eps))
+    return out
+
+
 def delta_norms(x_adv, x_clean):
     """Classification/main_perturb.py:188-192 -> (delta, l2[N], linf[N])."""
     x_adv, x_clean = _f32(x_adv), _f32(x_clean)

@@ -175,3 +175,41 @@ def test_full_size_properties():
     again = xa.clone()
     PKG.attack_algo.linfball_proj(xd, eps, again)
     assert torch.equal(again, xa)
+
+
+def _bf16_bits(t):
+    return t.detach().cpu().view(torch.int16).numpy().view(np.uint16)
+
+
+@pytest.mark.parametrize("shape", [(256, 40, 28, 28), (4, 80, 14, 14), (3, 5, 7, 3)])      # EfficientNet-B0 features[3]/[4], ragged
+@pytest.mark.parametrize("clip", [False, True])
+def test_bf16_twin_bitwise_vs_oracle_and_close_to_fp32(shape, clip):
+    """BASELINE config 3 (bf16): storage bf16, fp32 math.  Bit-equal to the oracle twin; delta within 1e-2 relative
+    (north-star tolerance) of the fp32 path on the same (bf16-representable) inputs."""
+    g = torch.Generator().manual_seed(sum(shape))
+    x = feature_like(shape, g).bfloat16()
+    grad = grad_like(shape, g).bfloat16()
+    u = torch.rand(shape, generator=g)
+    gamma, eps = 1.0 / 255, 2.0 / 255
+    xa = ops.pgd_init(x.to(dev()), eps, noise=u.to(dev()))
+    assert xa.dtype == torch.bfloat16
+    ref = orc.pgd_init_noise_bf16(_bf16_bits(x), u.numpy(), eps)
+    assert np.array_equal(_bf16_bits(xa), ref)
+    xa32 = ops.pgd_init(x.float().to(dev()), eps, noise=u.to(dev()))
+    n = shape[0]
+    delta, norms = torch.empty_like(xa), torch.zeros(2, n, device=dev())
+    d32, n32 = torch.empty_like(xa32), torch.zeros(2, n, device=dev())
+    for step in range(3):
+        gs = grad * (1 if step % 2 == 0 else -1)
+        ops.pgd_linf_step_(gs.to(dev()), x.to(dev()), xa, gamma, eps, clip, delta_out=delta, norms_out=norms)
+        ref, dref = orc.pgd_linf_step_bf16(_bf16_bits(gs), _bf16_bits(x), ref, gamma, eps, clip, want_delta=True)
+        assert np.array_equal(_bf16_bits(xa), ref), f"step {step}"
+        assert np.array_equal(_bf16_bits(delta), dref)
+        ops.pgd_linf_step_(gs.float().to(dev()), x.float().to(dev()), xa32, gamma, eps, clip, delta_out=d32, norms_out=n32)
+    # bf16 vs fp32 path: delta agrees to 1e-2 relative of the ball radius, norms to 1e-2
+    assert float((delta.float() - d32).abs().max()) <= 1e-2 * eps + 2 ** -8 * float(x.float().abs().max())
+    np.testing.assert_allclose(norms[1].cpu().numpy(), n32[1].cpu().numpy(), rtol=0.3, atol=1e-2 * eps + 2 ** -8 * float(x.float().abs().max()))
+    # Philox start is the same stream as the fp32 kernel's
+    p16 = ops.pgd_init(x.to(dev()), eps, seed=5, offset=3)
+    p32 = ops.pgd_init(x.float().to(dev()), eps, seed=5, offset=3)
+    assert torch.equal(p16, p32.bfloat16())
