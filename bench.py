@@ -446,8 +446,14 @@ def main():
         ks, peak_src = kernel_rooflines(pkg, dev)
         in_step = [k for k in ks if k["launches_per_iter"] > 0]
         dom = max(in_step, key=lambda k: k["us"] * k["launches_per_iter"])
+        try:                                  # DRAM bytes per launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(dom["kernel"])
+        except Exception:
+            traffic = None
         line["roofline"] = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
-                            "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                            "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "algorithmic_bytes": dom["bytes"],
+                            "peak_source": peak_src,
                             "timing": "CUDA events around a graph of back-to-back launches over rotating tensor sets (4x L2), per-launch average",
                             "share_of_step": dom["us"] * dom["launches_per_iter"] / (1e3 * sec / args.steps) / 1e3}
         line["kernels"] = ks
