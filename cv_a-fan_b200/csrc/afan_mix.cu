@@ -28,62 +28,77 @@ struct Welford {
     }
 };
 
-template <int VEC, int kMixThreads, int kMixUnroll>
+// NP = pixel groups per thread (group q sits 32*VEC pixels after group q-1): the scalar path takes NP = 2 so that
+// every thread owns 4 independent Welford chains (2 pixels x 2 tensors) and twice the loads in flight.
+template <int VEC, int NP, int kMixThreads, int kMixUnroll>
 __global__ void __launch_bounds__(kMixThreads)
 mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ adv, float* __restrict__ out,
                    unsigned int c, unsigned int hw, unsigned int tiles_per_sample) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
-    constexpr int PT = 32 * VEC;                                     // pixels per CTA tile
+    constexpr int PT = 32 * VEC * NP;                                // pixels per CTA tile
+    constexpr int S = VEC * NP;                                      // pixel slots per thread
     constexpr int kMixWarps = kMixThreads / 32;
     __shared__ float s_mean[2][kMixWarps][PT], s_m2[2][kMixWarps][PT];
     __shared__ float s_stat[4][PT];                                  // mean_cl, std_cl, mean_ad, std_ad
 
     const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int n = blockIdx.x / tiles_per_sample, tile = blockIdx.x - n * tiles_per_sample;
-    const unsigned int p0 = tile * PT + lane * VEC;                  // first pixel of this lane
-    const bool active = p0 < hw;                                     // VEC==4 implies hw % 4 == 0: whole vector valid
+    const unsigned int p0 = tile * PT + lane * VEC;                  // first pixel of group 0 of this lane
+    bool active[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) active[q] = p0 + q * 32 * VEC < hw; // VEC==4 implies hw % 4 == 0: whole vector valid
     const size_t base = static_cast<size_t>(n) * c * hw + p0;
 
-    // ---- sweep 1: Welford over this warp's channels (warp, warp+16, ...) ----
-    Welford wc[VEC], wa[VEC];
+    auto slot_px = [&](int q, int v) { return lane * VEC + q * 32 * VEC + v; };
+    auto unpack = [](const V& x, float (&f)[VEC]) {
+        if constexpr (VEC == 4) { f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; } else { f[0] = x; }
+    };
+
+    // ---- sweep 1: Welford over this warp's channels (warp, warp+W, ...), clean and adv together ----
+    Welford wc[S], wa[S];
     unsigned int count = 0;
-    if (active) {
-        for (unsigned int k0 = warp; k0 < c; k0 += kMixWarps * kMixUnroll) {
-            V xc[kMixUnroll] = {}, xa[kMixUnroll] = {};
+    for (unsigned int k0 = warp; k0 < c; k0 += kMixWarps * kMixUnroll) {
+        V xc[kMixUnroll][NP] = {}, xa[kMixUnroll][NP] = {};
 #pragma unroll
-            for (int u = 0; u < kMixUnroll; ++u) {
-                const unsigned int k = k0 + u * kMixWarps;
-                if (k < c) {
-                    xc[u] = *reinterpret_cast<const V*>(clean + base + static_cast<size_t>(k) * hw);
-                    xa[u] = *reinterpret_cast<const V*>(adv + base + static_cast<size_t>(k) * hw);
+        for (int u = 0; u < kMixUnroll; ++u) {
+            const unsigned int k = k0 + u * kMixWarps;
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+                if (k < c && active[q]) {
+                    const size_t off = base + static_cast<size_t>(k) * hw + q * 32 * VEC;
+                    xc[u][q] = *reinterpret_cast<const V*>(clean + off);
+                    xa[u][q] = *reinterpret_cast<const V*>(adv + off);
                 }
-            }
+        }
 #pragma unroll
-            for (int u = 0; u < kMixUnroll; ++u) {
-                const unsigned int k = k0 + u * kMixWarps;
-                if (k < c) {
-                    const float r = 1.0f / static_cast<float>(++count);
-                    if constexpr (VEC == 4) {
-                        wc[0].push(xc[u].x, r); wc[1].push(xc[u].y, r); wc[2].push(xc[u].z, r); wc[3].push(xc[u].w, r);
-                        wa[0].push(xa[u].x, r); wa[1].push(xa[u].y, r); wa[2].push(xa[u].z, r); wa[3].push(xa[u].w, r);
-                    } else {
-                        wc[0].push(xc[u], r);
-                        wa[0].push(xa[u], r);
-                    }
+        for (int u = 0; u < kMixUnroll; ++u) {
+            const unsigned int k = k0 + u * kMixWarps;
+            if (k < c) {
+                const float r = 1.0f / static_cast<float>(++count);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    float fc[VEC], fa[VEC];
+                    unpack(xc[u][q], fc);
+                    unpack(xa[u][q], fa);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { wc[q * VEC + v].push(fc[v], r); wa[q * VEC + v].push(fa[v], r); }
                 }
             }
         }
     }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        s_mean[0][warp][lane * VEC + v] = wc[v].mean; s_m2[0][warp][lane * VEC + v] = wc[v].m2;
-        s_mean[1][warp][lane * VEC + v] = wa[v].mean; s_m2[1][warp][lane * VEC + v] = wa[v].m2;
-    }
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int px = slot_px(q, v), i = q * VEC + v;
+            s_mean[0][warp][px] = wc[i].mean; s_m2[0][warp][px] = wc[i].m2;
+            s_mean[1][warp][px] = wa[i].mean; s_m2[1][warp][px] = wa[i].m2;
+        }
     __syncthreads();
 
     // ---- merge the warps' states in warp order (Chan et al.), one thread per (pixel, tensor) ----
-    if (threadIdx.x < 2 * PT) {
-        const unsigned int t = threadIdx.x / PT, px = threadIdx.x - t * PT;
+    for (unsigned int idx = threadIdx.x; idx < 2 * PT; idx += kMixThreads) {
+        const unsigned int t = idx / PT, px = idx - t * PT;
         float mean = 0.f, m2 = 0.f, cnt = 0.f;
         for (unsigned int w = 0; w < kMixWarps; ++w) {
             const float nb = w < c ? static_cast<float>((c - w + kMixWarps - 1) / kMixWarps) : 0.f;   // channels warp w saw
@@ -99,42 +114,41 @@ mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ ad
         s_stat[2 * t + 1][px] = sqrtf(var + 1e-5f);
     }
     __syncthreads();
-    if (!active) return;
 
     // ---- sweep 2: out = (clean - mean_cl) / std_cl * std_adv + mean_adv, in the reference's op order ----
-    float mcl[VEC], scl[VEC], mad[VEC], sad[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        mcl[v] = s_stat[0][lane * VEC + v]; scl[v] = s_stat[1][lane * VEC + v];
-        mad[v] = s_stat[2][lane * VEC + v]; sad[v] = s_stat[3][lane * VEC + v];
-    }
     auto mix1 = [](float x, float m_c, float s_c, float m_a, float s_a) {
         return __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, m_c), s_c), s_a), m_a);
     };
     for (unsigned int k0 = warp; k0 < c; k0 += kMixWarps * kMixUnroll) {
-        V xc[kMixUnroll] = {};
+        V xc[kMixUnroll][NP] = {};
 #pragma unroll
         for (int u = 0; u < kMixUnroll; ++u) {
             const unsigned int k = k0 + u * kMixWarps;
-            if (k < c) xc[u] = *reinterpret_cast<const V*>(clean + base + static_cast<size_t>(k) * hw);
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+                if (k < c && active[q])
+                    xc[u][q] = *reinterpret_cast<const V*>(clean + base + static_cast<size_t>(k) * hw + q * 32 * VEC);
         }
 #pragma unroll
         for (int u = 0; u < kMixUnroll; ++u) {
             const unsigned int k = k0 + u * kMixWarps;
-            if (k < c) {
-                V o;
-                if constexpr (VEC == 4) {
-                    o.x = mix1(xc[u].x, mcl[0], scl[0], mad[0], sad[0]); o.y = mix1(xc[u].y, mcl[1], scl[1], mad[1], sad[1]);
-                    o.z = mix1(xc[u].z, mcl[2], scl[2], mad[2], sad[2]); o.w = mix1(xc[u].w, mcl[3], scl[3], mad[3], sad[3]);
-                } else {
-                    o = mix1(xc[u], mcl[0], scl[0], mad[0], sad[0]);
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+                if (k < c && active[q]) {
+                    float f[VEC], o[VEC];
+                    unpack(xc[u][q], f);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const int px = slot_px(q, v);
+                        o[v] = mix1(f[v], s_stat[0][px], s_stat[1][px], s_stat[2][px], s_stat[3][px]);
+                    }
+                    V ov;
+                    if constexpr (VEC == 4) { ov.x = o[0]; ov.y = o[1]; ov.z = o[2]; ov.w = o[3]; } else { ov = o[0]; }
+                    st_stream(reinterpret_cast<V*>(out + base + static_cast<size_t>(k) * hw + q * 32 * VEC), ov);
                 }
-                st_stream(reinterpret_cast<V*>(out + base + static_cast<size_t>(k) * hw), o);
-            }
         }
     }
 }
-
 
 // ---- a9 + a8 fused: SAT sample points on the clean->adv segment with optional mix_feature per point -------------
 // Replaces get_sample_points + the per-point `adv_list[i] = mix_feature(clean, adv_list[i])` lines,
@@ -294,19 +308,17 @@ AFAN_EXPORT int afan_mix_feature_f32(const float* clean, const float* adv, float
     if (c >= (int64_t(1) << 31) || hw >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = (hw % 4 == 0) && aligned16(clean) && aligned16(adv) && aligned16(out);
-    const int64_t pt = vec ? 128 : 32;
+    const int64_t pt = vec ? 128 : 64;
     const int64_t tiles = (hw + pt - 1) / pt;
     if (n * tiles >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
     const unsigned int grid = static_cast<unsigned int>(n * tiles);
+    const unsigned int uc = static_cast<unsigned int>(c), uhw = static_cast<unsigned int>(hw), ut = static_cast<unsigned int>(tiles);
     if (vec)
-        mix_feature_kernel<4, 512, 4><<<grid, 512, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
-                                                           static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
-    else if (grid < 2u * static_cast<unsigned int>(sm_count()))        // few tiles: one fat CTA per SM keeps 64 KB in flight
-        mix_feature_kernel<1, 1024, 8><<<grid, 1024, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
-                                                             static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
-    else                                                             // many tiles: 3 x 512-thread CTAs per SM
-        mix_feature_kernel<1, 512, 8><<<grid, 512, 0, st>>>(clean, adv, out, static_cast<unsigned int>(c),
-                                                           static_cast<unsigned int>(hw), static_cast<unsigned int>(tiles));
+        mix_feature_kernel<4, 1, 512, 4><<<grid, 512, 0, st>>>(clean, adv, out, uc, uhw, ut);
+    else if (grid < 2u * static_cast<unsigned int>(sm_count()))        // few tiles: one fat CTA per SM
+        mix_feature_kernel<1, 2, 1024, 4><<<grid, 1024, 0, st>>>(clean, adv, out, uc, uhw, ut);
+    else                                                             // many tiles: several 512-thread CTAs per SM
+        mix_feature_kernel<1, 2, 512, 4><<<grid, 512, 0, st>>>(clean, adv, out, uc, uhw, ut);
     return launch_status();
 }
 

@@ -1,5 +1,6 @@
 """Drop-in for Detection/attack_algo.py's hot-path functions (Faster R-CNN flavour).
 
+
     PGD(x, image_batch, y, model, steps, eps, gamma, idx, randinit, clip)   (Detection/attack_algo.py:48-74)
     compute_loss(l1, l2, l3, l4)                                            (:21-27)
     mix_feature / get_sample_points                                         (:254-265 / :236-245)
@@ -21,3 +22,45 @@ def PGD(x, image_batch, y=None, model=None, steps=3, eps=None, gamma=None, idx=1
         return compute_loss(a_obj, a_trf, p_cls, p_trf)
 
     return pgd_loop(x, tail_loss, steps, gamma, eps, randinit, clip, **extras)
+
+
+def rpn_roi_PGD(layer="roi", rpn_roi_output_dict=None, y=None, model=None, steps=1, eps=None, gamma=None,
+                randinit=False, clip=False, only_roi_loss=True, **extras):
+    """Detection/attack_algo.py:77-150: PGD on the pooled ROI feature (layer='roi') through
+    model.train().forward({'adv': dict, 'out_idx': 'roi_tail', 'flag': 'clean'}, bb, lb).
+    Reference defects handled explicitly: the 'roi' clip branch uses an undefined name (:111) --
+    here it projects onto the eps-ball around the clean ROI feature; in the 'rpn' branch the update is commented out
+    (:127-147), so the observable result is the (optionally randomly started) clean RPN feature as a leaf -- reproduced
+    without the reference's wasted forward passes."""
+    if layer == "roi":
+        d = rpn_roi_output_dict
+        anchor = d["roi_output_dict"]["roi_feature_map"].detach()
+
+        def tail_loss(x_adv):
+            d["roi_output_dict"]["roi_feature_map"] = x_adv
+            a_obj, a_trf, p_cls, p_trf = model.train().forward({"adv": d, "out_idx": "roi_tail", "flag": "clean"},
+                                                               y["bb"], y["lb"])
+            if only_roi_loss:
+                return p_cls.mean() + p_trf.mean()
+            return compute_loss(a_obj, a_trf, p_cls, p_trf)
+
+        d["roi_output_dict"]["roi_feature_map"] = pgd_loop(anchor, tail_loss, steps, gamma, eps, randinit, clip, **extras)
+        return d
+    if layer == "rpn":
+        d = rpn_roi_output_dict
+        anchor = d["rpn_feature_map_dict"]["rpn_feature"].detach()
+        d["rpn_feature_map_dict"]["rpn_feature"] = pgd_loop(anchor, lambda x_adv: None, 0, gamma, eps, randinit, False,
+                                                            **extras)
+        return d
+    raise AssertionError(f"unknown layer {layer!r}")
+
+
+def adv_input(x=None, y=None, model=None, steps=3, eps=None, gamma=None, randinit=False, clip=False, **extras):
+    """Detection/attack_algo.py:153-178: input-space PGD on the image batch, then clamp to [0, 1]."""
+    import torch
+
+    def tail_loss(x_adv):
+        inputs = {"x": x_adv, "adv": None, "out_idx": -1, "flag": "clean"}
+        return compute_loss(*model.train().forward(inputs, y["bb"], y["lb"]))
+
+    return torch.clamp(pgd_loop(x, tail_loss, steps, gamma, eps, randinit, clip, **extras), 0, 1.0)

@@ -22,6 +22,31 @@ def PGD(x, image_batch, low_level_feat, criterion, y=None, model=None, steps=3, 
     return pgd_loop(x, tail_loss, steps, gamma, eps, randinit, clip, **extras)
 
 
+def decoder_PGD(input_dict, image_batch, criterion, y=None, model=None, steps=3, eps=None, gamma=None, idx=1,
+                randinit=False, clip=False, **extras):
+    """Segmentation/attack_algo.py:61-84: PGD on the decoder-side feature input_dict['adv'] (ASPP / concat input);
+    the tail is model({'x', 'adv': input_dict, 'out_idx': idx + '_tail', 'flag': 'clean'}).  Returns input_dict with
+    'adv' replaced by the adversarial leaf.  The reference's clip branch references an undefined `x` (:81, NameError);
+    the intended semantics -- projection onto the eps-ball around the CLEAN decoder feature -- is what runs here."""
+    anchor = input_dict["adv"].detach()
+
+    def tail_loss(x_adv):
+        input_dict["adv"] = x_adv
+        return criterion(model({"x": image_batch, "adv": input_dict, "out_idx": idx + "_tail", "flag": "clean"}), y)
+
+    input_dict["adv"] = pgd_loop(anchor, tail_loss, steps, gamma, eps, randinit, clip, **extras)
+    return input_dict
+
+
+def adv_input(x=None, criterion=None, y=None, model=None, steps=3, eps=None, gamma=None, randinit=False, clip=False,
+              **extras):
+    """Segmentation/attack_algo.py:86-105: input-space PGD followed by clamp to [0, 1]."""
+    def tail_loss(x_adv):
+        return criterion(model({"x": x_adv, "adv": None, "out_idx": 0, "flag": "clean", "low_level_feat": None}), y)
+
+    return torch.clamp(pgd_loop(x, tail_loss, steps, gamma, eps, randinit, clip, **extras), 0, 1.0)
+
+
 def mix_feature(clean_feature, adv_feature):
     """Channel-dim mean/std of clean swapped for those of adv, one fused kernel (forward only: the
     reference applies it to detached / lerped features, main_aug_final.py:200-210)."""

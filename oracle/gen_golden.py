@@ -57,16 +57,30 @@ class InjectingModel:
 
     def __call__(self, x, end_point=None, start_point=None):       # Classification + Segmentation
         if isinstance(x, dict):
-            return self._next(x["adv"])
+            adv = x["adv"]
+            if isinstance(adv, dict):                               # decoder_PGD: inputs['adv'] is the feature dict
+                adv = adv["adv"]
+            if adv is None:                                         # adv_input: the image itself is perturbed
+                adv = x["x"]
+            return self._next(adv)
         return self._next(x)
 
     def train(self):                                                # Detection: model.train().forward(...)
         return self
 
     def forward(self, inputs, bb, lb):
-        out = self._next(inputs["adv"])
+        adv = inputs["adv"]
+        if isinstance(adv, dict):                                   # rpn_roi_PGD('roi')
+            adv = adv["roi_output_dict"]["roi_feature_map"]
+        if adv is None:                                             # Detection adv_input
+            adv = inputs["x"]
+        out = self._next(adv)
         z = out * 0
+        if self.roi_loss_slot:                                      # only_roi_loss=True sums losses 3 and 4
+            return z, z, out, z
         return out, z, z, z
+
+    roi_loss_slot = False
 
 
 def feature_like(shape, gen):
@@ -177,6 +191,65 @@ def gen_helper_cases():
     print("helpers.npz written")
 
 
+def gen_f1_cases():
+    """decoder-side / ROI-side / input-space PGD variants of the reference (no-clip only for
+    decoder_PGD and rpn_roi_PGD('roi'): their clip branches raise NameError in the reference)."""
+    seg = ref_shim.load("Segmentation", "attack_algo")
+    det = ref_shim.load("Detection", "attack_algo")
+    gen = torch.Generator().manual_seed(13)
+    out = {}
+
+    def record(key, x, u, grads, model, result, gamma, eps, steps, randinit, clip):
+        out[key + "_meta"] = np.array([gamma, eps, steps, int(randinit), int(clip)], dtype=np.float64)
+        out[key + "_x"], out[key + "_u"] = x.numpy().copy(), u.numpy().copy()
+        out[key + "_grads"] = torch.stack(grads).numpy().copy()
+        out[key + "_out"] = result.detach().numpy().copy()
+
+    gamma, eps = 0.4 / 255, 2 / 255
+    for randinit in (False, True):
+        tag = "r" if randinit else "n"
+        # Seg decoder_PGD
+        shape, steps = (2, 6, 5, 5), 3
+        x, grads = feature_like(shape, gen), grads_like(shape, steps, gen)
+        torch.manual_seed(3); u = torch.rand(shape); torch.manual_seed(3)
+        model = InjectingModel(grads)
+        with ref_shim.cpu_cuda_identity():
+            d = seg.decoder_PGD({"adv": x.clone(), "aux": 1}, None, lambda o, y: o, y=None, model=model, steps=steps,
+                                eps=eps, gamma=gamma, idx="aspp", randinit=randinit, clip=False)
+        record(f"seg_decoder_{tag}", x, u, grads, model, d["adv"], gamma, eps, steps, randinit, False)
+        # Seg adv_input (with clip and the final clamp to [0,1])
+        shape, steps = (2, 3, 8, 8), 3
+        x = torch.rand(shape, generator=gen)
+        x.view(-1)[:4] = torch.tensor([0.0, 1.0, 0.001, 0.999])
+        grads = grads_like(shape, steps, gen, specials=False)
+        torch.manual_seed(3); u = torch.rand(shape); torch.manual_seed(3)
+        model = InjectingModel(grads)
+        with ref_shim.cpu_cuda_identity():
+            r = seg.adv_input(x, lambda o, y: o, y=None, model=model, steps=steps, eps=eps, gamma=gamma,
+                              randinit=randinit, clip=True)
+        record(f"seg_advinput_{tag}", x, u, grads, model, r, gamma, eps, steps, randinit, True)
+        # Det adv_input
+        grads = grads_like(shape, steps, gen, specials=False)
+        torch.manual_seed(3); u = torch.rand(shape); torch.manual_seed(3)
+        model = InjectingModel(grads)
+        with ref_shim.cpu_cuda_identity():
+            r = det.adv_input(x, y={"bb": None, "lb": None}, model=model, steps=steps, eps=eps, gamma=gamma,
+                              randinit=randinit, clip=True)
+        record(f"det_advinput_{tag}", x, u, grads, model, r, gamma, eps, steps, randinit, True)
+        # Det rpn_roi_PGD('roi'), only_roi_loss True
+        shape, steps = (7, 12, 1, 1), 2
+        x, grads = feature_like(shape, gen), grads_like(shape, steps, gen)
+        torch.manual_seed(3); u = torch.rand(shape); torch.manual_seed(3)
+        model = InjectingModel(grads)
+        model.roi_loss_slot = True
+        with ref_shim.cpu_cuda_identity():
+            d = det.rpn_roi_PGD("roi", {"roi_output_dict": {"roi_feature_map": x.clone()}}, y={"bb": None, "lb": None},
+                                model=model, steps=steps, eps=eps, gamma=gamma, randinit=randinit, clip=False)
+        record(f"det_roi_{tag}", x, u, grads, model, d["roi_output_dict"]["roi_feature_map"], gamma, eps, steps, randinit, False)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "pgd_f1.npz"), **out)
+    print("pgd_f1.npz:", len([k for k in out if k.endswith("_meta")]), "cases")
+
+
 class _RecordingCE(nn.Module):
     def __init__(self):
         super().__init__()
@@ -239,6 +312,12 @@ def gen_train_cases():
 if __name__ == "__main__":
     assert ref_shim.available(), "reference not mounted; goldens can only be generated where it is"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    gen_pgd_cases()
-    gen_helper_cases()
-    gen_train_cases()
+    which = sys.argv[1:] or ["pgd", "helpers", "train", "f1"]
+    if "pgd" in which:
+        gen_pgd_cases()
+    if "helpers" in which:
+        gen_helper_cases()
+    if "train" in which:
+        gen_train_cases()
+    if "f1" in which:
+        gen_f1_cases()

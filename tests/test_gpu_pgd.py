@@ -213,3 +213,58 @@ def test_bf16_twin_bitwise_vs_oracle_and_close_to_fp32(shape, clip):
     p16 = ops.pgd_init(x.to(dev()), eps, seed=5, offset=3)
     p32 = ops.pgd_init(x.float().to(dev()), eps, seed=5, offset=3)
     assert torch.equal(p16, p32.bfloat16())
+
+
+def test_f1_variants_match_reference_goldens_bitwise():
+    """decoder_PGD, input-space adv_input (Seg + Det) and rpn_roi_PGD('roi') vs vectors produced by the
+    unmodified reference functions (oracle/gen_golden.py f1)."""
+    import os
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "pgd_f1.npz"))
+    seg, det = PKG.segmentation, PKG.detection
+    n = 0
+    for tag in ("n", "r"):
+        def load(key):
+            gamma, eps, steps, randinit, clip = z[key + "_meta"]
+            x = torch.from_numpy(z[key + "_x"]).to(dev())
+            model = InjectingModel([torch.from_numpy(g).to(dev()) for g in z[key + "_grads"]])
+            return x, model, dict(steps=int(steps), eps=float(eps), gamma=float(gamma), randinit=bool(randinit),
+                                  clip=bool(clip), noise=torch.from_numpy(z[key + "_u"]))
+        x, model, kw = load(f"seg_decoder_{tag}")
+        model_call = lambda inputs, m=model: m._next(inputs["adv"]["adv"])
+        d = seg.decoder_PGD({"adv": x.clone(), "aux": 1}, None, lambda o, y: o, y=None, model=model_call, idx="aspp", **kw)
+        assert d["aux"] == 1 and d["adv"].is_leaf and d["adv"].requires_grad
+        assert_bitwise(d["adv"], z[f"seg_decoder_{tag}_out"], f"seg decoder {tag}")
+        x, model, kw = load(f"seg_advinput_{tag}")
+        r = seg.adv_input(x, lambda o, y: o, y=None, model=lambda inputs, m=model: m._next(inputs["x"]), **kw)
+        assert_bitwise(r, z[f"seg_advinput_{tag}_out"], f"seg adv_input {tag}")
+        assert float(r.min()) >= 0.0 and float(r.max()) <= 1.0
+        x, model, kw = load(f"det_advinput_{tag}")
+
+        class DetIn:
+            def __init__(self, m): self.m = m
+            def train(self): return self
+            def forward(self, inputs, bb, lb):
+                out = self.m._next(inputs["x"]); zz = out * 0
+                return out, zz, zz, zz
+        r = det.adv_input(x, y={"bb": None, "lb": None}, model=DetIn(model), **kw)
+        assert_bitwise(r, z[f"det_advinput_{tag}_out"], f"det adv_input {tag}")
+        x, model, kw = load(f"det_roi_{tag}")
+
+        class DetRoi:
+            def __init__(self, m): self.m = m
+            def train(self): return self
+            def forward(self, inputs, bb, lb):
+                out = self.m._next(inputs["adv"]["roi_output_dict"]["roi_feature_map"]); zz = out * 0
+                return zz, zz, out, zz
+        d = det.rpn_roi_PGD("roi", {"roi_output_dict": {"roi_feature_map": x.clone()}}, y={"bb": None, "lb": None},
+                            model=DetRoi(model), **kw)
+        assert_bitwise(d["roi_output_dict"]["roi_feature_map"], z[f"det_roi_{tag}_out"], f"det roi {tag}")
+        n += 4
+    assert n == 8
+    # 'rpn' branch: the reference never updates x_adv (update commented out, Detection/attack_algo.py:127-147)
+    feat = feature_like((2, 8, 4, 4), torch.Generator().manual_seed(0)).to(dev())
+    d = det.rpn_roi_PGD("rpn", {"rpn_feature_map_dict": {"rpn_feature": feat}}, y=None, model=None, steps=2,
+                        eps=2 / 255, gamma=1 / 255, randinit=False)
+    out = d["rpn_feature_map_dict"]["rpn_feature"]
+    assert out.is_leaf and out.requires_grad and torch.equal(out.detach(), feat)
