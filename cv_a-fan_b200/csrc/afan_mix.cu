@@ -31,7 +31,7 @@ struct Welford {
 // NP = pixel groups per thread (group q sits 32*VEC pixels after group q-1): the scalar path takes NP = 2 so that
 // every thread owns 4 independent Welford chains (2 pixels x 2 tensors) and twice the loads in flight.
 template <int VEC, int NP, int kMixThreads, int kMixUnroll>
-__global__ void __launch_bounds__(kMixThreads)
+__global__ void __launch_bounds__(kMixThreads, kMixThreads <= 512 ? 2 : 1)
 mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ adv, float* __restrict__ out,
                    unsigned int c, unsigned int hw, unsigned int tiles_per_sample) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
@@ -308,17 +308,21 @@ AFAN_EXPORT int afan_mix_feature_f32(const float* clean, const float* adv, float
     if (c >= (int64_t(1) << 31) || hw >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = (hw % 4 == 0) && aligned16(clean) && aligned16(adv) && aligned16(out);
-    const int64_t pt = vec ? 128 : 64;
+    // pixel groups per thread: 2 only when the grid still covers the chip twice over (more ILP per thread), else 1
+    const bool np2 = !vec && n * ((hw + 63) / 64) >= 4 * static_cast<int64_t>(sm_count());
+    const int64_t pt = vec ? 128 : (np2 ? 64 : 32);
     const int64_t tiles = (hw + pt - 1) / pt;
     if (n * tiles >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
     const unsigned int grid = static_cast<unsigned int>(n * tiles);
     const unsigned int uc = static_cast<unsigned int>(c), uhw = static_cast<unsigned int>(hw), ut = static_cast<unsigned int>(tiles);
     if (vec)
         mix_feature_kernel<4, 1, 512, 4><<<grid, 512, 0, st>>>(clean, adv, out, uc, uhw, ut);
-    else if (grid < 2u * static_cast<unsigned int>(sm_count()))        // few tiles: one fat CTA per SM
-        mix_feature_kernel<1, 2, 1024, 4><<<grid, 1024, 0, st>>>(clean, adv, out, uc, uhw, ut);
-    else                                                             // many tiles: several 512-thread CTAs per SM
+    else if (grid < 2u * static_cast<unsigned int>(sm_count()))        // few tiles: one fat CTA per SM keeps 64 KB in flight
+        mix_feature_kernel<1, 1, 1024, 8><<<grid, 1024, 0, st>>>(clean, adv, out, uc, uhw, ut);
+    else if (np2)                                                    // many tiles: 2 pixel groups per thread, 2-3 CTAs per SM
         mix_feature_kernel<1, 2, 512, 4><<<grid, 512, 0, st>>>(clean, adv, out, uc, uhw, ut);
+    else
+        mix_feature_kernel<1, 1, 512, 8><<<grid, 512, 0, st>>>(clean, adv, out, uc, uhw, ut);
     return launch_status();
 }
 
