@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams 
     if (!last_cta_arrives(p.counters + ch, p.groups * p.splits, &sflag)) return;
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
-    constexpr int kMaxGroups = 8;
+    constexpr int kMaxGroups = 16;                    // learnable-eta A-FAN batches 9 adversarial groups + clean
     double t0[kMaxGroups], t1[kMaxGroups];
     for (unsigned int gg = 0; gg < p.groups; ++gg) {
         const volatile double* pp = reinterpret_cast<const volatile double*>(p.partials + (static_cast<size_t>(gg) * p.c + ch) * p.splits);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams 
 __global__ void bn_fwd_finalize_kernel(const ReduceParams p, const double* sums) {
     const unsigned int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= p.c) return;
-    double t0[8], t1[8];
+    double t0[16], t1[16];
     for (unsigned int g = 0; g < p.groups; ++g) {
         t0[g] = sums[(static_cast<size_t>(g) * p.c + ch) * 2];
         t1[g] = sums[(static_cast<size_t>(g) * p.c + ch) * 2 + 1];
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParam
 // no global-memory partials, no atomics, no second launch.
 // =====================================================================================================
 constexpr int kClusterThreads = 512;
-constexpr int kMaxGroups = 8;
+constexpr int kMaxGroups = 16;                    // learnable-eta A-FAN batches 9 adversarial groups + clean
 constexpr int kMaxCluster = 8;                     // portable cluster size on sm_100a
 
 struct ClusterParams {
@@ -1042,7 +1042,7 @@ __host__ inline BnShape bn_shape(int64_t groups, int64_t n, int64_t c, int64_t h
     BnShape s{};
     s.err = AFAN_OK;
     if (groups < 1 || n < 0 || c < 0 || hw < 0) { s.err = AFAN_ERR_SIZE; return s; }
-    if (groups > 8 || groups * c > 65535) { s.err = AFAN_ERR_UNSUPPORTED; return s; }
+    if (groups > 16 || groups * c > 65535) { s.err = AFAN_ERR_UNSUPPORTED; return s; }
     const int64_t total = groups * n * c * hw;
     if (total >= (int64_t(1) << 32) || n * hw >= (int64_t(1) << 32)) { s.err = AFAN_ERR_UNSUPPORTED; return s; }
     s.vec = all_aligned && (hw % 4 == 0);
@@ -1221,7 +1221,7 @@ AFAN_EXPORT int afan_bn_fwd_finalize_f32(const double* sums, double count, const
                                          float* save_invstd, void* workspace, int64_t workspace_bytes, int64_t groups,
                                          int64_t c, float eps, float momentum, int replay, afan_stream_t stream) {
     if (groups < 1 || c < 0 || !(count > 0)) return AFAN_ERR_SIZE;
-    if (groups > 8) return AFAN_ERR_UNSUPPORTED;
+    if (groups > 16) return AFAN_ERR_UNSUPPORTED;
     if (c == 0) return AFAN_OK;
     if (!sums || !save_mean || !save_invstd) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
@@ -1353,7 +1353,7 @@ AFAN_EXPORT int afan_bn_bwd_finalize_f32(const double* sums, double count, const
                                          const float* save_invstd, void* workspace, int64_t workspace_bytes,
                                          int64_t groups, int64_t c, afan_stream_t stream) {
     if (groups < 1 || c < 0 || !(count > 0)) return AFAN_ERR_SIZE;
-    if (groups > 8) return AFAN_ERR_UNSUPPORTED;
+    if (groups > 16) return AFAN_ERR_UNSUPPORTED;
     if (c == 0) return AFAN_OK;
     if (!sums || !save_mean || !save_invstd) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;

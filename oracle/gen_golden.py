@@ -309,10 +309,45 @@ def gen_train_cases():
         print(name, "ce:", per_iter[-1], "l2/linf mean:", float(l2m), float(linfm))
 
 
+def gen_learnable_case():
+    """Execute the unmodified reference learnable-eta loop (Classification/main_learnable.py:175-300) on a
+    [3,3,3] net (16 layers) with 9 perturbation layers 4..12.  Initial weights are NOT stored: the product model
+    reproduces the reference init stream under the same seed (tests/test_host_logic.py); a checksum guards it."""
+    rs = ref_shim.load("Classification", "resnet_s")
+    ml = ref_shim.load("Classification", "main_learnable")
+    torch.manual_seed(3)
+    model = rs.ResNet(rs.BasicBlock, [3, 3, 3], num_classes=10, init_weight=1 / 9)
+    init_sum = float(sum(v.double().sum() for v in model.state_dict().values()))
+    points, steps, gamma, eps, bs, iters = [4, 5, 6, 7, 8, 9, 10, 11, 12], 2, 1.0, 2.0, 4, 2
+    gen = torch.Generator().manual_seed(17)
+    images = [torch.rand(bs, 3, 32, 32, generator=gen) for _ in range(iters)]
+    targets = [torch.randint(0, 10, (bs,), generator=gen) for _ in range(iters)]
+    ml.args = argparse.Namespace(steps=steps, gamma=gamma, eps=eps, randinit=False, clip=True, print_freq=10 ** 9, lr=0.1,
+                                 l1_coef=1.0)
+    ml.perturb_idx_list, ml.layer_number = points, len(model.sequential_model)
+    crit = _RecordingCE()
+    opt = torch.optim.SGD(model.sequential_model.parameters(), 0.1, momentum=0.9, weight_decay=5e-4)
+    opt_w = torch.optim.SGD([{"params": model.w, "lr": 0.01, "weight_decay": 0}], 0.01, momentum=0.9, weight_decay=0)
+    with ref_shim.cpu_cuda_identity():
+        top1, loss_avg, l2m, linfm = ml.train(list(zip(images, targets)), model, crit, opt, 1, opt_w)
+    per_iter = np.array(crit.values, dtype=np.float64).reshape(iters, 9 * steps + 9 + 1)
+    out = {"meta": np.array([steps, gamma, eps, bs, iters], dtype=np.float64), "points": np.array(points),
+           "images": torch.stack(images).numpy(), "targets": torch.stack(targets).numpy(), "ce_values": per_iter,
+           "loss_avg": np.float64(loss_avg), "l2_mean": np.asarray(l2m), "linf_mean": np.asarray(linfm),
+           "init_checksum": np.float64(init_sum)}
+    keep = ("w", "sequential_model.1.weight", "sequential_model.15.weight", "sequential_model.15.bias",
+            "sequential_model.8.conv2.weight")
+    for k, v in model.state_dict().items():
+        if k in keep or "running" in k or "num_batches" in k or k.endswith("bn1.weight"):
+            out["final/" + k] = v.detach().numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "cls_learnable.npz"), **out)
+    print("cls_learnable.npz: loss_avg", loss_avg, "w", model.w.detach().numpy())
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "reference not mounted; goldens can only be generated where it is"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    which = sys.argv[1:] or ["pgd", "helpers", "train", "f1"]
+    which = sys.argv[1:] or ["pgd", "helpers", "train", "f1", "learnable"]
     if "pgd" in which:
         gen_pgd_cases()
     if "helpers" in which:
@@ -321,3 +356,5 @@ if __name__ == "__main__":
         gen_train_cases()
     if "f1" in which:
         gen_f1_cases()
+    if "learnable" in which:
+        gen_learnable_case()

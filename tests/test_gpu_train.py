@@ -103,3 +103,43 @@ def test_trainer_vs_cpu_port_resnet20_config1():
         assert abs(float(out["loss"]) - float(loss_ref)) < 2e-3 * float(loss_ref)
         np.testing.assert_allclose(out["l2"].cpu().numpy(), l2.numpy(), rtol=2e-2)
         np.testing.assert_allclose(out["linf"].cpu().numpy(), linf.numpy(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["reference_order", "batched", "batched_graph"])
+def test_learnable_eta_trainer_matches_reference_golden(mode):
+    """9-layer learnable-eta A-FAN vs the unmodified reference main_learnable.train (golden)."""
+    z = np.load(os.path.join(GOLDEN, "cls_learnable.npz"))
+    steps, gamma, eps, bs, iters = z["meta"]
+    torch.manual_seed(3)
+    model = PKG.resnet_s.ResNet(num_blocks=(3, 3, 3), num_classes=10, init_weight=1 / 9)
+    assert abs(float(sum(v.double().sum() for v in model.state_dict().values())) - float(z["init_checksum"])) < 1e-6
+    model.to(dev())
+    tr = PKG.trainer_learnable.LearnableEtaTrainer(
+        model, perturb_idx_list=[int(k) for k in z["points"]], steps=int(steps), gamma=float(gamma), eps=float(eps),
+        randinit=False, clip=True, lr=0.1, w_lr=0.01, l1_coef=1.0, batched=mode != "reference_order",
+        use_cuda_graph=mode == "batched_graph")
+    losses = []
+    for i in range(int(iters)):
+        w_l1 = float(model.w.detach().abs().sum())
+        out = tr.step(torch.from_numpy(z["images"][i]).to(dev()), torch.from_numpy(z["targets"][i]).to(dev()))
+        ce = z["ce_values"][i]
+        expect = (ce[-1] + ce[-10:-1].sum() / 9) / 2 + w_l1
+        assert abs(float(out["loss"]) - expect) < 3e-3 * expect, (mode, i, float(out["loss"]), expect)
+        losses.append(float(out["loss"]))
+    assert abs(np.mean(losses) - float(z["loss_avg"])) < 3e-3 * float(z["loss_avg"])
+    np.testing.assert_allclose(tr.point_norms()[:, 1].mean(dim=1).cpu().numpy(), z["linf_mean"], rtol=2e-2)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for k in z.files:
+        if not k.startswith("final/"):
+            continue
+        ref, got = z[k], sd[k[6:]]
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(ref), k
+        elif "running" in k:
+            # reference_order reproduces the pass order; batched mode only reorders which pass's statistics enter the
+            # running average when (declared deviation), so the averages agree loosely
+            tol = dict(rtol=2e-3, atol=2e-4) if mode == "reference_order" else dict(rtol=0.15, atol=5e-2)
+            np.testing.assert_allclose(got.numpy(), ref, err_msg=k, **tol)
+        else:
+            np.testing.assert_allclose(got.numpy(), ref, rtol=1e-2, atol=1e-3, err_msg=k)
+    np.testing.assert_allclose(float(model.w.detach().sum()), 1.0, atol=1e-5)       # sum_project invariant
