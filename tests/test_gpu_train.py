@@ -143,3 +143,34 @@ def test_learnable_eta_trainer_matches_reference_golden(mode):
         else:
             np.testing.assert_allclose(got.numpy(), ref, rtol=1e-2, atol=1e-3, err_msg=k)
     np.testing.assert_allclose(float(model.w.detach().sum()), 1.0, atol=1e-5)       # sum_project invariant
+
+
+def test_loss_and_accuracy_curves_track_cpu_port():
+    """North star: 'training loss and clean accuracy curves within a stated tolerance'.  40 iterations of config 1's net
+    (resnet_s [3,3,3], PGD-3 + random start + clip, learnable synthetic task) on the GPU trainer (head cache, dual-BN,
+    CUDA graph) and on the CPU port of the reference from the same weights / data / noise.
+    Tolerance: every loss within 3 % of the port's, mean |delta loss| < 1 %, running clean accuracy within 3 points."""
+    torch.manual_seed(3)
+    model = PKG.resnet_s.resnet20()
+    ref = ref_t.CifarResNetRef((3, 3, 3), 10)
+    ref.load_state_dict(model.state_dict())
+    model.to(dev())
+    g = torch.Generator().manual_seed(12)
+    protos = torch.rand(10, 3, 32, 32, generator=g)                 # class prototypes: a task that can be learnt
+    tr = PKG.trainer.AfanTrainer(model, perturb_idx=7, steps=3, gamma=1.0, eps=2.0, randinit=True, clip=True, lr=0.05)
+    opt, crit = ref_t.make_sgd(ref, lr=0.05), torch.nn.CrossEntropyLoss()
+    ref.train()
+    rel, acc_g, acc_c = [], [], []
+    for it in range(40):
+        y = torch.randint(0, 10, (32,), generator=g)
+        x = (0.6 * protos[y] + 0.4 * torch.rand(32, 3, 32, 32, generator=g)).clamp(0, 1)
+        noise = torch.rand(32, 16, 32, 32, generator=g)             # layers [0,7) of [3,3,3]: 16 x 32 x 32
+        out = tr.step(x.to(dev()), y.to(dev()), noise.to(dev()))
+        loss_ref, out_ref, _, _, _ = ref_t.afan_train_iteration(ref, opt, crit, x, y, steps=3, gamma=1.0, eps=2.0,
+                                                                perturb_idx=7, randinit=True, clip=True, noise=noise)
+        rel.append(abs(float(out["loss"]) - float(loss_ref)) / float(loss_ref))
+        acc_g.append(float((out["output_clean"].argmax(1).cpu() == y).float().mean()))
+        acc_c.append(float((out_ref.argmax(1) == y).float().mean()))
+    assert max(rel) < 3e-2 and float(np.mean(rel)) < 1e-2, (max(rel), np.mean(rel))
+    assert abs(np.mean(acc_g[-20:]) - np.mean(acc_c[-20:])) < 0.03
+    assert np.mean(acc_c[-10:]) > np.mean(acc_c[:10])               # the task is actually being learnt
