@@ -31,6 +31,8 @@ SIGNATURES = {
     "afan_l2ball_proj_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp]),
     "afan_mix_feature_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "afan_sat_mix_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _i64, _vp]),
+    "afan_nms_workspace_bytes": (_i64, [_i64]),
+    "afan_nms_f32": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64, _i64, _vp]),
     "afan_bn_workspace_bytes": (_i64, [_i64, _i64]),
     "afan_bn_fwd_f32": (_int, [_vp] * 9 + [_vp, _i64] + [_i64] * 4 + [_f32, _f32, _int, _int, _vp]),
     "afan_bn_bwd_f32": (_int, [_vp] * 10 + [_vp, _i64] + [_i64] * 4 + [_int, _vp]),
@@ -55,7 +57,7 @@ SIGNATURES = {
 AFAN_ERR_UNSUPPORTED = -5
 _lib = None
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); bumped by check() on success
-KERNELS_PER_CALL = {"afan_bn_fwd_f32": 2, "afan_bn_bwd_f32": 2}
+KERNELS_PER_CALL = {"afan_nms_f32": 2}
 launch_count = 0
 
 

@@ -64,3 +64,15 @@ def adv_input(x=None, y=None, model=None, steps=3, eps=None, gamma=None, randini
         return compute_loss(*model.train().forward(inputs, y["bb"], y["lb"]))
 
     return torch.clamp(pgd_loop(x, tail_loss, steps, gamma, eps, randinit, clip, **extras), 0, 1.0)
+
+
+def nms(bboxes, scores, threshold):
+    """Detection/support/layer/nms.py (`_C.nms`): indices of the kept boxes, ascending, like the reference returns them
+    (`nms.cu:126-130`).  The suppression itself never leaves the GPU; only sizing the variable-length result
+    synchronises (as torch.nonzero does).  `ops.nms_flags` gives the fixed-size device-side form."""
+    import torch
+    from . import ops
+    if bboxes.numel() == 0:
+        return torch.empty(0, dtype=torch.long, device=bboxes.device)
+    keep, _ = ops.nms_flags(bboxes.float().contiguous(), scores.float().contiguous(), threshold)
+    return torch.nonzero(keep).squeeze(1)

@@ -272,3 +272,25 @@ def sgd_momentum_(param, grad, buf, lr_device, *, momentum=0.9, weight_decay=5e-
                                            float(momentum), float(weight_decay), float(grad_scale), stream()),
           "afan_sgd_momentum_f32")
     return param
+
+
+# ------------------------------------------------------------------------------------------------
+# NMS (f4)
+# ------------------------------------------------------------------------------------------------
+def nms_flags(boxes: torch.Tensor, scores: torch.Tensor, threshold: float):
+    """Greedy NMS on the device.  Returns (keep_flags uint8 [N] by original index, count int32 [1]); no host sync."""
+    if boxes.dim() != 2 or boxes.shape[1] != 4 or scores.shape[0] != boxes.shape[0]:
+        raise AfanError("nms needs boxes [N, 4] and scores [N]")
+    n = boxes.shape[0]
+    keep = torch.zeros(n, dtype=torch.uint8, device=boxes.device)
+    count = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    if n == 0:
+        return keep, count
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    sorted_boxes = boxes.index_select(0, order).contiguous()
+    nbytes = _lib.lib().afan_nms_workspace_bytes(n)
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=boxes.device)
+    check(_lib.lib().afan_nms_f32(f32(sorted_boxes, "boxes"), _lib.dev_ptr(order, torch.int64, "order"), float(threshold),
+                                  _lib.dev_ptr(keep, torch.uint8, "keep"), _lib.dev_ptr(count, torch.int32, "count"),
+                                  ptr(ws), ws.numel() * 8, n, stream()), "afan_nms_f32")
+    return keep, count

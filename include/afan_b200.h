@@ -196,6 +196,16 @@ int afan_p2p_close_handle(void* ptr);
 int afan_bn_affine_f32(const float* x, const float* residual, const float* scale_shift, float* y,
                        int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream);
 
+/* ---- f4: greedy NMS, fully on the device ---------------------------------------------------------------------
+ * Replaces Detection/support/src/cuda/nms.cu:23-131 (+ its D2H mask copy and serial CPU sweep, :99-123).
+ * boxes_sorted: [n][4] (x1,y1,x2,y2) ALREADY sorted by score descending (16-byte aligned); order[i] = original index
+ * of sorted position i.  Legacy "+1" areas; a box is dropped when IoU > threshold with an earlier kept box.
+ * keep_flags [n] (uint8, indexed by ORIGINAL box index) and count_out (device int32, nullable) are written on the
+ * stream; nothing is copied to the host. */
+int64_t afan_nms_workspace_bytes(int64_t n);
+int afan_nms_f32(const float* boxes_sorted, const int64_t* order, float threshold, uint8_t* keep_flags,
+                 int32_t* count_out, void* workspace, int64_t workspace_bytes, int64_t n, afan_stream_t stream);
+
 /* ---- a7 tail: fused SGD(momentum, weight decay) over a flat parameter arena ---------------------
  * Replaces optimizer.step() of torch.optim.SGD, main_perturb.py:72-74,201:
  *     g = grad*grad_scale + wd*p;  buf = momentum*buf + g;  p -= lr*buf      (buf starts at 0)

@@ -334,3 +334,34 @@ ORC_API void orc_philox_uniform_f32(float *u, int64_t n, uint64_t seed, uint64_t
         for (int j = 0; j < 4 && i + j < n; ++j) u[i + j] = (float)(r[j] >> 8) * 0x1p-24f;
     }
 }
+
+/* ---- f4: greedy NMS, Detection/support/src/cuda/nms.cu:13-21,99-123 (GPU flavour: suppress when IoU > thr;
+ * the CPU flavour nms_cpu.cpp:60 uses >=) with the legacy "+1" areas.  order[] = indices sorted by score
+ * descending (computed by the caller); keep[i] = 1 for kept ORIGINAL indices.  Returns the number kept. */
+ORC_API int64_t orc_nms_f32(const float *boxes, const int64_t *order, int64_t n, float thr, int strict_gt, uint8_t *keep) {
+    uint8_t *supp = (uint8_t *)calloc((size_t)(n > 0 ? n : 1), 1);
+    int64_t kept = 0;
+    for (int64_t i = 0; i < n; ++i) keep[i] = 0;
+    for (int64_t _i = 0; _i < n; ++_i) {
+        int64_t i = order[_i];
+        if (supp[i]) continue;
+        keep[i] = 1; ++kept;
+        const float *a = boxes + 4 * i;
+        float sa = (a[2] - a[0] + 1) * (a[3] - a[1] + 1);
+        for (int64_t _j = _i + 1; _j < n; ++_j) {
+            int64_t j = order[_j];
+            if (supp[j]) continue;
+            const float *b = boxes + 4 * j;
+            float left = a[0] > b[0] ? a[0] : b[0], right = a[2] < b[2] ? a[2] : b[2];
+            float top = a[1] > b[1] ? a[1] : b[1], bottom = a[3] < b[3] ? a[3] : b[3];
+            float w = right - left + 1, h = bottom - top + 1;
+            if (w < 0) w = 0;
+            if (h < 0) h = 0;
+            float inter = w * h, sb = (b[2] - b[0] + 1) * (b[3] - b[1] + 1);
+            float ovr = inter / (sa + sb - inter);
+            if (strict_gt ? (ovr > thr) : (ovr >= thr)) supp[j] = 1;
+        }
+    }
+    free(supp);
+    return kept;
+}

@@ -344,10 +344,19 @@ def gen_learnable_case():
     print("cls_learnable.npz: loss_avg", loss_avg, "w", model.w.detach().numpy())
 
 
+def gen_nms_case():
+    """The reference's OWN golden vectors for NMS (Detection/test/nms/nms-large-{input,output}.npy, used by
+    Detection/test/nms/test_nms.py:39-52 with threshold 0.7) repackaged as one fixture (data, not source)."""
+    d = os.path.join(ref_shim.REFERENCE_ROOT, "Detection", "test", "nms")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "nms_large.npz"), input=np.load(os.path.join(d, "nms-large-input.npy")),
+                        output=np.load(os.path.join(d, "nms-large-output.npy")), threshold=np.float32(0.7))
+    print("nms_large.npz written")
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "reference not mounted; goldens can only be generated where it is"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    which = sys.argv[1:] or ["pgd", "helpers", "train", "f1", "learnable"]
+    which = sys.argv[1:] or ["pgd", "helpers", "train", "f1", "learnable", "nms"]
     if "pgd" in which:
         gen_pgd_cases()
     if "helpers" in which:
@@ -358,3 +367,5 @@ if __name__ == "__main__":
         gen_f1_cases()
     if "learnable" in which:
         gen_learnable_case()
+    if "nms" in which:
+        gen_nms_case()

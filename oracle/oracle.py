@@ -203,3 +203,15 @@ def philox_uniform(n, seed, offset=0):
     u = np.empty(n, np.float32)
     lib().orc_philox_uniform_f32(_p(u), _i64(n), ctypes.c_uint64(seed), ctypes.c_uint64(offset))
     return u
+
+
+def nms(boxes, scores, thr, strict_gt=True):
+    """Detection/support/src/cuda/nms.cu (IoU > thr) / cpu/nms_cpu.cpp (>=): kept ORIGINAL indices, ascending."""
+    boxes = _f32(boxes)
+    n = boxes.shape[0]
+    order = np.ascontiguousarray(np.argsort(-np.asarray(scores, np.float32), kind="stable"), dtype=np.int64)
+    keep = np.zeros(max(n, 1), np.uint8)
+    lib().orc_nms_f32.restype = ctypes.c_int64
+    lib().orc_nms_f32(_p(boxes), order.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _i64(n), ctypes.c_float(thr),
+                      int(bool(strict_gt)), keep.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    return np.nonzero(keep[:n])[0].astype(np.int64)

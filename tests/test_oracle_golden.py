@@ -153,3 +153,17 @@ def test_torch_port_replays_reference_training(golden_dir, name):
             assert int(v) == int(final[k]), k
         else:
             np.testing.assert_allclose(v.numpy(), final[k], rtol=2e-3, atol=2e-5, err_msg=k)
+
+
+def test_nms_oracle_reproduces_the_references_own_golden(golden_dir):
+    """Detection/test/nms/test_nms.py:39-52: 9770 boxes -> 1934 kept at threshold 0.7 (the reference's only unit test)."""
+    z = np.load(os.path.join(golden_dir, "nms_large.npz"))
+    det, expect = z["input"], np.sort(z["output"])
+    assert det.shape == (9770, 5) and expect.shape == (1934,)
+    for strict in (True, False):                     # GPU flavour (>) and CPU flavour (>=) agree on this input
+        assert np.array_equal(orc.nms(det[:, :4], det[:, 4], float(z["threshold"]), strict), expect)
+    # test_nms.py:19-37: empty / single / small
+    assert orc.nms(np.zeros((0, 4), np.float32), np.zeros(0, np.float32), 0.7).size == 0
+    assert orc.nms(np.array([[5, 5, 10, 10]], np.float32), np.array([0.8], np.float32), 0.7).tolist() == [0]
+    small = np.array([[5, 5, 10, 10], [5, 5, 10, 10], [5, 5, 30, 30]], np.float32)
+    assert orc.nms(small, np.array([0.6, 0.9, 0.4], np.float32), 0.7).tolist() == [1, 2]
