@@ -33,6 +33,8 @@ SIGNATURES = {
     "afan_sat_mix_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _i64, _vp]),
     "afan_nms_workspace_bytes": (_i64, [_i64]),
     "afan_nms_f32": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "afan_roi_align_fwd_f32": (_int, [_vp, _vp, _vp] + [_i64] * 7 + [_f32, _int, _vp]),
+    "afan_roi_align_bwd_f32": (_int, [_vp, _vp, _vp] + [_i64] * 7 + [_f32, _int, _vp]),
     "afan_bn_workspace_bytes": (_i64, [_i64, _i64]),
     "afan_bn_fwd_f32": (_int, [_vp] * 9 + [_vp, _i64] + [_i64] * 4 + [_f32, _f32, _int, _int, _vp]),
     "afan_bn_bwd_f32": (_int, [_vp] * 10 + [_vp, _i64] + [_i64] * 4 + [_int, _vp]),

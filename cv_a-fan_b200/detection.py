@@ -76,3 +76,49 @@ def nms(bboxes, scores, threshold):
         return torch.empty(0, dtype=torch.long, device=bboxes.device)
     keep, _ = ops.nms_flags(bboxes.float().contiguous(), scores.float().contiguous(), threshold)
     return torch.nonzero(keep).squeeze(1)
+
+
+class _ROIAlign(__import__("torch").autograd.Function):
+    """Detection/support/layer/roi_align.py:11-44 on the sm_100a kernels."""
+
+    @staticmethod
+    def forward(ctx, input, roi, output_size, spatial_scale, sampling_ratio):
+        import torch
+        from . import _lib
+        oh, ow = (output_size, output_size) if isinstance(output_size, int) else output_size
+        input, roi = input.contiguous(), roi.contiguous().float()
+        n, c, h, w = input.shape
+        out = torch.empty(roi.shape[0], c, oh, ow, dtype=input.dtype, device=input.device)
+        _lib.check(_lib.lib().afan_roi_align_fwd_f32(_lib.f32(input, "input"), _lib.f32(roi, "roi"), _lib.f32(out), n, c, h, w,
+                                                     roi.shape[0], oh, ow, float(spatial_scale), int(sampling_ratio),
+                                                     _lib.stream()), "afan_roi_align_fwd_f32")
+        ctx.save_for_backward(roi)
+        ctx.cfg = (n, c, h, w, oh, ow, float(spatial_scale), int(sampling_ratio))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        import torch
+        from . import _lib
+        (roi,) = ctx.saved_tensors
+        n, c, h, w, oh, ow, scale, ratio = ctx.cfg
+        grad_output = grad_output.contiguous()
+        dfeat = torch.empty(n, c, h, w, dtype=grad_output.dtype, device=grad_output.device)
+        _lib.check(_lib.lib().afan_roi_align_bwd_f32(_lib.f32(grad_output, "grad_output"), _lib.f32(roi), _lib.f32(dfeat), n, c,
+                                                     h, w, roi.shape[0], oh, ow, scale, ratio, _lib.stream()),
+                   "afan_roi_align_bwd_f32")
+        return dfeat, None, None, None, None
+
+
+roi_align = _ROIAlign.apply
+
+
+class ROIAlign(__import__("torch").nn.Module):
+    """Detection/support/layer/roi_align.py:50-68."""
+
+    def __init__(self, output_size, spatial_scale, sampling_ratio):
+        super().__init__()
+        self.output_size, self.spatial_scale, self.sampling_ratio = output_size, spatial_scale, sampling_ratio
+
+    def forward(self, input, rois):
+        return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio)

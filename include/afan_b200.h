@@ -206,6 +206,18 @@ int64_t afan_nms_workspace_bytes(int64_t n);
 int afan_nms_f32(const float* boxes_sorted, const int64_t* order, float threshold, uint8_t* keep_flags,
                  int32_t* count_out, void* workspace, int64_t workspace_bytes, int64_t n, afan_stream_t stream);
 
+/* ---- f4: ROIAlign ------------------------------------------------------------------------------------------------
+ * Replaces Detection/support/src/cuda/ROIAlign_cuda.cu:64-122 (forward) and :177-254 (backward), bound by
+ * Detection/support/layer/roi_align.py.  feat [n][c][h][w]; rois [r][5] = (batch index, x1, y1, x2, y2) in image
+ * coordinates; out / dout [r][c][ph][pw].  Legacy (non-"aligned") coordinates; sampling_ratio <= 0 -> adaptive grid
+ * ceil(roi_size / pooled_size).  _bwd zero-fills dfeat itself, then scatters with atomic adds. */
+int afan_roi_align_fwd_f32(const float* feat, const float* rois, float* out, int64_t n, int64_t c, int64_t h,
+                           int64_t w, int64_t r, int64_t ph, int64_t pw, float spatial_scale,
+                           int sampling_ratio, afan_stream_t stream);
+int afan_roi_align_bwd_f32(const float* dout, const float* rois, float* dfeat, int64_t n, int64_t c, int64_t h,
+                           int64_t w, int64_t r, int64_t ph, int64_t pw, float spatial_scale,
+                           int sampling_ratio, afan_stream_t stream);
+
 /* ---- a7 tail: fused SGD(momentum, weight decay) over a flat parameter arena ---------------------
  * Replaces optimizer.step() of torch.optim.SGD, main_perturb.py:72-74,201:
  *     g = grad*grad_scale + wd*p;  buf = momentum*buf + g;  p -= lr*buf      (buf starts at 0)

@@ -365,3 +365,53 @@ ORC_API int64_t orc_nms_f32(const float *boxes, const int64_t *order, int64_t n,
     free(supp);
     return kept;
 }
+
+/* ---- f4: ROIAlign forward / backward, Detection/support/src/cuda/ROIAlign_cuda.cu:15-122,124-254
+ * (== Detection/support/src/cpu/ROIAlign_cpu.cpp; the maskrcnn-benchmark kernel that torchvision.ops.roi_align
+ * (aligned=False) descends from).  feat [n][c][h][w]; rois [r][5]; out [r][c][ph][pw]. */
+static int orc_tap(float y, float x, int h, int w, int off[4], float wt[4]) {
+    if (y < -1.0f || y > h || x < -1.0f || x > w) return 0;
+    if (y <= 0) y = 0;
+    if (x <= 0) x = 0;
+    int y0 = (int)y, x0 = (int)x, y1, x1;
+    if (y0 >= h - 1) { y1 = y0 = h - 1; y = (float)y0; } else y1 = y0 + 1;
+    if (x0 >= w - 1) { x1 = x0 = w - 1; x = (float)x0; } else x1 = x0 + 1;
+    float ly = y - y0, lx = x - x0, hy = 1.f - ly, hx = 1.f - lx;
+    off[0] = y0 * w + x0; off[1] = y0 * w + x1; off[2] = y1 * w + x0; off[3] = y1 * w + x1;
+    wt[0] = hy * hx; wt[1] = hy * lx; wt[2] = ly * hx; wt[3] = ly * lx;
+    return 1;
+}
+ORC_API void orc_roi_align_f32(const float *feat, const float *rois, float *out /*fwd: written*/, const float *dout /*bwd*/,
+                               float *dfeat /*bwd: accumulated into (caller zeroes)*/, int64_t c, int64_t h, int64_t w,
+                               int64_t r, int64_t ph, int64_t pw, float scale, int sampling_ratio) {
+    for (int64_t ri = 0; ri < r; ++ri) {
+        const float *roi = rois + 5 * ri;
+        int b = (int)roi[0];
+        float sw = roi[1] * scale, sh = roi[2] * scale, ew = roi[3] * scale, eh = roi[4] * scale;
+        float rw = ew - sw > 1.f ? ew - sw : 1.f, rh = eh - sh > 1.f ? eh - sh : 1.f;
+        float bh = rh / (float)ph, bw = rw / (float)pw;
+        int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / ph);
+        int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / pw);
+        float count = (float)(gh * gw);
+        for (int64_t ci = 0; ci < c; ++ci) {
+            const float *plane = feat ? feat + (b * c + ci) * h * w : NULL;
+            float *dplane = dfeat ? dfeat + (b * c + ci) * h * w : NULL;
+            for (int64_t oh = 0; oh < ph; ++oh)
+                for (int64_t ow = 0; ow < pw; ++ow) {
+                    int64_t oi = ((ri * c + ci) * ph + oh) * pw + ow;
+                    float acc = 0.f;
+                    for (int iy = 0; iy < gh; ++iy) {
+                        float y = sh + oh * bh + (iy + .5f) * bh / (float)gh;
+                        for (int ix = 0; ix < gw; ++ix) {
+                            float x = sw + ow * bw + (ix + .5f) * bw / (float)gw;
+                            int off[4]; float wt[4];
+                            if (!orc_tap(y, x, (int)h, (int)w, off, wt)) continue;
+                            if (out) acc += wt[0] * plane[off[0]] + wt[1] * plane[off[1]] + wt[2] * plane[off[2]] + wt[3] * plane[off[3]];
+                            if (dplane) for (int k = 0; k < 4; ++k) dplane[off[k]] += dout[oi] * wt[k] / count;
+                        }
+                    }
+                    if (out) out[oi] = acc / count;
+                }
+        }
+    }
+}

@@ -215,3 +215,21 @@ def nms(boxes, scores, thr, strict_gt=True):
     lib().orc_nms_f32(_p(boxes), order.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _i64(n), ctypes.c_float(thr),
                       int(bool(strict_gt)), keep.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
     return np.nonzero(keep[:n])[0].astype(np.int64)
+
+
+def roi_align(feat, rois, output_size, spatial_scale, sampling_ratio=0, dout=None):
+    """Detection/support/src/cuda/ROIAlign_cuda.cu fwd (:64-122) and, when dout is given, bwd (:177-254).
+    Returns out [R,C,PH,PW] (and dfeat [N,C,H,W] when dout is given)."""
+    feat, rois = _f32(feat), _f32(rois)
+    n, c, h, w = feat.shape
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    r = rois.shape[0]
+    out = np.zeros((r, c, ph, pw), np.float32)
+    args = (_i64(c), _i64(h), _i64(w), _i64(r), _i64(ph), _i64(pw), ctypes.c_float(spatial_scale), int(sampling_ratio))
+    lib().orc_roi_align_f32(_p(feat), _p(rois), _p(out), _p(None), _p(None), *args)
+    if dout is None:
+        return out
+    dout = _f32(dout)
+    dfeat = np.zeros_like(feat)
+    lib().orc_roi_align_f32(_p(None), _p(rois), _p(None), _p(dout), _p(dfeat), *args)
+    return out, dfeat

@@ -167,3 +167,21 @@ def test_nms_oracle_reproduces_the_references_own_golden(golden_dir):
     assert orc.nms(np.array([[5, 5, 10, 10]], np.float32), np.array([0.8], np.float32), 0.7).tolist() == [0]
     small = np.array([[5, 5, 10, 10], [5, 5, 10, 10], [5, 5, 30, 30]], np.float32)
     assert orc.nms(small, np.array([0.6, 0.9, 0.4], np.float32), 0.7).tolist() == [1, 2]
+
+
+def test_roi_align_oracle_matches_torchvision_lineage():
+    """The reference's ROIAlign is the maskrcnn-benchmark kernel; torchvision.ops.roi_align(aligned=False) on CPU is its
+    direct descendant (third-party check of the restatement, torchvision 0.26)."""
+    tv_ops = pytest.importorskip("torchvision.ops")
+    g = torch.Generator().manual_seed(2)
+    feat = torch.randn(2, 5, 19, 23, generator=g)
+    rois = torch.tensor([[0, 3.0, 5.0, 120.0, 90.0], [1, 0.0, 0.0, 40.0, 30.0], [0, 200.0, 10.0, 400.0, 300.0],
+                         [1, 50.0, 60.0, 50.5, 60.5], [0, -20.0, -10.0, 30.0, 40.0]])
+    for ratio in (0, 2):
+        ft = feat.clone().requires_grad_(True)
+        ref = tv_ops.roi_align(ft, rois, (7, 7), spatial_scale=1 / 16, sampling_ratio=ratio if ratio else -1, aligned=False)
+        dy = torch.randn(ref.shape, generator=g)
+        ref.backward(dy)
+        out, dfeat = orc.roi_align(feat.numpy(), rois.numpy(), (7, 7), 1 / 16, ratio, dout=dy.numpy())
+        np.testing.assert_allclose(out, ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(dfeat, ft.grad.numpy(), rtol=1e-4, atol=1e-5)
