@@ -28,7 +28,7 @@ def test_roi_align_fwd_bwd_vs_oracle(shape, r, out, scale, ratio):
     y.backward(dy.to(dev()))
     y_ref, d_ref = orc.roi_align(feat.numpy(), rois.numpy(), out, scale, ratio, dout=dy.numpy())
     np.testing.assert_allclose(y.detach().cpu().numpy(), y_ref, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(ft.grad.cpu().numpy(), d_ref, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(ft.grad.cpu().numpy(), d_ref, rtol=1e-4, atol=5e-5)   # atomic scatter: summation order differs
 
 
 def test_roi_align_empty_rois():
