@@ -21,13 +21,21 @@ __device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi, f
     g.batch = static_cast<int>(roi[0]);
     g.start_w = roi[1] * scale;
     g.start_h = roi[2] * scale;
-    const float roi_w = fmaxf(roi[3] * scale - g.start_w, 1.f);      // malformed ROIs are forced to 1x1
-    const float roi_h = fmaxf(roi[4] * scale - g.start_h, 1.f);
+    // explicit round-to-nearest ops: an FMA-contracted coordinate can land on the other side of an integer / of the
+    // "outside the map" test and change which taps a sample uses
+    const float roi_w = fmaxf(__fsub_rn(__fmul_rn(roi[3], scale), g.start_w), 1.f);      // malformed ROIs are forced to 1x1
+    const float roi_h = fmaxf(__fsub_rn(__fmul_rn(roi[4], scale), g.start_h), 1.f);
     g.bin_w = roi_w / static_cast<float>(pw);
     g.bin_h = roi_h / static_cast<float>(ph);
     g.grid_w = sampling_ratio > 0 ? sampling_ratio : static_cast<int>(ceilf(roi_w / pw));
     g.grid_h = sampling_ratio > 0 ? sampling_ratio : static_cast<int>(ceilf(roi_h / ph));
     return g;
+}
+
+// start + p * bin + (i + .5) * bin / grid, evaluated left to right with one rounding per operation
+__device__ __forceinline__ float sample_coord(float start, int p, float bin, int i, int grid) {
+    return __fadd_rn(__fadd_rn(start, __fmul_rn(static_cast<float>(p), bin)),
+                     __fdiv_rn(__fmul_rn(static_cast<float>(i) + .5f, bin), static_cast<float>(grid)));
 }
 
 struct Tap {                 // the four neighbours of one sample point and their bilinear weights
@@ -64,9 +72,9 @@ roi_align_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ r
         const float count = static_cast<float>(g.grid_h * g.grid_w);
         float acc = 0.f;
         for (int iy = 0; iy < g.grid_h; ++iy) {
-            const float y = g.start_h + oh * g.bin_h + (iy + .5f) * g.bin_h / static_cast<float>(g.grid_h);
+            const float y = sample_coord(g.start_h, oh, g.bin_h, iy, g.grid_h);
             for (int ix = 0; ix < g.grid_w; ++ix) {
-                const float x = g.start_w + ow * g.bin_w + (ix + .5f) * g.bin_w / static_cast<float>(g.grid_w);
+                const float x = sample_coord(g.start_w, ow, g.bin_w, ix, g.grid_w);
                 const Tap t = make_tap(y, x, height, width);
                 if (t.lo >= 0)
                     acc += t.w1 * __ldg(plane + t.lo) + t.w2 * __ldg(plane + t.hi_x) + t.w3 * __ldg(plane + t.hi_y) +
@@ -89,9 +97,9 @@ roi_align_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ r
         const float count = static_cast<float>(g.grid_h * g.grid_w);
         const float d = __ldcs(dout + idx);
         for (int iy = 0; iy < g.grid_h; ++iy) {
-            const float y = g.start_h + oh * g.bin_h + (iy + .5f) * g.bin_h / static_cast<float>(g.grid_h);
+            const float y = sample_coord(g.start_h, oh, g.bin_h, iy, g.grid_h);
             for (int ix = 0; ix < g.grid_w; ++ix) {
-                const float x = g.start_w + ow * g.bin_w + (ix + .5f) * g.bin_w / static_cast<float>(g.grid_w);
+                const float x = sample_coord(g.start_w, ow, g.bin_w, ix, g.grid_w);
                 const Tap t = make_tap(y, x, height, width);
                 if (t.lo >= 0) {
                     atomicAdd(plane + t.lo, d * t.w1 / count);
