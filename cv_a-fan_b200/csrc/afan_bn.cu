@@ -391,6 +391,8 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const C
     using V = typename std::conditional<VEC == 4, float4, float>::type;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
+    pdl_wait();                                                     // PDL: scheduled during the previous kernel's tail
+    pdl_launch_dependents();
     __shared__ double2 s_part[kMaxGroups];
     __shared__ double2 s_all[kMaxGroups][kMaxCluster];
     __shared__ double2 s_stat[kMaxGroups];                          // (mean, unbiased var) for the running update
@@ -507,6 +509,8 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
     using V = typename std::conditional<VEC == 4, float4, float>::type;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
+    pdl_wait();                                                     // PDL: scheduled during the previous kernel's tail
+    pdl_launch_dependents();
     __shared__ double2 s_part[kMaxGroups];
     __shared__ double2 s_all[kMaxGroups][kMaxCluster];
     __shared__ double2 s_sum[kMaxGroups];
@@ -768,6 +772,8 @@ __global__ void __launch_bounds__(kClusterThreads, (G * NV <= 8) ? 2 : 1)
 bn_fwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
+    pdl_wait();                                                     // PDL: scheduled during the previous kernel's tail
+    pdl_launch_dependents();
     __shared__ double2 s_part[kMaxGroups];
     __shared__ double2 s_all[kMaxGroups][kMaxCluster];
     __shared__ double2 s_stat[kMaxGroups];
@@ -876,6 +882,8 @@ __global__ void __launch_bounds__(kClusterThreads, (G * NV <= 4) ? 2 : 1)
 bn_bwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
+    pdl_wait();                                                     // PDL: scheduled during the previous kernel's tail
+    pdl_launch_dependents();
     __shared__ double2 s_part[kMaxGroups];
     __shared__ double2 s_all[kMaxGroups][kMaxCluster];
     __shared__ double2 s_sum[kMaxGroups];
@@ -1022,11 +1030,13 @@ int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st, co
     cfg.gridDim = dim3(p.c * cs);
     cfg.blockDim = dim3(kClusterThreads);
     cfg.stream = st;
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2]{};
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;        // every cluster kernel starts with pdl_wait()
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, kernel, p, extra...) != cudaSuccess) { cudaGetLastError(); return AFAN_ERR_LAUNCH; }
     return launch_status();
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/afan_b200.h"
 
@@ -29,6 +30,37 @@ __host__ inline int sm_count() {
 __host__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __host__ inline int launch_status() {
+    return cudaPeekAtLastError() == cudaSuccess ? AFAN_OK : (cudaGetLastError(), AFAN_ERR_LAUNCH);
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// Kernels that begin with pdl_wait() may be launched with cudaLaunchAttributeProgrammaticStreamSerialization: their
+// CTAs are scheduled while the previous kernel of the stream drains, and block in pdl_wait() until that kernel's
+// memory is visible -- the ~2 us launch ramp of every small kernel overlaps its predecessor's tail.  Both
+// instructions are no-ops for a normal launch.  AFAN_PDL=0 in the environment disables the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__host__ inline bool pdl_enabled() {
+    static int cached = -1;            // benign race
+    if (cached < 0) {
+        const char* e = getenv("AFAN_PDL");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached == 1;
+}
+
+// <<<grid, block, smem, stream>>> with the PDL attribute
+template <typename K, typename... Args>
+__host__ inline int launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, kernel, args...) != cudaSuccess) { cudaGetLastError(); return AFAN_ERR_LAUNCH; }
     return cudaPeekAtLastError() == cudaSuccess ? AFAN_OK : (cudaGetLastError(), AFAN_ERR_LAUNCH);
 }
 

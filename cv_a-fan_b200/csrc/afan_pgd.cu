@@ -120,6 +120,8 @@ pgd_linf_step_kernel(const float* __restrict__ grad, const float* __restrict__ x
     const int chunks = gridDim.x, k = blockIdx.x, s = blockIdx.y;
     const long long lo = pv * k / chunks, hi = pv * (k + 1) / chunks;
     const long long base = static_cast<long long>(s) * pv;
+    pdl_wait();
+    pdl_launch_dependents();
     const V* g_v = STEP ? reinterpret_cast<const V*>(grad) + base : nullptr;
     const V* c_v = NEED_CLEAN ? reinterpret_cast<const V*>(x_clean) + base : nullptr;
     V* a_v = reinterpret_cast<V*>(x_adv) + base;
@@ -423,10 +425,9 @@ int launch_step(const float* grad, const float* x_clean, float* x_adv, float* de
                 float* partials, unsigned int* counters, long long n_samples, long long per_sample, int chunks,
                 float gamma, float eps, cudaStream_t st) {
     dim3 grid(chunks, static_cast<unsigned int>(n_samples));
-    pgd_linf_step_kernel<VEC, STEP, CLIP, DELTA, NORMS><<<grid, kThreads, 0, st>>>(
-        grad, x_clean, x_adv, delta_out, norms_out, partials, counters, per_sample / VEC,
-        static_cast<int>(n_samples), gamma, eps);
-    return launch_status();
+    return launch_pdl(pgd_linf_step_kernel<VEC, STEP, CLIP, DELTA, NORMS>, grid, dim3(kThreads), 0, st, grad, x_clean, x_adv,
+                      delta_out, norms_out, partials, counters, static_cast<long long>(per_sample / VEC),
+                      static_cast<int>(n_samples), gamma, eps);
 }
 
 template <int VEC>
