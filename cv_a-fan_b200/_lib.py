@@ -23,6 +23,7 @@ SIGNATURES = {
     "afan_pgd_init_philox_f32": (_int, [_vp, _vp, _i64, _f32, _u64, _u64, _vp, _vp]),
     "afan_pgd_norms_workspace_bytes": (_i64, [_i64]),
     "afan_pgd_linf_step_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _int, _vp]),
+    "afan_tensor_clamp_f32": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "afan_pgd_linf_step_bf16": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _int, _vp]),
     "afan_pgd_init_noise_bf16": (_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
     "afan_pgd_init_philox_bf16": (_int, [_vp, _vp, _i64, _f32, _u64, _u64, _vp, _vp]),

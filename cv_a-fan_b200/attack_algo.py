@@ -46,9 +46,17 @@ def linfball_proj(center, radius, t, in_place=True):
 
 
 def tensor_clamp(t, min, max, in_place=True):
-    """attack_algo.py:9-19 with tensor bounds.  Only the form the reference uses (min = c - r, max = c + r
-    via linfball_proj) runs on the fused kernel; arbitrary bounds are not part of the hot path."""
-    raise AfanError("tensor_clamp with free-form bounds is not on the A-FAN hot path; use linfball_proj")
+    """attack_algo.py:9-19 with tensor bounds: t < min -> min, then t > max -> max (NaN left alone), one launch."""
+    from . import _lib
+    res = t if in_place else t.clone()
+    if not res.is_contiguous():
+        raise AfanError("tensor_clamp needs a contiguous tensor")
+    lo, hi = _as_cuda_f32(min, "min"), _as_cuda_f32(max, "max")
+    if lo.shape != res.shape or hi.shape != res.shape:
+        raise AfanError("min / max must have the shape of t")
+    _lib.check(_lib.lib().afan_tensor_clamp_f32(_lib.f32(res.data, "t"), _lib.f32(lo), _lib.f32(hi), res.numel(),
+                                                _lib.stream()), "afan_tensor_clamp_f32")
+    return res
 
 
 def l2ball_proj(center, radius, t, in_place=True):

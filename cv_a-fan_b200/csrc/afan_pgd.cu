@@ -413,6 +413,23 @@ pgd_init_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     }
 }
 
+// tensor_clamp with free-form tensor bounds, Classification/attack_algo.py:9-19:
+//   idx = t < min; t[idx] = min[idx]; idx = t > max; t[idx] = max[idx]     (NaN compares false -> left alone)
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+tensor_clamp_kernel(float* t, const float* __restrict__ lo, const float* __restrict__ hi, long long nv) {
+    using V = typename Vec<VEC>::type;
+    const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+    auto one = [](float v, float l, float h) { v = (v < l) ? l : v; return (v > h) ? h : v; };
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < nv; i += stride) {
+        V v = reinterpret_cast<V*>(t)[i];
+        const V l = ld_stream(reinterpret_cast<const V*>(lo) + i), h = ld_stream(reinterpret_cast<const V*>(hi) + i);
+        if constexpr (VEC == 4) { v.x = one(v.x, l.x, h.x); v.y = one(v.y, l.y, h.y); v.z = one(v.z, l.z, h.z); v.w = one(v.w, l.w, h.w); }
+        else { v = one(v, l, h); }
+        reinterpret_cast<V*>(t)[i] = v;
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------
 inline int flat_grid(long long n_vec, int per_cta) {
     const long long want = (n_vec + per_cta - 1) / per_cta;
@@ -687,5 +704,17 @@ AFAN_EXPORT int afan_pgd_init_philox_bf16(const void* x, void* x_adv, int64_t n_
     pgd_init_bf16_kernel<true><<<flat_grid((n_elem + 3) / 4, kThreads * 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), nullptr, static_cast<__nv_bfloat16*>(x_adv), n_elem, eps, seed, offset,
         reinterpret_cast<const unsigned long long*>(offset_device));
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_tensor_clamp_f32(float* t, const float* min, const float* max, int64_t n_elem, afan_stream_t stream) {
+    if (n_elem < 0) return AFAN_ERR_SIZE;
+    if (n_elem == 0) return AFAN_OK;
+    if (!t || !min || !max) return AFAN_ERR_NULL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_elem % 4 == 0 && aligned16(t) && aligned16(min) && aligned16(max))
+        tensor_clamp_kernel<4><<<flat_grid(n_elem / 4, kThreads * 2), kThreads, 0, st>>>(t, min, max, n_elem / 4);
+    else
+        tensor_clamp_kernel<1><<<flat_grid(n_elem, kThreads * 2), kThreads, 0, st>>>(t, min, max, n_elem);
     return launch_status();
 }

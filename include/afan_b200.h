@@ -72,6 +72,10 @@ int afan_pgd_linf_step_f32(const float* grad, const float* x_clean, float* x_adv
                            int64_t n_samples, int64_t per_sample, float gamma, float eps, int clip,
                            afan_stream_t stream);
 
+/* tensor_clamp with free-form tensor bounds (Classification/attack_algo.py:9-19), in place on t:
+ * t < min -> min; then t > max -> max; NaN in t is left alone.  (linfball_proj is the grad == NULL form above.) */
+int afan_tensor_clamp_f32(float* t, const float* min, const float* max, int64_t n_elem, afan_stream_t stream);
+
 /* bf16-storage twins (BASELINE config 3): tensors are bf16 (void* = __nv_bfloat16*), arithmetic is the same fp32
  * sequence on the widened values, stores round to nearest even; delta / norms are formed from the ROUNDED x_adv.
  * `u` stays fp32.  No reference exists for this dtype: the contract is bit-equality with oracle/afan_oracle.c's

@@ -113,6 +113,12 @@ def test_helpers_goldens():
     out = PKG.attack_algo.linfball_proj(torch.from_numpy(z["linf_center"]).to(dev()), float(z["linf_radius"]), t)
     assert out is t
     assert_bitwise(t, z["linf_out"], "linfball_proj (incl. -0.0 and NaN)")
+    # tensor_clamp with explicit bounds == what linfball_proj builds (attack_algo.py:35-36)
+    c, t2 = torch.from_numpy(z["linf_center"]).to(dev()), torch.from_numpy(z["linf_t"]).to(dev())
+    r = float(z["linf_radius"])
+    out2 = PKG.attack_algo.tensor_clamp(t2, min=c - r, max=c + r, in_place=False)
+    assert out2 is not t2
+    assert_bitwise(out2, z["linf_out"], "tensor_clamp")
     t = torch.from_numpy(z["l2_t"]).to(dev())
     PKG.attack_algo.l2ball_proj(torch.from_numpy(z["l2_center"]).to(dev()), float(z["l2_radius"]), t)
     ref = z["l2_out"]
