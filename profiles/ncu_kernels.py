@@ -13,6 +13,7 @@ dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(3)
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 
 
 def cold(fn):
@@ -27,7 +28,7 @@ if which in ("all", "pgd"):
         gr = 1e-3 * torch.randn(shape, device=dev, generator=g)
         xa, d = x.clone(), torch.empty_like(x)
         nrm, ws = torch.zeros(2, shape[0], device=dev), ops.norms_workspace(shape[0], dev)
-        for _ in range(2):
+        for _ in range(REPS):
             cold(lambda: ops.pgd_linf_step_(gr, x, xa, 0.5 / 255, 2 / 255, True))
             cold(lambda: ops.pgd_linf_step_(gr, x, xa, 0.5 / 255, 2 / 255, True, delta_out=d, norms_out=nrm, workspace=ws))
             cold(lambda: ops.pgd_init(x, 2 / 255, seed=1, out=xa))
@@ -38,7 +39,7 @@ if which in ("all", "bn"):
         w, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
         rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
         ws = ops.bn_workspace(G, C, dev)
-        for _ in range(2):
+        for _ in range(REPS):
             out = {}
             cold(lambda: out.update(r=ops.bn_fwd(x, None, w, b, rm, rv, ws, groups=G, relu=True)))
             y, sm, si = out["r"]
@@ -47,6 +48,20 @@ if which in ("all", "mix"):
     for shape in ((4, 2048, 33, 33), (8, 1024, 38, 63), (4, 256, 128, 128)):
         cl = torch.relu(torch.randn(shape, device=dev, generator=g))
         ad = cl + 0.01 * torch.randn(shape, device=dev, generator=g)
-        for _ in range(2):
+        for _ in range(REPS):
             cold(lambda: ops.mix_feature(cl, ad))
+if which in ("all", "aux"):
+    pts = pkg.segmentation.sat_sample_points
+    cl = torch.relu(torch.randn(4, 256, 128, 128, device=dev, generator=g))
+    ad = cl + 0.01 * torch.randn(cl.shape, device=dev, generator=g)
+    for _ in range(REPS):
+        cold(lambda: pts(cl, ad, 3, (True, True)))
+    boxes = torch.rand(12000, 4, device=dev, generator=g) * 300
+    boxes[:, 2:] += boxes[:, :2] + 4
+    scores = torch.rand(12000, device=dev, generator=g)
+    feat = torch.randn(2, 1024, 38, 63, device=dev, generator=g)
+    rois = torch.cat([torch.randint(0, 2, (256, 1), device=dev, generator=g).float(), boxes[:256] * 2], 1)
+    for _ in range(REPS):
+        cold(lambda: ops.nms_flags(boxes, scores, 0.7))
+        cold(lambda: pkg.detection.roi_align(feat, rois, (14, 14), 1 / 16, 0))
 print("done")
