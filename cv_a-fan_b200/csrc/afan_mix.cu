@@ -285,21 +285,34 @@ __global__ void __launch_bounds__(kMixThreads) sat_mix_kernel(const SatParams p)
     }
     if (!active) return;
 
-    // ---- sweep 2 (cache-hot): write every point ----
-    for (unsigned int k0 = warp; k0 < c; k0 += kMixWarps * kMixUnroll) {
+    // ---- sweep 2 (cache-hot): write every point; per-pixel coefficients hoisted into registers ----
+    float m_c[VEC], ratio[kSatMax][VEC], m_p[kSatMax][VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const unsigned int px = lane * VEC + v;
+        m_c[v] = s_stat[0][0][px];
+#pragma unroll
+        for (int j = 0; j < kSatMax; ++j) {
+            ratio[j][v] = (p.mix_mask & (1u << j)) ? __fdiv_rn(s_stat[1 + j][1][px], s_stat[0][1][px]) : 0.f;
+            m_p[j][v] = (p.mix_mask & (1u << j)) ? s_stat[1 + j][0][px] : 0.f;
+        }
+    }
+    const size_t cstride = static_cast<size_t>(kMixWarps) * hw;
+    const float* pc = p.clean + base + static_cast<size_t>(warp) * hw;
+    const float* pa = p.adv + base + static_cast<size_t>(warp) * hw;
+    size_t ooff = base + static_cast<size_t>(warp) * hw;
+    const unsigned int my_channels = warp < c ? (c - warp + kMixWarps - 1) / kMixWarps : 0u;
+    for (unsigned int done = 0; done < my_channels; done += kMixUnroll) {
         V xc[kMixUnroll] = {}, xa[kMixUnroll] = {};
 #pragma unroll
-        for (int u = 0; u < kMixUnroll; ++u) {
-            const unsigned int k = k0 + u * kMixWarps;
-            if (k < c) {
-                xc[u] = *reinterpret_cast<const V*>(p.clean + base + static_cast<size_t>(k) * hw);
-                xa[u] = *reinterpret_cast<const V*>(p.adv + base + static_cast<size_t>(k) * hw);
+        for (int u = 0; u < kMixUnroll; ++u)
+            if (done + u < my_channels) {
+                xc[u] = *reinterpret_cast<const V*>(pc + u * cstride);
+                xa[u] = *reinterpret_cast<const V*>(pa + u * cstride);
             }
-        }
 #pragma unroll
-        for (int u = 0; u < kMixUnroll; ++u) {
-            const unsigned int k = k0 + u * kMixWarps;
-            if (k < c) {
+        for (int u = 0; u < kMixUnroll; ++u)
+            if (done + u < my_channels) {
                 float cv[VEC], av[VEC];
                 if constexpr (VEC == 4) {
                     cv[0] = xc[u].x; cv[1] = xc[u].y; cv[2] = xc[u].z; cv[3] = xc[u].w;
@@ -307,25 +320,23 @@ __global__ void __launch_bounds__(kMixThreads) sat_mix_kernel(const SatParams p)
                 } else {
                     cv[0] = xc[u]; av[0] = xa[u];
                 }
-                for (unsigned int j = 0; j < p.m; ++j) {
-                    float o[VEC];
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const float pt = torch_lerp(cv[v], av[v], p.w[j]);
-                        if (p.mix_mask & (1u << j)) {
-                            const unsigned int px = lane * VEC + v;
-                            o[v] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(cv[v], s_stat[0][0][px]), s_stat[0][1][px]),
-                                                       s_stat[1 + j][1][px]), s_stat[1 + j][0][px]);
-                        } else {
-                            o[v] = pt;
-                        }
+                for (int j = 0; j < kSatMax; ++j) {
+                    if (j < static_cast<int>(p.m)) {
+                        float o[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v)
+                            o[v] = (p.mix_mask & (1u << j)) ? fmaf(cv[v] - m_c[v], ratio[j][v], m_p[j][v])
+                                                            : torch_lerp(cv[v], av[v], p.w[j]);
+                        V ov;
+                        if constexpr (VEC == 4) { ov.x = o[0]; ov.y = o[1]; ov.z = o[2]; ov.w = o[3]; } else { ov = o[0]; }
+                        st_stream(reinterpret_cast<V*>(p.out[j] + ooff + u * cstride), ov);
                     }
-                    V ov;
-                    if constexpr (VEC == 4) { ov.x = o[0]; ov.y = o[1]; ov.z = o[2]; ov.w = o[3]; } else { ov = o[0]; }
-                    st_stream(reinterpret_cast<V*>(p.out[j] + base + static_cast<size_t>(k) * hw), ov);
                 }
             }
-        }
+        pc += kMixUnroll * cstride;
+        pa += kMixUnroll * cstride;
+        ooff += kMixUnroll * cstride;
     }
 }
 

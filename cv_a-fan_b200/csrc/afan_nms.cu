@@ -5,8 +5,8 @@
 // per forward.  Semantics kept: boxes sorted by score (descending), legacy "+1" areas (devIoU :13-21), a box is
 // suppressed when IoU > threshold with an earlier kept box.  Here the sweep stays on the GPU:
 //   nms_mask_kernel   only the upper-triangular tiles (row block <= col block); one 64-bit word per (box, col block)
-//   nms_sweep_kernel  ONE CTA walks the 64-box blocks in order: a single lane resolves the block's internal
-//                     dependencies on the diagonal words (<= 64 register steps), then all threads OR the mask rows
+//   nms_sweep_kernel  ONE CTA walks the 64-box blocks in order: the block's 64 diagonal words are staged in shared
+//                     memory, a single lane resolves the block's internal dependencies on them (<= 64 steps), then all threads OR the mask rows
 //                     of the newly kept boxes into the running `removed` bit vector in shared memory.
 // Outputs live on the device: keep flags indexed by ORIGINAL box index + the count; no host synchronisation.
 #include "afan_common.cuh"
@@ -50,19 +50,22 @@ __global__ void __launch_bounds__(kNmsSweepThreads)
 nms_sweep_kernel(const unsigned long long* __restrict__ mask, const long long* __restrict__ order,
                  unsigned char* __restrict__ keep_flags, int* __restrict__ count_out, int n, int col_blocks) {
     extern __shared__ unsigned long long removed[];                  // col_blocks words
-    __shared__ unsigned long long s_keep;
+    __shared__ unsigned long long s_keep, s_diag[kNmsTile];
     for (int j = threadIdx.x; j < col_blocks; j += kNmsSweepThreads) removed[j] = 0ULL;
     for (int i = threadIdx.x; i < n; i += kNmsSweepThreads) keep_flags[i] = 0;
     __syncthreads();
     int kept = 0;
     for (int b = 0; b < col_blocks; ++b) {
         const int size = min(n - b * kNmsTile, kNmsTile);
-        if (threadIdx.x == 0) {                                      // resolve the block's internal chain on the diagonal words
+        if (threadIdx.x < size)                                      // the block's 64 diagonal words, fetched in parallel
+            s_diag[threadIdx.x] = mask[static_cast<size_t>(b * kNmsTile + threadIdx.x) * col_blocks + b];
+        __syncthreads();
+        if (threadIdx.x == 0) {                                      // resolve the block's internal chain out of shared memory
             unsigned long long rem = removed[b], keep = 0ULL;
             for (int i = 0; i < size; ++i)
                 if (!((rem >> i) & 1ULL)) {
                     keep |= 1ULL << i;
-                    rem |= mask[static_cast<size_t>(b * kNmsTile + i) * col_blocks + b];
+                    rem |= s_diag[i];
                 }
             s_keep = keep;
         }
