@@ -444,6 +444,13 @@ def main():
 
     if rank == 0 and not args.skip_rooflines:
         ks, peak_src = kernel_rooflines(pkg, dev)
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tmap = json.load(f)
+        except Exception:
+            tmap = {}
+        for k in ks:
+            k["traffic"] = tmap.get(k["kernel"])
         in_step = [k for k in ks if k["launches_per_iter"] > 0]
         dom = max(in_step, key=lambda k: k["us"] * k["launches_per_iter"])
         try:                                  # DRAM bytes per launch from the committed ncu --set full capture
