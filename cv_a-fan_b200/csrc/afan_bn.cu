@@ -343,8 +343,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParam
 // =====================================================================================================
 constexpr int kClusterThreads = 512;
 constexpr int kMaxGroups = 16;                    // learnable-eta A-FAN batches 9 adversarial groups + clean
-constexpr int kMaxCluster = 16;                    // 8 = portable cluster size on sm_100a, 16 = non-portable (opt-in)
-constexpr int kPortableCluster = 8;
+constexpr int kMaxCluster = 8;                     // portable cluster size on sm_100a
 
 struct ClusterParams {
     const float* a;          // fwd: x            bwd: dy
@@ -995,11 +994,11 @@ __host__ inline RegPlan pick_reg_plan(int64_t groups, int64_t n, int64_t c, int6
     if (!vec || groups > 2) return r;
     const int64_t J = n * (hw / 4);
     int cs = 1;
-    while (cs < kPortableCluster && c * cs * 2 <= sm_count()) cs *= 2;    // whole chip in ONE wave of 1 CTA / SM
+    while (cs < kMaxCluster && c * cs * 2 <= sm_count()) cs *= 2;    // whole chip in ONE wave of 1 CTA / SM
     for (int nv = 1; nv <= 8; nv *= 2) {
         if (static_cast<int64_t>(cs) * kClusterThreads * nv >= J) {
             if (groups * nv > max_gnv) return r;
-            if (cs == kPortableCluster && groups * nv > max_gnv / 2) return r;   // 8-CTA clusters need 2 CTAs/SM (<= 64 regs) to pack
+            if (cs == kMaxCluster && groups * nv > max_gnv / 2) return r;   // 8-CTA clusters need 2 CTAs/SM (<= 64 regs) to pack
             // do not spread a tiny domain over more CTAs than it can feed with >= 1 vector per thread
             while (cs > 1 && static_cast<int64_t>(cs / 2) * kClusterThreads * nv >= J) cs /= 2;
             r.cs = cs; r.nv = nv;
@@ -1011,41 +1010,25 @@ __host__ inline RegPlan pick_reg_plan(int64_t groups, int64_t n, int64_t c, int6
 
 // cluster size: enough CTAs to cover the chip (C * CS >= ~148), power of two, <= 8, and every CTA keeps
 // >= 512 vectors per group; 0 -> shape not suited (per-channel domain too large to stay L2-resident)
-struct ClusterPlan { int cs; int smem_pad; };       // cs == 0 -> not applicable; smem_pad > 0 forces one CTA per SM
-__host__ inline ClusterPlan pick_cluster(int64_t groups, int64_t n, int64_t c, int64_t hw, bool vec) {
+__host__ inline int pick_cluster(int64_t groups, int64_t n, int64_t c, int64_t hw, bool vec) {
     const int64_t v = vec ? 4 : 1;
     const int64_t J = n * (hw / v);                                   // vectors per (group, channel)
-    const int64_t domain_bytes = groups * n * hw * 4;                 // bytes of one channel (all groups) per swept tensor
+    const int64_t domain_bytes = groups * n * hw * 4;
     int cs = 1;
-    while (cs < kPortableCluster && c * cs < sm_count() && J / (cs * 2) >= 512) cs *= 2;
-    // sweep 2 must find the slice in L2: the concurrently resident footprint has to stay well below 126 MB
+    while (cs < kMaxCluster && c * cs < sm_count() && J / (cs * 2) >= 512) cs *= 2;
+    // concurrently resident footprint must fit L2 for sweep 2 to hit: (CTAs resident) * slice <= ~48 MB
     const int64_t resident = static_cast<int64_t>(sm_count()) * 4;   // 4 x 512 threads per SM
+    const int64_t slice = domain_bytes / cs;
     const int64_t ctas = c * cs < resident ? c * cs : resident;
-    if (ctas * (domain_bytes / cs) <= (int64_t(48) << 20)) return {cs, 0};
-    // large per-channel domains: bound the number of channels in flight instead -- big clusters, ONE CTA per SM
-    // (dynamic shared memory padding), so only sm_count / cs channels stream at a time and each is re-read from L2
-    for (int big : {kPortableCluster, kMaxCluster}) {
-        const int64_t in_flight = sm_count() / big + 1;
-        if (in_flight * domain_bytes <= (int64_t(64) << 20) && J / big >= 2048) return {big, 120 * 1024};
-    }
-    return {0, 0};
+    if (ctas * slice > (int64_t(48) << 20)) return 0;
+    return cs;
 }
+
 template <typename K, typename... Extra>
-int launch_cluster_smem(K kernel, const ClusterParams& p, int cs, int smem_pad, cudaStream_t st, const Extra&... extra) {
-    if (smem_pad > 48 * 1024 &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pad) != cudaSuccess) {
-        cudaGetLastError();
-        return AFAN_ERR_LAUNCH;
-    }
-    if (cs > kPortableCluster &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-        cudaGetLastError();
-        return AFAN_ERR_LAUNCH;
-    }
+int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st, const Extra&... extra) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.c * cs);
     cfg.blockDim = dim3(kClusterThreads);
-    cfg.dynamicSmemBytes = static_cast<size_t>(smem_pad);
     cfg.stream = st;
     cudaLaunchAttribute attr[2]{};
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1056,11 +1039,6 @@ int launch_cluster_smem(K kernel, const ClusterParams& p, int cs, int smem_pad, 
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, kernel, p, extra...) != cudaSuccess) { cudaGetLastError(); return AFAN_ERR_LAUNCH; }
     return launch_status();
-}
-
-template <typename K, typename... Extra>
-int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st, const Extra&... extra) {
-    return launch_cluster_smem(kernel, p, cs, 0, st, extra...);
 }
 
 // ---- host helpers -------------------------------------------------------------------------------
@@ -1203,8 +1181,7 @@ AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const flo
     if (!s.ok) return AFAN_OK;
     if (!x || !y || !save_mean || !save_invstd) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;   // uniform contract on both paths
-    const ClusterPlan cp = pick_cluster(groups, n, c, hw, s.vec);
-    const int cs = cp.cs;
+    const int cs = pick_cluster(groups, n, c, hw, s.vec);
     const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 16);
     if (cs > 0 || rp.nv > 0) {                                       // single-launch cluster paths
         ClusterParams p{};
@@ -1225,7 +1202,7 @@ AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const flo
 #undef AFAN_RFN
 #undef AFAN_RF4
         }
-#define AFAN_CF(V, R, S) return launch_cluster_smem(bn_fwd_cluster_kernel<V, R, S>, p, cs, cp.smem_pad, st)
+#define AFAN_CF(V, R, S) return launch_cluster(bn_fwd_cluster_kernel<V, R, S>, p, cs, st)
         if (cs <= 0) goto two_launch_fwd;
         if (s.vec) { if (r) { if (rs) AFAN_CF(4, true, true); else AFAN_CF(4, true, false); }
                      else   { if (rs) AFAN_CF(4, false, true); else AFAN_CF(4, false, false); } }
@@ -1335,8 +1312,7 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
     if (!s.ok) return AFAN_OK;
     if (!dy || !x || !dx || !save_mean || !save_invstd || (relu && !y)) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
-    const ClusterPlan cp = pick_cluster(groups * 3, n, c, hw, s.vec);        // three tensors are swept twice
-    const int cs = cp.cs;
+    const int cs = pick_cluster(groups * 3, n, c, hw, s.vec);        // three tensors are swept twice
     const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 8);    // dy and x are both held: G*NV <= 8
     if (cs > 0 || rp.nv > 0) {
         ClusterParams p{};
@@ -1356,7 +1332,7 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
             else             { switch (rp.nv) { case 1: AFAN_RB4(2, 1) case 2: AFAN_RB4(2, 2) default: AFAN_RB4(2, 4) } }
 #undef AFAN_RB4
         }
-#define AFAN_CB(V, R, S) return launch_cluster_smem(bn_bwd_cluster_kernel<V, R, S>, p, cs, cp.smem_pad, st)
+#define AFAN_CB(V, R, S) return launch_cluster(bn_bwd_cluster_kernel<V, R, S>, p, cs, st)
         if (cs <= 0) goto two_launch_bwd;
         if (s.vec) { if (r) { if (dr) AFAN_CB(4, true, true); else AFAN_CB(4, true, false); }
                      else   { if (dr) AFAN_CB(4, false, true); else AFAN_CB(4, false, false); } }
