@@ -200,7 +200,8 @@ def kernel_rooflines(pkg, dev, reps=10):
             e2.synchronize()
             if i >= 3:
                 iso.append(s2.elapsed_time(e2) * 1e-3)
-        res.append({"kernel": name, "bytes": bytes_per_launch, "us": t * 1e6, "us_isolated": 1e6 * sum(iso) / len(iso),
+        res.append({"kernel": name, "family": name.split(" [")[0].split("+")[0].split(" clip")[0].split(" noclip")[0].strip(),
+                    "bytes": bytes_per_launch, "us": t * 1e6, "us_isolated": 1e6 * sum(iso) / len(iso),
                     "achieved": bytes_per_launch / t / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": bytes_per_launch / t / 1e9 / peak, "rotating_sets": R,
                     "launches_per_iter": launches_per_iter, "note": note})
@@ -451,18 +452,34 @@ def main():
             tmap = {}
         for k in ks:
             k["traffic"] = tmap.get(k["kernel"])
-        in_step = [k for k in ks if k["launches_per_iter"] > 0]
-        dom = max(in_step, key=lambda k: k["us"] * k["launches_per_iter"])
-        try:                                  # DRAM bytes per launch from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get(dom["kernel"])
-        except Exception:
-            traffic = None
-        line["roofline"] = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
-                            "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "algorithmic_bytes": dom["bytes"],
-                            "peak_source": peak_src,
-                            "timing": "CUDA events around a graph of back-to-back launches over rotating tensor sets (4x L2), per-launch average",
-                            "share_of_step": dom["us"] * dom["launches_per_iter"] / (1e3 * sec / args.steps) / 1e3}
+        # the dominant hand-written kernel of the step = the kernel FAMILY (all its in-step shapes) with the largest
+        # share of the step; achieved = its algorithmic bytes per step / its device time per step
+        step_us = 1e3 * sec / args.steps * 1e3
+        fam = {}
+        for k in ks:
+            if k["launches_per_iter"] > 0:
+                f = fam.setdefault(k["family"], {"bytes": 0.0, "us": 0.0, "launches": 0, "traffic": 0.0, "traffic_ok": True, "shapes": []})
+                f["bytes"] += k["bytes"] * k["launches_per_iter"]
+                f["us"] += k["us"] * k["launches_per_iter"]
+                f["launches"] += k["launches_per_iter"]
+                f["shapes"].append(k["kernel"])
+                if k["traffic"] is None:
+                    f["traffic_ok"] = False
+                else:
+                    f["traffic"] += k["traffic"] * k["launches_per_iter"]
+        dom_name, dom = max(fam.items(), key=lambda kv: kv[1]["us"])
+        achieved = dom["bytes"] / (dom["us"] * 1e-6) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": ks[0]["peak"], "unit": "GB/s",
+                            "frac": achieved / ks[0]["peak"], "traffic": dom["traffic"] / dom["launches"] if dom["traffic_ok"] else None,
+                            "algorithmic_bytes": dom["bytes"] / dom["launches"], "launches_per_step": dom["launches"],
+                            "avg_us_per_launch": dom["us"] / dom["launches"], "share_of_step": dom["us"] / step_us,
+                            "shapes": dom["shapes"], "peak_source": peak_src,
+                            "timing": "per shape: CUDA events around a graph of back-to-back launches over rotating tensor sets "
+                                      "(4x L2, every launch L2-cold), weighted by the launches of that shape in one step; "
+                                      "traffic / algorithmic_bytes are per-launch averages",
+                            "families": {n: {"share_of_step": f["us"] / step_us, "launches_per_step": f["launches"],
+                                             "achieved": f["bytes"] / (f["us"] * 1e-6) / 1e9,
+                                             "frac": f["bytes"] / (f["us"] * 1e-6) / 1e9 / ks[0]["peak"]} for n, f in fam.items()}}
         line["kernels"] = ks
     if world > 1:
         torch.distributed.barrier()
