@@ -117,7 +117,7 @@ def cpu_reference(steps, warmup, batch=None):
             "ms_per_step": 1e3 * dt / steps}
 
 
-def config_dict(n_gpus, conv_math="fp32"):
+def config_dict(n_gpus, conv_math="fp32", conv="afan"):
     w = WORKLOAD
     return {"workload": "BASELINE configs[1]: ResNet-56 CIFAR-100-shaped synthetic 32x32, A-FAN PGD-5 with dual BN",
             "global_batch": w["batch_per_gpu"] * n_gpus, "batch_per_gpu": w["batch_per_gpu"],
@@ -125,6 +125,7 @@ def config_dict(n_gpus, conv_math="fp32"):
             "pgd_steps": w["steps"], "gamma_255": w["gamma"], "eps_255": w["eps"], "randinit": w["randinit"],
             "clip": w["clip"], "parallelism": f"dp{n_gpus} (one process per GPU, NCCL)",
             "conv_math": "fp32 (TF32 off)" if conv_math == "fp32" else "tf32 tensor cores (cuDNN), fp32 accumulate",
+            "conv3x3": "hand-written sm_100a direct convolution (strict fp32 FFMA)" if conv == "afan" else "cuDNN",
             "l2": "no flush between steps: per-step working set (saved activations ~0.9 GB) exceeds the 126 MB L2; "
                   "kernel rooflines are measured separately with an L2 flush between launches"}
 
@@ -333,6 +334,8 @@ def main():
                     help="multi-GPU dual-BN statistics: fused NVLink peer-memory exchange inside the kernel, or NCCL all-reduce")
     ap.add_argument("--conv-math", default="fp32", choices=["fp32", "tf32"],
                     help="cuDNN/cuBLAS math of the (library) convolutions / fc: strict fp32 (headline) or TF32 tensor cores")
+    ap.add_argument("--conv", default="afan", choices=["afan", "cudnn"],
+                    help="3x3 tail convolutions: hand-written sm_100a FFMA kernels (default) or the cuDNN library path")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-rooflines", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
@@ -360,6 +363,7 @@ def main():
     torch.backends.cudnn.benchmark = True
 
     pkg = importlib.import_module("cv_a-fan_b200")
+    pkg.conv.MODE = args.conv
     w = WORKLOAD
     torch.manual_seed(3)                                     # identical weights on every rank
     model = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)
@@ -435,7 +439,7 @@ def main():
     line = {"metric": "A-FAN train img/s", "value": global_batch * args.steps / sec, "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(world, args.conv_math), "clocks": clocks,
+            "config": config_dict(world, args.conv_math, args.conv), "clocks": clocks,
             "e2e": {"value": global_batch * args.steps / sec_e2e, "unit": "img/s",
                     "h2d_bytes_per_step": (host_x[0].numel() * 4 + host_y[0].numel() * 8) * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * sec_e2e / args.steps},

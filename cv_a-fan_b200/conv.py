@@ -1,0 +1,107 @@
+"""3x3 convolution module of the splittable ResNet, backed by the hand-written sm_100a kernels.
+
+`Conv3x3` is an `nn.Conv2d` (same parameter name / shape / init, so reference checkpoints load,
+Classification/resnet_s.py:53,55) whose forward + backward run `afan_conv3x3_f32` (forward and, with the other weight
+packing, the input gradient) and `afan_conv3x3_wgrad_f32` for the shapes those kernels cover -- stride 1, C_in == C_out
+in {16, 32, 64}, square 8/16/32 maps, i.e. every BasicBlock convolution of the CIFAR ResNets except the two
+stride-2 stage transitions and the stem.  Anything else is the library convolution (cuDNN), which the north star leaves
+outside the hand-written scope.
+
+Weight packing.  The kernels read W as [reduction channel][tap][output channel].  A module repacks its own weight when
+`weight._version` moved (optimizer.step(), load_state_dict, ...).  A trainer that updates the weights behind autograd's
+back (the arena SGD kernel) calls `pack_all(model)` once per iteration instead: ONE launch for all layers.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+# "afan" | "cudnn": module-level switch (env AFAN_CONV) used by the benchmarks to time the library path
+MODE = os.environ.get("AFAN_CONV", "afan")
+
+
+class _Conv3x3Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, mod):
+        x = x.contiguous()
+        wf, wd = mod.packed()
+        ctx.save_for_backward(x)
+        ctx.mod, ctx.wd = mod, wd
+        return ops.conv3x3(x, wf)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.conv3x3(dy, ctx.wd) if ctx.needs_input_grad[0] else None
+        dw = ops.conv3x3_wgrad(x, dy, ctx.mod.wgrad_workspace()) if ctx.needs_input_grad[1] else None
+        return dx, dw, None
+
+
+class Conv3x3(nn.Conv2d):
+    def __init__(self, in_planes: int, planes: int, stride: int = 1):
+        super().__init__(in_planes, planes, 3, stride, 1, bias=False)
+        self._packed = None            # float32 [2, C*9*C]: forward packing, dgrad packing
+        self._packed_key = None        # (weight data_ptr, weight version) the packing was made from
+        self._managed = False          # True while a trainer repacks all layers itself (pack_all)
+        self._ws = None
+
+    def _buffers_for(self, device):
+        if self._packed is None or self._packed.device != device:
+            c = self.out_channels
+            self._packed = torch.empty((2, c * 9 * c), dtype=torch.float32, device=device)
+            self._packed_key = None
+        return self._packed
+
+    def desc_row(self):
+        p = self._buffers_for(self.weight.device)
+        return [self.weight.data_ptr(), p[0].data_ptr(), p[1].data_ptr(), self.out_channels]
+
+    def packed(self):
+        p = self._buffers_for(self.weight.device)
+        if not self._managed:
+            key = (self.weight.data_ptr(), self.weight._version)
+            if key != self._packed_key:
+                descs = torch.tensor([self.desc_row()], dtype=torch.int64, device=self.weight.device)
+                ops.conv3x3_pack(descs, self.out_channels)
+                self._packed_key = key
+        return p[0], p[1]
+
+    def wgrad_workspace(self):
+        if self._ws is None or self._ws.device != self.weight.device:
+            self._ws = ops.conv3x3_wgrad_workspace(self.out_channels, self.weight.device)
+        return self._ws
+
+    def forward(self, x):
+        if MODE == "afan" and self.stride == (1, 1) and self.in_channels == self.out_channels \
+                and ops.conv3x3_supported(x, self.weight):
+            return _Conv3x3Fn.apply(x, self.weight, self)
+        return super().forward(x)
+
+
+class PackPlan:
+    """One-launch repack of every eligible Conv3x3 of a model (for trainers whose optimiser writes the weights with a
+    raw kernel).  The descriptor table is rebuilt when a weight moved (e.g. into the flat parameter arena)."""
+
+    def __init__(self, model: nn.Module):
+        self.mods = [m for m in model.modules() if isinstance(m, Conv3x3) and m.stride == (1, 1)
+                     and m.in_channels == m.out_channels and m.out_channels in ops.CONV3X3_CHANNELS]
+        self._ptrs, self._descs = None, None
+        for m in self.mods:
+            m._managed = True
+
+    def pack(self):
+        if not self.mods or MODE != "afan":
+            return
+        ptrs = tuple(m.weight.data_ptr() for m in self.mods)
+        if ptrs != self._ptrs:
+            dev = self.mods[0].weight.device
+            self._descs = torch.tensor([m.desc_row() for m in self.mods], dtype=torch.int64, device=dev)
+            self._ptrs = ptrs
+        ops.conv3x3_pack(self._descs, max(m.out_channels for m in self.mods))
+
+    def release(self):
+        for m in self.mods:
+            m._managed, m._packed_key = False, None

@@ -1,0 +1,445 @@
+// afan_conv.cu -- strict-fp32 3x3 / stride 1 / pad 1 convolutions of the tail sub-network that the PGD ascent
+// re-executes `steps` times per batch (Classification/resnet_s.py:53,55 `conv1` / `conv2` of BasicBlock, driven by
+// attack_algo.py:49-52 `model(x_adv, start_point=k)` + `autograd.grad`).  cuDNN serves these tiny-channel shapes
+// (16/32/64 channels on 32x32 / 16x16 / 8x8 maps) with its generic `implicit_convolve_sgemm` / `dgrad_engine` pair at
+// ~12-27 TFLOP/s plus a zero-fill launch per dgrad; a direct convolution that keeps a whole image (or half of one)
+// in shared memory runs the same FFMA work at the pipe rate.
+//
+//   forward  y[n,co,h,w] = sum_{ci,kh,kw} x[n,ci,h+kh-1,w+kw-1] * W[co,ci,kh,kw]
+//   dgrad    dx[n,ci,h,w] = sum_{co,kh,kw} dy[n,co,h-kh+1,w-kw+1] * W[co,ci,kh,kw]  == forward with the packed
+//            weights W'[k][t'][j] = W[k][j][8-t']  (same kernel, other packing)
+//   wgrad    dW[co,ci,kh,kw] = sum_{n,h,w} dy[n,co,h,w] * x[n,ci,h+kh-1,w+kw-1]
+//
+// Data layout: NCHW fp32 (the reference's).  Weights are repacked once per optimiser step (one launch for all layers)
+// into [reduction channel][tap][output channel] so that a K-chunk of weights is one contiguous cp.async stream and a
+// thread's TQ output channels are one 128-bit shared-memory load.
+//
+// Kernel shape (forward / dgrad): CTA = R rows x full width of ONE image x all output channels.  The reduction
+// channels arrive in chunks of CK through a 2-stage cp.async pipeline (input rows incl. halo + that chunk's weights).
+// Thread tile = 2 rows x 4 columns x TQ output channels: per reduction channel 4 x (LDS.32 + LDS.128 + LDS.32) input
+// loads and 9 LDS.128 weight loads feed 72*TQ FFMAs.  Lanes 0-7 of a warp walk 8 neighbouring pixel blocks, lanes / 8
+// walk 4 channel groups: input loads hit 8 distinct conflict-free 16-byte words (row pitch chosen per width), weight
+// loads 4.  Accumulation order is fixed (ci ascending, taps row-major): results are deterministic.
+#include "afan_common.cuh"
+
+namespace afan {
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int C_, int HW_, int R_, int TQ_, int CK_>
+struct ConvCfg {
+    static constexpr int C = C_, H = HW_, W = HW_, R = R_, TQ = TQ_, CK = CK_;
+    // shared-memory row pitch: interior starts at column 4 (16-byte aligned), halo columns 3 and W+4.  The pitch makes
+    // the 8 pixel blocks of a quarter-warp (W/4 per row, rows 2 apart) land on distinct banks.
+    static constexpr int S = (W == 32) ? 40 : (W == 16 ? 24 : 20);
+    static constexpr int PBW = W / 4, PBH = R / 2, NPB = PBW * PBH, NCG = C / TQ;
+    static constexpr int THREADS = NPB * NCG;
+    static constexpr int ROWS = R + 2;
+    static constexpr int IN_ELEMS = CK * ROWS * S;
+    static constexpr int W_ELEMS = CK * 9 * C;
+    static constexpr int STAGE = IN_ELEMS + W_ELEMS;
+    static constexpr int SMEM_BYTES = 2 * STAGE * 4;
+    static constexpr int NCHUNK = C / CK;
+    static constexpr int TPI = H / R;      // CTAs (row tiles) per image
+    static_assert(NPB % 8 == 0 && NCG % 4 == 0, "warp = 8 pixel blocks x 4 channel groups");
+    static_assert(THREADS <= 1024 && THREADS % 32 == 0, "CTA size");
+    static_assert(C % CK == 0 && H % R == 0 && R % 2 == 0 && (TQ == 2 || TQ == 4 || TQ == 8), "tiling");
+};
+
+template <class K>
+__global__ void __launch_bounds__(K::THREADS)
+conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y) {
+    constexpr int C = K::C, H = K::H, W = K::W, R = K::R, TQ = K::TQ, CK = K::CK, S = K::S;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.x / K::TPI, r0 = (blockIdx.x % K::TPI) * R;
+    constexpr int PG = K::NPB / 8;
+    const int pix = (warp % PG) * 8 + (lane & 7);
+    const int cg = (warp / PG) * 4 + (lane >> 3);
+    const int pby = pix / K::PBW, pbx = pix % K::PBW;
+
+    // zero both stages once: rows / columns outside the image are never written by the pipeline
+    for (int i = tid; i < 2 * K::STAGE / 4; i += K::THREADS)
+        reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    auto load_chunk = [&](int chunk, int buf) {
+        float* in_s = smem + buf * K::STAGE;
+        float* w_s = in_s + K::IN_ELEMS;
+        const int ci0 = chunk * CK;
+        constexpr int SEGS = W / 4, NIN = CK * K::ROWS * SEGS;
+        for (int i = tid; i < NIN; i += K::THREADS) {
+            const int seg = i % SEGS, row = (i / SEGS) % K::ROWS, cil = i / (SEGS * K::ROWS);
+            const int gr = r0 - 1 + row;
+            if (gr >= 0 && gr < H)
+                cp_async16(in_s + (cil * K::ROWS + row) * S + 4 + 4 * seg,
+                           x + (static_cast<size_t>(n * C + ci0 + cil) * H + gr) * W + 4 * seg);
+        }
+        const float* wsrc = wp + static_cast<size_t>(ci0) * 9 * C;
+        for (int i = tid; i < K::W_ELEMS / 4; i += K::THREADS) cp_async16(w_s + 4 * i, wsrc + 4 * i);
+        cp_async_commit();
+    };
+
+    float acc[TQ][2][4];
+#pragma unroll
+    for (int q = 0; q < TQ; ++q)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[q][r][c] = 0.f;
+
+    load_chunk(0, 0);
+#pragma unroll 1
+    for (int ch = 0; ch < K::NCHUNK; ++ch) {
+        cp_async_wait_all();
+        __syncthreads();               // chunk ch has landed for everyone; everyone is done with chunk ch-1's buffer
+        if (ch + 1 < K::NCHUNK) load_chunk(ch + 1, (ch + 1) & 1);
+        const float* in_s = smem + (ch & 1) * K::STAGE + (2 * pby) * S + 4 * pbx + 3;
+        const float* w_s = smem + (ch & 1) * K::STAGE + K::IN_ELEMS + cg * TQ;
+#pragma unroll
+        for (int cil = 0; cil < CK; ++cil) {
+            float v[4][6];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const float* p = in_s + (cil * K::ROWS + rr) * S;
+                v[rr][0] = p[0];
+                const float4 m = *reinterpret_cast<const float4*>(p + 1);
+                v[rr][1] = m.x; v[rr][2] = m.y; v[rr][3] = m.z; v[rr][4] = m.w;
+                v[rr][5] = p[5];
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int kh = t / 3, kw = t % 3;
+                float wv[TQ];
+                const float* wq = w_s + (cil * 9 + t) * C;
+                if constexpr (TQ == 2) {
+                    const float2 a = *reinterpret_cast<const float2*>(wq);
+                    wv[0] = a.x; wv[1] = a.y;
+                } else {
+#pragma unroll
+                    for (int q4 = 0; q4 < TQ / 4; ++q4) {
+                        const float4 a = *reinterpret_cast<const float4*>(wq + 4 * q4);
+                        wv[4 * q4] = a.x; wv[4 * q4 + 1] = a.y; wv[4 * q4 + 2] = a.z; wv[4 * q4 + 3] = a.w;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < TQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[q][r][c] = fmaf(wv[q], v[r + kh][c + kw], acc[q][r][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < TQ; ++q)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float* dst = y + (static_cast<size_t>(n * C + cg * TQ + q) * H + r0 + 2 * pby + r) * W + 4 * pbx;
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[q][r][0], acc[q][r][1], acc[q][r][2], acc[q][r][3]);
+        }
+}
+
+// W[co][ci][3][3] -> forward packing wf[ci][t][co] and dgrad packing wd[co][8-t][ci]; blockIdx.y = layer.
+struct ConvPackDesc {
+    const float* w;
+    float* wf;
+    float* wd;
+    long long c;
+};
+
+__global__ void __launch_bounds__(kThreads) conv3x3_pack_kernel(const ConvPackDesc* __restrict__ descs) {
+    const ConvPackDesc d = descs[blockIdx.y];
+    const int C = static_cast<int>(d.c), total = C * C * 9;
+    for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < total; idx += gridDim.x * kThreads) {
+        const int co = idx / (C * 9), ci = (idx / 9) % C, t = idx % 9;
+        const float v = d.w[idx];
+        d.wf[(ci * 9 + t) * C + co] = v;
+        d.wd[(co * 9 + (8 - t)) * C + ci] = v;
+    }
+}
+
+template <class K>
+static int launch_conv(const float* x, const float* wp, float* y, int n, cudaStream_t st) {
+    static bool attr_set = false;      // benign race: idempotent
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv3x3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            return AFAN_ERR_LAUNCH;
+        }
+        attr_set = true;
+    }
+    // plain launches: with the PDL attribute the early-scheduled CTAs of these shared-memory-heavy kernels serialise
+    // against their neighbours inside the captured step (measured: 27.4 ms/step with, 15.8 ms without)
+    conv3x3_kernel<K><<<static_cast<unsigned>(n * K::TPI), K::THREADS, K::SMEM_BYTES, st>>>(x, wp, y);
+    return launch_status();
+}
+
+
+// ---- wgrad ----------------------------------------------------------------------------------------------------
+// dW[co,ci,kh,kw] = sum over images and pixels of dy[n,co,h,w] * x[n,ci,h+kh-1,w+kw-1].  Persistent CTAs walk
+// "units" (an RB-row band of one image) through a 2-stage cp.async pipeline; a thread owns 4 output channels x 2
+// input channels x 9 taps (72 accumulators) and consumes 4 pixels per step: 4 LDS.128 of dy + 2x3 x (LDS.32, LDS.128,
+// LDS.32) of x feed 288 FFMAs.  Lanes walk the output-channel groups (dy is staged as [pixel quad][co][4] so those
+// loads are one contiguous 16-byte word per lane); the x words are shared by the whole group (broadcast).  PS thread
+// slices take alternate rows of the band and are folded in shared memory; every CTA then writes its partial dW and a
+// second kernel sums the partials in CTA order: no atomics, deterministic.
+template <int C_, int HW_, int RB_, int PS_, int NY_>
+struct WgradCfg {
+    static constexpr int C = C_, H = HW_, W = HW_, RB = RB_, PS = PS_, NY = NY_;
+    static constexpr int S = (W == 32) ? 40 : (W == 16 ? 24 : 20);
+    static constexpr int CIB = C / NY;                     // input channels per CTA (blockIdx.y selects the slice)
+    static constexpr int NCG = C / 4, NCP = CIB / 2, TC = NCG * NCP, THREADS = TC * PS;
+    static constexpr int XROWS = RB + 2;
+    static constexpr int PLANE = ((XROWS * S + 23) / 32) * 32 + 8;   // == 8 (mod 32): neighbouring channels on distinct banks
+    static constexpr int X_ELEMS = CIB * PLANE;
+    static constexpr int DY_ELEMS = RB * W * C;
+    static constexpr int STAGE = X_ELEMS + DY_ELEMS;
+    static constexpr int RED_ELEMS = (PS - 1) * 72 * TC;
+    static constexpr int SMEM_ELEMS = (2 * STAGE > RED_ELEMS) ? 2 * STAGE : RED_ELEMS;
+    static constexpr int SMEM_BYTES = SMEM_ELEMS * 4;
+    static constexpr int UPI = H / RB;                     // units per image
+    static_assert(PLANE >= XROWS * S && PLANE % 4 == 0, "plane pitch");
+    static_assert(RB % PS == 0 && H % RB == 0 && THREADS % 32 == 0 && THREADS <= 512, "tiling");
+};
+
+template <class K>
+__global__ void __launch_bounds__(K::THREADS)
+conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial, int n_images) {
+    constexpr int C = K::C, H = K::H, W = K::W, RB = K::RB, S = K::S;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int cg = tid % K::NCG, cp = (tid / K::NCG) % K::NCP, slice = tid / K::TC;
+    const int ci_base = blockIdx.y * K::CIB;
+    const int units = n_images * K::UPI;
+
+    for (int i = tid; i < 2 * K::STAGE / 4; i += K::THREADS)
+        reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    auto load_unit = [&](int u, int buf) {
+        float* x_s = smem + buf * K::STAGE;
+        float* dy_s = x_s + K::X_ELEMS;
+        const int n = u / K::UPI, r0 = (u % K::UPI) * RB;
+        constexpr int SEGS = W / 4, NX = K::CIB * K::XROWS * SEGS, ND = C * RB * SEGS;
+        for (int i = tid; i < NX; i += K::THREADS) {
+            const int seg = i % SEGS, row = (i / SEGS) % K::XROWS, cil = i / (SEGS * K::XROWS);
+            const int gr = r0 - 1 + row;
+            float* dst = x_s + cil * K::PLANE + row * S + 4 + 4 * seg;
+            if (gr >= 0 && gr < H)
+                cp_async16(dst, x + (static_cast<size_t>(n * C + ci_base + cil) * H + gr) * W + 4 * seg);
+            else
+                *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // band touches the image border
+        }
+        for (int i = tid; i < ND; i += K::THREADS) {
+            const int seg = i % SEGS, row = (i / SEGS) % RB, co = i / (SEGS * RB);
+            cp_async16(dy_s + ((row * SEGS + seg) * C + co) * 4,
+                       dy + (static_cast<size_t>(n * C + co) * H + r0 + row) * W + 4 * seg);
+        }
+        cp_async_commit();
+    };
+
+    float acc[4][2][9];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[q][j][t] = 0.f;
+
+    int u = blockIdx.x, buf = 0;
+    if (u < units) load_unit(u, 0);
+#pragma unroll 1
+    for (; u < units; u += gridDim.x, buf ^= 1) {
+        cp_async_wait_all();
+        __syncthreads();
+        if (u + static_cast<int>(gridDim.x) < units) load_unit(u + gridDim.x, buf ^ 1);
+        const float* x_s = smem + buf * K::STAGE + (2 * cp) * K::PLANE + 3;
+        const float* dy_s = smem + buf * K::STAGE + K::X_ELEMS + cg * 4;
+#pragma unroll 1
+        for (int r = slice; r < RB; r += K::PS) {
+#pragma unroll 2
+            for (int wq = 0; wq < W / 4; ++wq) {
+                float4 d[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    d[q] = *reinterpret_cast<const float4*>(dy_s + ((r * (W / 4) + wq) * C + K::NCG * q) * 4);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const float* p = x_s + j * K::PLANE + (r + kh) * S + 4 * wq;
+                        float xv[6];
+                        xv[0] = p[0];
+                        const float4 m = *reinterpret_cast<const float4*>(p + 1);
+                        xv[1] = m.x; xv[2] = m.y; xv[3] = m.z; xv[4] = m.w;
+                        xv[5] = p[5];
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float a = acc[q][j][kh * 3 + kw];
+                                a = fmaf(d[q].x, xv[kw], a);
+                                a = fmaf(d[q].y, xv[kw + 1], a);
+                                a = fmaf(d[q].z, xv[kw + 2], a);
+                                a = fmaf(d[q].w, xv[kw + 3], a);
+                                acc[q][j][kh * 3 + kw] = a;
+                            }
+                    }
+            }
+        }
+    }
+    // fold the PS row slices (fixed order), then publish this CTA's partial as [k = (q, j, t)][thread of slice 0]
+    if constexpr (K::PS > 1) {
+        __syncthreads();               // everyone is done reading the tiles; reuse the shared memory
+        if (slice > 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int t = 0; t < 9; ++t)
+                        smem[((slice - 1) * 72 + (q * 2 + j) * 9 + t) * K::TC + (tid % K::TC)] = acc[q][j][t];
+        }
+        __syncthreads();
+        if (slice == 0) {
+            for (int s = 0; s < K::PS - 1; ++s)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) acc[q][j][t] += smem[(s * 72 + (q * 2 + j) * 9 + t) * K::TC + tid];
+        }
+    }
+    if (slice == 0) {
+        float* dst = partial + static_cast<size_t>(blockIdx.x * K::NY + blockIdx.y) * 72 * K::TC + tid;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) dst[((q * 2 + j) * 9 + t) * K::TC] = acc[q][j][t];
+    }
+}
+
+// dW[o] = sum over CTAs (ascending) of their partials; one thread per (slice y, k, thread-of-slice-0).
+template <class K>
+__global__ void __launch_bounds__(kThreads) conv3x3_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nbx) {
+    const int idx = blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= K::NY * 72 * K::TC) return;
+    const int tc = idx % K::TC, k = (idx / K::TC) % 72, y = idx / (K::TC * 72);
+    float s = 0.f;
+#pragma unroll 8
+    for (int b = 0; b < nbx; ++b) s += partial[(static_cast<size_t>(b * K::NY + y) * 72 + k) * K::TC + tc];
+    const int q = k / 18, j = (k / 9) % 2, t = k % 9;
+    const int cg = tc % K::NCG, cp = tc / K::NCG;
+    const int co = cg + K::NCG * q, ci = y * K::CIB + 2 * cp + j;
+    dw[(co * K::C + ci) * 9 + t] = s;
+}
+
+template <class K>
+static int launch_wgrad(const float* x, const float* dy, float* dw, float* ws, long long ws_bytes, int n, cudaStream_t st) {
+    static bool attr_set = false;      // benign race: idempotent
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv3x3_wgrad_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            return AFAN_ERR_LAUNCH;
+        }
+        attr_set = true;
+    }
+    const int units = n * K::UPI;
+    int gx = sm_count() / K::NY;
+    if (gx > units) gx = units;
+    if (static_cast<long long>(gx) * K::NY * K::C * K::C * 9 * 4 > ws_bytes) return AFAN_ERR_WORKSPACE;
+    conv3x3_wgrad_kernel<K><<<dim3(gx, K::NY), K::THREADS, K::SMEM_BYTES, st>>>(x, dy, ws, n);
+    if (launch_status() != AFAN_OK) return AFAN_ERR_LAUNCH;
+    const int total = K::C * K::C * 9;
+    conv3x3_wgrad_reduce_kernel<K><<<(total + kThreads - 1) / kThreads, kThreads, 0, st>>>(ws, dw, gx);
+    return launch_status();
+}
+
+}  // namespace afan
+
+using namespace afan;
+
+AFAN_EXPORT int afan_conv3x3_pack_f32(const void* descs_device, int64_t n_layers, int64_t c_max, afan_stream_t stream) {
+    if (n_layers < 0 || c_max <= 0) return AFAN_ERR_SIZE;
+    if (n_layers == 0) return AFAN_OK;
+    if (!descs_device) return AFAN_ERR_NULL;
+    const long long total = c_max * c_max * 9;
+    const unsigned gx = static_cast<unsigned>((total + kThreads - 1) / kThreads);
+    conv3x3_pack_kernel<<<dim3(gx < 16u ? gx : 16u, static_cast<unsigned>(n_layers)), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const ConvPackDesc*>(descs_device));
+    return launch_status();
+}
+
+// variant: 0 = default tiling for the shape; other values select tuning candidates (bench only)
+AFAN_EXPORT int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
+                                 int variant, afan_stream_t stream) {
+    if (n < 0 || c <= 0 || hw <= 0) return AFAN_ERR_SIZE;
+    if (n == 0) return AFAN_OK;
+    if (!x || !w_packed || !y) return AFAN_ERR_NULL;
+    if (!aligned16(x) || !aligned16(w_packed) || !aligned16(y) || n * c * hw > (1ll << 30) / hw) return AFAN_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ni = static_cast<int>(n);
+#define AFAN_CONV(C, HW, R, TQ, CK) return launch_conv<ConvCfg<C, HW, R, TQ, CK>>(x, w_packed, y, ni, st)
+    if (c == 16 && hw == 32) {
+        if (variant == 1) AFAN_CONV(16, 32, 16, 4, 8);
+        if (variant == 2) AFAN_CONV(16, 32, 32, 4, 4);
+        if (variant == 3) AFAN_CONV(16, 32, 8, 4, 4);
+        AFAN_CONV(16, 32, 16, 4, 4);
+    }
+    if (c == 32 && hw == 16) {
+        if (variant == 1) AFAN_CONV(32, 16, 16, 8, 8);
+        if (variant == 2) AFAN_CONV(32, 16, 8, 4, 8);
+        if (variant == 3) AFAN_CONV(32, 16, 16, 4, 4);
+        AFAN_CONV(32, 16, 16, 4, 8);
+    }
+    if (c == 64 && hw == 8) {
+        if (variant == 1) AFAN_CONV(64, 8, 8, 4, 8);
+        if (variant == 2) AFAN_CONV(64, 8, 8, 8, 8);
+        if (variant == 3) AFAN_CONV(64, 8, 8, 2, 4);
+        AFAN_CONV(64, 8, 8, 2, 8);
+    }
+    if (c == 16 && hw == 16) AFAN_CONV(16, 16, 16, 4, 4);
+    if (c == 16 && hw == 8) AFAN_CONV(16, 8, 8, 4, 4);
+    if (c == 32 && hw == 32) AFAN_CONV(32, 32, 16, 4, 8);
+    if (c == 32 && hw == 8) AFAN_CONV(32, 8, 8, 4, 8);
+    if (c == 64 && hw == 16) AFAN_CONV(64, 16, 16, 4, 8);
+    if (c == 64 && hw == 32) AFAN_CONV(64, 32, 16, 8, 8);
+#undef AFAN_CONV
+    return AFAN_ERR_UNSUPPORTED;
+}
+
+AFAN_EXPORT int64_t afan_conv3x3_wgrad_workspace_bytes(int64_t c) {
+    return c <= 0 ? 0 : static_cast<int64_t>(sm_count()) * c * c * 9 * 4;
+}
+
+AFAN_EXPORT int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
+                                       int64_t n, int64_t c, int64_t hw, afan_stream_t stream) {
+    if (n <= 0 || c <= 0 || hw <= 0) return AFAN_ERR_SIZE;
+    if (!x || !dy || !dw) return AFAN_ERR_NULL;
+    if (!workspace) return AFAN_ERR_WORKSPACE;
+    if (!aligned16(x) || !aligned16(dy) || !aligned16(workspace) || n * c * hw > (1ll << 30) / hw) return AFAN_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ni = static_cast<int>(n);
+    float* ws = static_cast<float*>(workspace);
+#define AFAN_WGRAD(C, HW, RB, PS, NY) return launch_wgrad<WgradCfg<C, HW, RB, PS, NY>>(x, dy, dw, ws, workspace_bytes, ni, st)
+    if (c == 16 && hw == 32) AFAN_WGRAD(16, 32, 8, 8, 1);
+    if (c == 16 && hw == 16) AFAN_WGRAD(16, 16, 8, 8, 1);
+    if (c == 16 && hw == 8) AFAN_WGRAD(16, 8, 8, 8, 1);
+    if (c == 32 && hw == 32) AFAN_WGRAD(32, 32, 2, 2, 1);
+    if (c == 32 && hw == 16) AFAN_WGRAD(32, 16, 2, 2, 1);
+    if (c == 32 && hw == 8) AFAN_WGRAD(32, 8, 2, 2, 1);
+    if (c == 64 && hw == 32) AFAN_WGRAD(64, 32, 2, 1, 2);
+    if (c == 64 && hw == 16) AFAN_WGRAD(64, 16, 2, 1, 2);
+    if (c == 64 && hw == 8) AFAN_WGRAD(64, 8, 2, 1, 2);
+#undef AFAN_WGRAD
+    return AFAN_ERR_UNSUPPORTED;
+}

@@ -294,3 +294,46 @@ def nms_flags(boxes: torch.Tensor, scores: torch.Tensor, threshold: float):
                                   _lib.dev_ptr(keep, torch.uint8, "keep"), _lib.dev_ptr(count, torch.int32, "count"),
                                   ptr(ws), ws.numel() * 8, n, stream()), "afan_nms_f32")
     return keep, count
+
+
+# ------------------------------------------------------------------------------------------------
+# 3x3 / stride 1 / pad 1 convolutions of the re-executed tail (Classification/resnet_s.py:53,55)
+# ------------------------------------------------------------------------------------------------
+CONV3X3_CHANNELS = (16, 32, 64)
+CONV3X3_SIZES = (8, 16, 32)
+
+
+def conv3x3_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Shapes the hand-written kernels cover: square 8/16/32 maps, C_in == C_out in {16, 32, 64}, fp32 NCHW."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and weight.shape[0] == weight.shape[1] == x.shape[1]
+            and x.shape[1] in CONV3X3_CHANNELS and x.shape[2] == x.shape[3] and x.shape[2] in CONV3X3_SIZES
+            and tuple(weight.shape[2:]) == (3, 3))
+
+
+def conv3x3_pack(descs: torch.Tensor, c_max: int):
+    """Repack every layer listed in `descs` (int64 [L, 4] = weight ptr, fwd-packed ptr, dgrad-packed ptr, C) in ONE launch."""
+    check(_lib.lib().afan_conv3x3_pack_f32(_lib.dev_ptr(descs, torch.int64, "descs"), descs.shape[0], int(c_max), stream()),
+          "afan_conv3x3_pack_f32")
+
+
+def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0) -> torch.Tensor:
+    """y = conv2d(x, W, stride 1, pad 1) with W packed as [reduction channel][tap][output channel] (forward packing), or
+    the input gradient of that convolution when given dy and the dgrad packing."""
+    n, c, h, _ = x.shape
+    y = torch.empty_like(x)
+    check(_lib.lib().afan_conv3x3_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), n, c, h, int(variant), stream()),
+          "afan_conv3x3_f32")
+    return y
+
+
+def conv3x3_wgrad_workspace(c: int, device) -> torch.Tensor:
+    return torch.empty(_lib.lib().afan_conv3x3_wgrad_workspace_bytes(int(c)) // 4, dtype=torch.float32, device=device)
+
+
+def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
+    """dW [C, C, 3, 3] of the convolution above (deterministic: per-CTA partials folded in CTA order)."""
+    n, c, h, _ = x.shape
+    dw = torch.empty((c, c, 3, 3), dtype=torch.float32, device=x.device)
+    check(_lib.lib().afan_conv3x3_wgrad_f32(f32(x, "x"), f32(dy, "dy"), f32(dw), ptr(ws), ws.numel() * 4, n, c, h, stream()),
+          "afan_conv3x3_wgrad_f32")
+    return dw

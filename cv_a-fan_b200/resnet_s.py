@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .conv import Conv3x3
 from .dual_bn import DualBatchNorm2d
 
 CIFAR_MEAN = (0.4914, 0.4822, 0.4465)
@@ -40,9 +41,9 @@ class BasicBlock(nn.Module):
 
     def __init__(self, in_planes: int, planes: int, stride: int = 1):
         super().__init__()
-        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride, 1, bias=False)
+        self.conv1 = Conv3x3(in_planes, planes, stride)
         self.bn1 = DualBatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.conv2 = Conv3x3(planes, planes, 1)
         self.bn2 = DualBatchNorm2d(planes)
         self.shortcut = nn.Sequential()            # keeps the (parameter-free) child name of the reference
         self.downsample = stride != 1 or in_planes != planes

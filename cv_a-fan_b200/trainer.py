@@ -23,7 +23,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import _lib, attack_algo, ops, sync
+from . import _lib, attack_algo, conv, ops, sync
 from ._lib import AfanError
 from .dual_bn import DualBatchNorm2d
 
@@ -77,6 +77,7 @@ class AfanTrainer:
         self._static = {}
         self._bn = [m for m in model.modules() if isinstance(m, DualBatchNorm2d)]
         self._bn_per_iter = None
+        self._conv_pack = conv.PackPlan(model)     # one-launch weight repack for the hand-written 3x3 convolutions
         self.iterations = 0
         self.kernel_launches_per_iter = None       # afan kernels per iteration (counted at trace time)
 
@@ -155,6 +156,7 @@ class AfanTrainer:
         scale = sync.allreduce_grad_arena_(self.flat_grad, self.pg)                  # one NCCL message / iteration
         ops.sgd_momentum_(self.flat_param, self.flat_grad, self.flat_buf, self.lr_dev, momentum=self.momentum,
                           weight_decay=self.weight_decay, grad_scale=scale)                   # :201
+        self._conv_pack.pack()                     # the SGD kernel wrote the weights behind autograd's back
 
     def _discover_arena(self, images, target, noise, norms_out, ws):
         """First iteration: find the parameters that actually receive gradients (torch.optim.SGD skips
@@ -163,11 +165,13 @@ class AfanTrainer:
         snap = self._snapshot()
         for p in self.model.parameters():
             p.grad = None
+        self._conv_pack.pack()
         loss, _ = self._iteration(images, target, noise, norms_out, ws)
         loss.backward()
         used = [p for p in self.model.parameters() if p.grad is not None]
         self._restore(snap)
         self._build_arena(used)
+        self._conv_pack.pack()
 
     # ---- state snapshot (graph warm-up must not leak into training state) -------------------------
     def _snapshot(self):
@@ -199,6 +203,7 @@ class AfanTrainer:
             self._discover_arena(images, target, noise, st["norms"], st["ws"])
         if not self.use_graph:
             l0 = _lib.launch_count
+            self._conv_pack.pack()                 # weights may have been written from outside (load_state_dict)
             loss, out_clean = self._iteration(images, target, noise, st["norms"], st["ws"])
             self._optimize(loss)
             self.kernel_launches_per_iter = _lib.launch_count - l0
@@ -227,6 +232,7 @@ class AfanTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):                      # warm-up: cuDNN autotune, NCCL communicator, lazy module load
+                self._conv_pack.pack()
                 loss, _ = self._iteration(st["images"], st["target"], st["noise"], st["norms"], st["ws"])
                 self._optimize(loss)
             del loss
@@ -236,6 +242,7 @@ class AfanTrainer:
         self._graph = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count
         with torch.cuda.graph(self._graph, stream=side):
+            self._conv_pack.pack()
             loss, out_clean = self._iteration(st["images"], st["target"], st["noise"], st["norms"], st["ws"])
             self._optimize(loss)
             st["loss"], st["out_clean"] = loss.detach(), out_clean.detach()
@@ -258,5 +265,6 @@ class AfanTrainer:
     @torch.no_grad()
     def evaluate(self, images, target):
         self.model.eval()
+        self._conv_pack.pack()
         out = self.model(images, end_point=self.L, start_point=0)
         return self.criterion(out, target), out

@@ -222,6 +222,27 @@ int afan_roi_align_bwd_f32(const float* dout, const float* rois, float* dfeat, i
                            int64_t w, int64_t r, int64_t ph, int64_t pw, float spatial_scale,
                            int sampling_ratio, afan_stream_t stream);
 
+/* ---- a1/a6 tail: 3x3 / stride 1 / pad 1 convolutions re-executed by every PGD step ---------------
+ * Replace nn.Conv2d `conv1` / `conv2` of BasicBlock (Classification/resnet_s.py:53,55) as called by the
+ * ascent's tail passes (attack_algo.py:49-52) and the final adversarial / clean passes
+ * (main_perturb.py:195-200), for C_in == C_out == c in {16, 32, 64} on square hw in {8, 16, 32} maps,
+ * fp32 NCHW, strict fp32 FFMA accumulation in a fixed order (deterministic).  Other shapes return
+ * AFAN_ERR_UNSUPPORTED (the caller keeps the library convolution for them).
+ *
+ * afan_conv3x3_pack_f32: descs_device = device array of n_layers records {const float* w; float* wf;
+ *     float* wd; int64 c}; repacks W[co][ci][3][3] of every layer in ONE launch into the forward packing
+ *     wf[ci][tap][co] and the input-gradient packing wd[co][8-tap][ci] (c*9*c floats each).
+ * afan_conv3x3_f32: y = conv(x, W) when given wf; dx = conv_transpose(dy, W) when given dy and wd.
+ *     variant 0 = tuned default; other values select alternative tilings (benchmarking only).
+ * afan_conv3x3_wgrad_f32: dW[co][ci][3][3] = sum_{n,h,w} dy * shifted x.  Two launches: per-CTA partials
+ *     into `workspace` (>= afan_conv3x3_wgrad_workspace_bytes(c), need not be zeroed), then a fixed-order fold. */
+int afan_conv3x3_pack_f32(const void* descs_device, int64_t n_layers, int64_t c_max, afan_stream_t stream);
+int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
+                     int variant, afan_stream_t stream);
+int64_t afan_conv3x3_wgrad_workspace_bytes(int64_t c);
+int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
+                           int64_t n, int64_t c, int64_t hw, afan_stream_t stream);
+
 /* ---- a7 tail: fused SGD(momentum, weight decay) over a flat parameter arena ---------------------
  * Replaces optimizer.step() of torch.optim.SGD, main_perturb.py:72-74,201:
  *     g = grad*grad_scale + wd*p;  buf = momentum*buf + g;  p -= lr*buf      (buf starts at 0)

@@ -1,0 +1,72 @@
+"""Hand-written 3x3 convolutions (forward / input gradient / weight gradient) against an fp64 convolution of the same
+inputs -- the tail's nn.Conv2d of Classification/resnet_s.py:53,55.  Tolerance: fp32 accumulation over K = 9*C terms,
+|err| <= 2e-5 * max|ref| (cuDNN's own fp32 algorithms measure 1e-5 .. 5e-5 on these shapes)."""
+import importlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+pkg = importlib.import_module("cv_a-fan_b200")
+ops, conv = pkg.ops, pkg.conv
+
+SHAPES = [(128, 16, 32), (128, 32, 16), (128, 64, 8), (256, 32, 16), (3, 64, 32), (5, 32, 8), (2, 16, 8), (7, 16, 16),
+          (1, 32, 32), (9, 64, 16)]
+
+
+def _rel(a, ref):
+    return ((a.double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("n,c,h", SHAPES)
+def test_conv3x3_forward_dgrad_wgrad_vs_fp64(n, c, h):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(n * 1000 + c + h)
+    x = torch.randn(n, c, h, h, generator=g).to(dev)
+    w = (torch.randn(c, c, 3, 3, generator=g) * (2.0 / (9 * c)) ** 0.5).to(dev)
+    dy = torch.randn(n, c, h, h, generator=g).to(dev)
+    m = conv.Conv3x3(c, c, 1).to(dev)
+    with torch.no_grad():
+        m.weight.copy_(w)
+    xr = x.clone().requires_grad_(True)
+    y = m(xr)
+    dx, dw = torch.autograd.grad(y, (xr, m.weight), dy)
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    ref_dx = torch.nn.grad.conv2d_input(x.shape, w.double(), dy.double(), padding=1)
+    ref_dw = torch.nn.grad.conv2d_weight(x.double(), w.shape, dy.double(), padding=1)
+    assert _rel(y, ref) < 2e-5 and _rel(dx, ref_dx) < 2e-5 and _rel(dw, ref_dw) < 2e-5
+    # zero padding really is zero: a constant image convolved with an all-ones kernel counts the taps inside the image
+    with torch.no_grad():
+        m.weight.fill_(1.0)
+    ones = m(torch.ones(1, c, h, h, device=dev))
+    assert ones[0, 0, 0, 0].item() == 4 * c and ones[0, 0, 1, 1].item() == 9 * c and ones[0, -1, -1, 0].item() == 4 * c
+    assert ones[0, 0, 0, 1].item() == 6 * c
+
+
+def test_conv3x3_is_deterministic_and_repacks_after_weight_update():
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = conv.Conv3x3(32, 32, 1).to(dev)
+    x = torch.randn(16, 32, 16, 16, device=dev, requires_grad=True)
+    dy = torch.randn(16, 32, 16, 16, device=dev)
+    outs = [torch.autograd.grad(m(x), (x, m.weight), dy) for _ in range(3)]
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
+    y0 = m(x).detach()
+    with torch.no_grad():
+        m.weight.mul_(2.0)             # bumps weight._version -> the module repacks
+    assert torch.allclose(m(x).detach(), 2 * y0, rtol=1e-6, atol=1e-6)
+
+
+def test_unsupported_shapes_use_the_library_convolution():
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = conv.Conv3x3(16, 32, 2).to(dev)                      # stride-2 stage transition (resnet_s.py:98)
+    x = torch.randn(4, 16, 32, 32, device=dev)
+    assert torch.allclose(m(x), F.conv2d(x, m.weight, stride=2, padding=1))
+    m2 = conv.Conv3x3(16, 16, 1).to(dev)
+    x2 = torch.randn(2, 16, 12, 12, device=dev)              # 12x12 is not a covered map size
+    assert torch.allclose(m2(x2), F.conv2d(x2, m2.weight, padding=1))
+    assert ops.conv3x3_supported(torch.randn(2, 16, 16, 16, device=dev), m2.weight)
