@@ -58,7 +58,7 @@ SIGNATURES = {
     "afan_conv3x3_pack_f32": (_int, [_vp, _i64, _i64, _vp]),
     "afan_conv3x3_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "afan_conv3x3_wgrad_workspace_bytes": (_i64, [_i64]),
-    "afan_conv3x3_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "afan_conv3x3_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
 }
 
 AFAN_ERR_UNSUPPORTED = -5

@@ -36,7 +36,13 @@ class _Conv3x3Fn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         dy = dy.contiguous()
         dx = ops.conv3x3(dy, ctx.wd) if ctx.needs_input_grad[0] else None
-        dw = ops.conv3x3_wgrad(x, dy, ctx.mod.wgrad_workspace()) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            mod = ctx.mod
+            if mod.grad_direct and mod.weight.grad is not None:
+                ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)   # no temporary, no add launch
+            else:
+                dw = ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace())
         return dx, dw, None
 
 
@@ -46,6 +52,7 @@ class Conv3x3(nn.Conv2d):
         self._packed = None            # float32 [2, C*9*C]: forward packing, dgrad packing
         self._packed_key = None        # (weight data_ptr, weight version) the packing was made from
         self._managed = False          # True while a trainer repacks all layers itself (pack_all)
+        self.grad_direct = False       # trainer-owned gradient arena: wgrad adds straight into weight.grad
         self._ws = None
 
     def _buffers_for(self, device):

@@ -328,23 +328,33 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
     }
 }
 
-// dW[o] = sum over CTAs (ascending) of their partials; one thread per (slice y, k, thread-of-slice-0).
+// dW[o] (+)= sum over CTAs of their partials.  Block = 32 consecutive outputs x 8 slices of the CTA range: every thread
+// folds its slice in ascending CTA order, the 8 slice sums are folded in slice order (fixed order: deterministic).
 template <class K>
-__global__ void __launch_bounds__(kThreads) conv3x3_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nbx) {
-    const int idx = blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= K::NY * 72 * K::TC) return;
+__global__ void __launch_bounds__(256) conv3x3_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nbx,
+                                                                   int accumulate) {
+    __shared__ float red[8][32];
+    const int idx = blockIdx.x * 32 + threadIdx.x;          // < NY * 72 * TC (a multiple of 32)
     const int tc = idx % K::TC, k = (idx / K::TC) % 72, y = idx / (K::TC * 72);
     float s = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < nbx; ++b) s += partial[(static_cast<size_t>(b * K::NY + y) * 72 + k) * K::TC + tc];
-    const int q = k / 18, j = (k / 9) % 2, t = k % 9;
-    const int cg = tc % K::NCG, cp = tc / K::NCG;
-    const int co = cg + K::NCG * q, ci = y * K::CIB + 2 * cp + j;
-    dw[(co * K::C + ci) * 9 + t] = s;
+#pragma unroll 4
+    for (int b = threadIdx.y; b < nbx; b += 8) s += partial[(static_cast<size_t>(b * K::NY + y) * 72 + k) * K::TC + tc];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) s += red[i][threadIdx.x];
+        const int q = k / 18, j = (k / 9) % 2, t = k % 9;
+        const int cg = tc % K::NCG, cp = tc / K::NCG;
+        const int co = cg + K::NCG * q, ci = y * K::CIB + 2 * cp + j;
+        float* dst = dw + (co * K::C + ci) * 9 + t;
+        *dst = accumulate ? *dst + s : s;
+    }
 }
 
 template <class K>
-static int launch_wgrad(const float* x, const float* dy, float* dw, float* ws, long long ws_bytes, int n, cudaStream_t st) {
+static int launch_wgrad(const float* x, const float* dy, float* dw, float* ws, long long ws_bytes, int n, int accumulate,
+                        cudaStream_t st) {
     static bool attr_set = false;      // benign race: idempotent
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv3x3_wgrad_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES) != cudaSuccess) {
@@ -360,7 +370,7 @@ static int launch_wgrad(const float* x, const float* dy, float* dw, float* ws, l
     conv3x3_wgrad_kernel<K><<<dim3(gx, K::NY), K::THREADS, K::SMEM_BYTES, st>>>(x, dy, ws, n);
     if (launch_status() != AFAN_OK) return AFAN_ERR_LAUNCH;
     const int total = K::C * K::C * 9;
-    conv3x3_wgrad_reduce_kernel<K><<<(total + kThreads - 1) / kThreads, kThreads, 0, st>>>(ws, dw, gx);
+    conv3x3_wgrad_reduce_kernel<K><<<total / 32, dim3(32, 8), 0, st>>>(ws, dw, gx, accumulate);
     return launch_status();
 }
 
@@ -422,7 +432,7 @@ AFAN_EXPORT int64_t afan_conv3x3_wgrad_workspace_bytes(int64_t c) {
 }
 
 AFAN_EXPORT int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
-                                       int64_t n, int64_t c, int64_t hw, afan_stream_t stream) {
+                                       int64_t n, int64_t c, int64_t hw, int accumulate, afan_stream_t stream) {
     if (n <= 0 || c <= 0 || hw <= 0) return AFAN_ERR_SIZE;
     if (!x || !dy || !dw) return AFAN_ERR_NULL;
     if (!workspace) return AFAN_ERR_WORKSPACE;
@@ -430,7 +440,7 @@ AFAN_EXPORT int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* d
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int ni = static_cast<int>(n);
     float* ws = static_cast<float*>(workspace);
-#define AFAN_WGRAD(C, HW, RB, PS, NY) return launch_wgrad<WgradCfg<C, HW, RB, PS, NY>>(x, dy, dw, ws, workspace_bytes, ni, st)
+#define AFAN_WGRAD(C, HW, RB, PS, NY) return launch_wgrad<WgradCfg<C, HW, RB, PS, NY>>(x, dy, dw, ws, workspace_bytes, ni, accumulate, st)
     if (c == 16 && hw == 32) AFAN_WGRAD(16, 32, 8, 8, 1);
     if (c == 16 && hw == 16) AFAN_WGRAD(16, 16, 8, 8, 1);
     if (c == 16 && hw == 8) AFAN_WGRAD(16, 8, 8, 8, 1);

@@ -19,7 +19,7 @@ from ._lib import AfanError
 class _DualBNTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, ws, groups, eps, momentum, relu, replay,
-                process_group, mailbox):
+                process_group, mailbox, grad_out=None):
         x = x.contiguous()
         res = residual.contiguous() if residual is not None else None
         y, save_mean, save_invstd = ops.bn_fwd(x, res, weight, bias, running_mean, running_var, ws, groups=groups,
@@ -27,17 +27,23 @@ class _DualBNTrainFn(torch.autograd.Function):
                                                process_group=process_group, mailbox=mailbox)
         ctx.save_for_backward(x, y if relu else None, weight, save_mean, save_invstd)
         ctx.ws, ctx.groups, ctx.relu, ctx.has_res, ctx.pg, ctx.mailbox = ws, groups, relu, residual is not None, process_group, mailbox
+        ctx.grad_out = grad_out
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y, weight, save_mean, save_invstd = ctx.saved_tensors
         want_res = ctx.has_res and ctx.needs_input_grad[1]
+        direct = ctx.grad_out is not None and ctx.needs_input_grad[2] and ctx.needs_input_grad[3]
         dx, dres, dw, db = ops.bn_bwd(dy.contiguous(), x, y, weight, save_mean, save_invstd, ctx.ws,
                                       groups=ctx.groups, relu=ctx.relu, want_dresidual=want_res,
-                                      process_group=ctx.pg, mailbox=ctx.mailbox)
+                                      process_group=ctx.pg, mailbox=ctx.mailbox,
+                                      dweight_out=ctx.grad_out[0] if direct else None,
+                                      dbias_out=ctx.grad_out[1] if direct else None)
+        if direct:                       # already stored in weight.grad / bias.grad: nothing for autograd to accumulate
+            dw = db = None
         return (dx, dres, dw if ctx.needs_input_grad[2] else None, db if ctx.needs_input_grad[3] else None,
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 class _AffineEvalFn(torch.autograd.Function):
@@ -74,6 +80,9 @@ class DualBatchNorm2d(nn.Module):
         self._pending_batches = 0      # host-side count, folded into num_batches_tracked lazily (no launch per pass)
         self.process_group = None      # set by the trainer for NCCL-synchronised statistics
         self.mailbox = None            # p2p.PeerMailbox: statistics exchanged over NVLink inside the kernel instead
+        # set by a trainer that owns a zeroed gradient arena AND runs this layer once per differentiated pass: the
+        # backward kernel stores d(weight), d(bias) straight into .grad (no temporaries, no accumulation launches)
+        self.grad_direct = False
         self._register_state_dict_hook(_flush_hook)
 
     def _workspace(self, groups: int, device):
@@ -93,9 +102,13 @@ class DualBatchNorm2d(nn.Module):
             raise AfanError(f"expected [N, {self.num_features}, H, W], got {tuple(x.shape)}")
         if self.training:
             self._pending_batches += groups * replay
+            grad_out = None
+            if self.grad_direct and self.weight.requires_grad and self.bias.requires_grad \
+                    and self.weight.grad is not None and self.bias.grad is not None and torch.is_grad_enabled():
+                grad_out = (self.weight.grad, self.bias.grad)
             return _DualBNTrainFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                                         self._workspace(groups, x.device), groups, self.eps, self.momentum, relu,
-                                        replay, self.process_group, self.mailbox)
+                                        replay, self.process_group, self.mailbox, grad_out)
         invstd = torch.rsqrt(self.running_var + self.eps)
         scale = self.weight.detach() * invstd
         scale_shift = torch.stack((scale, self.bias.detach() - self.running_mean * scale), dim=1).contiguous()

@@ -216,15 +216,16 @@ def bn_fwd(x, residual, weight, bias, running_mean, running_var, ws, *, groups=1
 
 
 def bn_bwd(dy, x, y, weight, save_mean, save_invstd, ws, *, groups=1, relu=False, want_dresidual=False,
-           process_group=None, split=False, mailbox=None):
+           process_group=None, split=False, mailbox=None, dweight_out=None, dbias_out=None):
     """Backward of bn_fwd.  Returns (dx, dresidual|None, dweight[C], dbias[C]) (dweight/dbias are LOCAL sums;
     the data-parallel gradient all-reduce averages them with the other parameters)."""
     n, c, hw = _nchw(x, groups)
     L = _lib.lib()
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dresidual else None
-    dweight = torch.empty(c, dtype=torch.float32, device=x.device)
-    dbias = torch.empty_like(dweight)
+    # dweight_out / dbias_out: the kernels STORE the sums there (e.g. straight into the gradient arena)
+    dweight = torch.empty(c, dtype=torch.float32, device=x.device) if dweight_out is None else dweight_out
+    dbias = torch.empty_like(dweight) if dbias_out is None else dbias_out
     world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     if mailbox is not None and not split:
         rc = L.afan_bn_bwd_p2p_f32(f32(dy), f32(x), f32(y) if relu else None, f32(weight), f32(save_mean), f32(save_invstd),
@@ -330,10 +331,13 @@ def conv3x3_wgrad_workspace(c: int, device) -> torch.Tensor:
     return torch.empty(_lib.lib().afan_conv3x3_wgrad_workspace_bytes(int(c)) // 4, dtype=torch.float32, device=device)
 
 
-def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
-    """dW [C, C, 3, 3] of the convolution above (deterministic: per-CTA partials folded in CTA order)."""
+def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, ws: torch.Tensor, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW [C, C, 3, 3] of the convolution above (deterministic: per-CTA partials folded in a fixed order).
+    accumulate_into: add the result to this tensor (a parameter's .grad inside the gradient arena) instead."""
     n, c, h, _ = x.shape
-    dw = torch.empty((c, c, 3, 3), dtype=torch.float32, device=x.device)
-    check(_lib.lib().afan_conv3x3_wgrad_f32(f32(x, "x"), f32(dy, "dy"), f32(dw), ptr(ws), ws.numel() * 4, n, c, h, stream()),
-          "afan_conv3x3_wgrad_f32")
+    dw = torch.empty((c, c, 3, 3), dtype=torch.float32, device=x.device) if accumulate_into is None else accumulate_into
+    if dw.numel() != c * c * 9:
+        raise AfanError("accumulate_into must hold C*C*9 floats")
+    check(_lib.lib().afan_conv3x3_wgrad_f32(f32(x, "x"), f32(dy, "dy"), f32(dw), ptr(ws), ws.numel() * 4, n, c, h,
+                                            int(accumulate_into is not None), stream()), "afan_conv3x3_wgrad_f32")
     return dw

@@ -103,6 +103,14 @@ class AfanTrainer:
             off += k
         self._params = used
         self._arena_built = True
+        # the arena is zeroed before every backward: gradient kernels may write straight into it.  Convolution weight
+        # gradients ADD (safe for any number of uses); BatchNorm d(weight)/d(bias) are STORED, which needs the layer to
+        # run exactly once per differentiated pass -- true for the head-cached [adv; clean] schedule of this trainer.
+        for m in self._conv_pack.mods:
+            m.grad_direct = True
+        if self.head_cache and type(self) is AfanTrainer:
+            for m in self._bn:
+                m.grad_direct = True
 
     @contextlib.contextmanager
     def _params_frozen(self):

@@ -235,13 +235,15 @@ int afan_roi_align_bwd_f32(const float* dout, const float* rois, float* dfeat, i
  * afan_conv3x3_f32: y = conv(x, W) when given wf; dx = conv_transpose(dy, W) when given dy and wd.
  *     variant 0 = tuned default; other values select alternative tilings (benchmarking only).
  * afan_conv3x3_wgrad_f32: dW[co][ci][3][3] = sum_{n,h,w} dy * shifted x.  Two launches: per-CTA partials
- *     into `workspace` (>= afan_conv3x3_wgrad_workspace_bytes(c), need not be zeroed), then a fixed-order fold. */
+ *     into `workspace` (>= afan_conv3x3_wgrad_workspace_bytes(c), need not be zeroed), then a fixed-order fold
+ *     that stores (accumulate = 0) or adds into dw (accumulate = 1: writes straight into a gradient arena
+ *     instead of a temporary + autograd's accumulation launch). */
 int afan_conv3x3_pack_f32(const void* descs_device, int64_t n_layers, int64_t c_max, afan_stream_t stream);
 int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
                      int variant, afan_stream_t stream);
 int64_t afan_conv3x3_wgrad_workspace_bytes(int64_t c);
 int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
-                           int64_t n, int64_t c, int64_t hw, afan_stream_t stream);
+                           int64_t n, int64_t c, int64_t hw, int accumulate, afan_stream_t stream);
 
 /* ---- a7 tail: fused SGD(momentum, weight decay) over a flat parameter arena ---------------------
  * Replaces optimizer.step() of torch.optim.SGD, main_perturb.py:72-74,201:

@@ -76,7 +76,7 @@ for (n, c, h) in ((128, 16, 32), (128, 32, 16), (128, 64, 8), (256, 32, 16), (25
     ws = torch.empty(wsb // 4, device=dev)
     dw = torch.empty_like(w)
     def wgrad():
-        _lib.check(L.afan_conv3x3_wgrad_f32(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), wsb, n, c, h, _lib.stream()), "wgrad")
+        _lib.check(L.afan_conv3x3_wgrad_f32(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), wsb, n, c, h, 0, _lib.stream()), "wgrad")
     wgrad()
     ref_dw = torch.nn.grad.conv2d_weight(x.double(), w.shape, dy.double(), padding=1)
     cud_dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, padding=1)
