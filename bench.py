@@ -125,7 +125,9 @@ def config_dict(n_gpus, conv_math="fp32", conv="afan"):
             "pgd_steps": w["steps"], "gamma_255": w["gamma"], "eps_255": w["eps"], "randinit": w["randinit"],
             "clip": w["clip"], "parallelism": f"dp{n_gpus} (one process per GPU, NCCL)",
             "conv_math": "fp32 (TF32 off)" if conv_math == "fp32" else "tf32 tensor cores (cuDNN), fp32 accumulate",
-            "conv3x3": "hand-written sm_100a direct convolution (strict fp32 FFMA)" if conv == "afan" else "cuDNN",
+            "conv3x3": {"afan": "hand-written sm_100a direct convolution (strict fp32 FFMA)" if conv_math == "fp32"
+                        else "hand-written sm_100a mma.sync TF32 implicit GEMM (1 pass)",
+                        "3xtf32": "hand-written sm_100a mma.sync 3xTF32 implicit GEMM", "cudnn": "cuDNN"}[conv],
             "l2": "no flush between steps: per-step working set (saved activations ~0.9 GB) exceeds the 126 MB L2; "
                   "kernel rooflines are measured separately with an L2 flush between launches"}
 
@@ -334,8 +336,9 @@ def main():
                     help="multi-GPU dual-BN statistics: fused NVLink peer-memory exchange inside the kernel, or NCCL all-reduce")
     ap.add_argument("--conv-math", default="fp32", choices=["fp32", "tf32"],
                     help="cuDNN/cuBLAS math of the (library) convolutions / fc: strict fp32 (headline) or TF32 tensor cores")
-    ap.add_argument("--conv", default="afan", choices=["afan", "cudnn"],
-                    help="3x3 tail convolutions: hand-written sm_100a FFMA kernels (default) or the cuDNN library path")
+    ap.add_argument("--conv", default="afan", choices=["afan", "cudnn", "3xtf32"],
+                    help="3x3 tail convolutions: hand-written sm_100a kernels (default; strict-fp32 FFMA, or the TF32 "
+                         "tensor-core twin under --conv-math tf32), the cuDNN library path, or the 3xTF32 split kernels")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-rooflines", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
@@ -363,7 +366,7 @@ def main():
     torch.backends.cudnn.benchmark = True
 
     pkg = importlib.import_module("cv_a-fan_b200")
-    pkg.conv.MODE = args.conv
+    pkg.conv.MODE = "tf32" if (args.conv == "afan" and args.conv_math == "tf32") else args.conv
     w = WORKLOAD
     torch.manual_seed(3)                                     # identical weights on every rank
     model = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)

@@ -18,8 +18,13 @@ import torch.nn as nn
 
 from . import ops
 
-# "afan" | "cudnn": module-level switch (env AFAN_CONV) used by the benchmarks to time the library path
+# Module-level switch (env AFAN_CONV), read at call time:
+#   "afan"   hand-written kernels, strict fp32 FFMA accumulation (default)
+#   "tf32"   hand-written tensor-core kernels, one TF32 pass (PyTorch's default conv math on Ampere+; opt-in here)
+#   "3xtf32" hand-written tensor-core kernels, hi/lo split (fp32-level accuracy; measured no faster than "afan")
+#   "cudnn"  the library convolution (benchmark comparisons)
 MODE = os.environ.get("AFAN_CONV", "afan")
+_MATH = {"afan": "fp32", "tf32": "tf32", "3xtf32": "3xtf32"}
 
 
 class _Conv3x3Fn(torch.autograd.Function):
@@ -28,14 +33,14 @@ class _Conv3x3Fn(torch.autograd.Function):
         x = x.contiguous()
         wf, wd = mod.packed()
         ctx.save_for_backward(x)
-        ctx.mod, ctx.wd = mod, wd
-        return ops.conv3x3(x, wf)
+        ctx.mod, ctx.wd, ctx.math = mod, wd, _MATH[MODE]
+        return ops.conv3x3(x, wf, math=ctx.math)
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = ops.conv3x3(dy, ctx.wd) if ctx.needs_input_grad[0] else None
+        dx = ops.conv3x3(dy, ctx.wd, math=ctx.math) if ctx.needs_input_grad[0] else None
         dw = None
         if ctx.needs_input_grad[1]:
             mod = ctx.mod
@@ -49,7 +54,7 @@ class _Conv3x3Fn(torch.autograd.Function):
 class Conv3x3(nn.Conv2d):
     def __init__(self, in_planes: int, planes: int, stride: int = 1):
         super().__init__(in_planes, planes, 3, stride, 1, bias=False)
-        self._packed = None            # float32 [2, C*9*C]: forward packing, dgrad packing
+        self._packed = None            # float32 [2, 2*C*9*C]: forward packing, dgrad packing (sized for the hi/lo split)
         self._packed_key = None        # (weight data_ptr, weight version) the packing was made from
         self._managed = False          # True while a trainer repacks all layers itself (pack_all)
         self.grad_direct = False       # trainer-owned gradient arena: wgrad adds straight into weight.grad
@@ -58,7 +63,7 @@ class Conv3x3(nn.Conv2d):
     def _buffers_for(self, device):
         if self._packed is None or self._packed.device != device:
             c = self.out_channels
-            self._packed = torch.empty((2, c * 9 * c), dtype=torch.float32, device=device)
+            self._packed = torch.empty((2, 2 * c * 9 * c), dtype=torch.float32, device=device)
             self._packed_key = None
         return self._packed
 
@@ -69,10 +74,10 @@ class Conv3x3(nn.Conv2d):
     def packed(self):
         p = self._buffers_for(self.weight.device)
         if not self._managed:
-            key = (self.weight.data_ptr(), self.weight._version)
+            key = (self.weight.data_ptr(), self.weight._version, MODE)
             if key != self._packed_key:
                 descs = torch.tensor([self.desc_row()], dtype=torch.int64, device=self.weight.device)
-                ops.conv3x3_pack(descs, self.out_channels)
+                ops.conv3x3_pack(descs, self.out_channels, _MATH[MODE])
                 self._packed_key = key
         return p[0], p[1]
 
@@ -82,7 +87,7 @@ class Conv3x3(nn.Conv2d):
         return self._ws
 
     def forward(self, x):
-        if MODE == "afan" and self.stride == (1, 1) and self.in_channels == self.out_channels \
+        if MODE in _MATH and self.stride == (1, 1) and self.in_channels == self.out_channels \
                 and ops.conv3x3_supported(x, self.weight):
             return _Conv3x3Fn.apply(x, self.weight, self)
         return super().forward(x)
@@ -100,14 +105,14 @@ class PackPlan:
             m._managed = True
 
     def pack(self):
-        if not self.mods or MODE != "afan":
+        if not self.mods or MODE not in _MATH:
             return
         ptrs = tuple(m.weight.data_ptr() for m in self.mods)
         if ptrs != self._ptrs:
             dev = self.mods[0].weight.device
             self._descs = torch.tensor([m.desc_row() for m in self.mods], dtype=torch.int64, device=dev)
             self._ptrs = ptrs
-        ops.conv3x3_pack(self._descs, max(m.out_channels for m in self.mods))
+        ops.conv3x3_pack(self._descs, max(m.out_channels for m in self.mods), _MATH[MODE])
 
     def release(self):
         for m in self.mods:

@@ -181,6 +181,199 @@ static int launch_conv(const float* x, const float* wp, float* y, int n, cudaStr
 }
 
 
+// ---- tensor-core forward / dgrad (mma.sync m16n8k8 TF32, fp32 accumulate) -----------------------------------------------
+// Same CTA tile and cp.async pipeline as the FFMA kernel, but the tile is staged channel-innermost -- in_s[pixel][8 ci],
+// w_s[tap][co][8 ci][hi, lo] -- so that one LDS.64 yields the (k, k+4) pair of an A fragment and one LDS.128 the B pair
+// with its TF32 split.  NPASS = 3 is the "3xTF32" scheme: x = x_hi + x_lo (x_hi = x rounded to TF32), products
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulated in fp32 recover fp32-level accuracy (the dropped a_lo*b_lo term is 2^-22
+// relative) on the tensor pipe; NPASS = 1 is plain TF32 (opt-in, PyTorch's default cuDNN conv math on Ampere+).
+// MMA k index <-> channel: k = tig <-> ci 2*tig, k = tig + 4 <-> ci 2*tig + 1 (any bijection works if A and B agree).
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// round-to-nearest (ties away) to TF32's 10-bit mantissa with integer ops; the remainder x - hi is exact in fp32
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+
+template <int C_, int HW_, int R_, int MT_, int NT_, int NPASS_>
+struct MmaCfg {
+    static constexpr int C = C_, H = HW_, W = HW_, R = R_, MT = MT_, NT = NT_, NPASS = NPASS_;
+    static constexpr int MTILES = R * W / 16, NTILES = C / 8;
+    static constexpr int MG = MTILES / MT, NG = NTILES / NT, WARPS = MG * NG, THREADS = WARPS * 32;
+    static constexpr int ROWS = R + 2, PW = W + 2;                 // tile incl. halo, in pixels
+    static constexpr int IN_ELEMS = ROWS * PW * 8;
+    static constexpr int WPK = NPASS == 3 ? 16 : 8;                // floats per (tap, co): [8 ci][hi, lo] or [8 ci]
+    static constexpr int W_ELEMS = 9 * C * WPK;
+    static constexpr int STAGE = IN_ELEMS + W_ELEMS;
+    static constexpr int SMEM_BYTES = 2 * STAGE * 4;
+    static constexpr int NCHUNK = C / 8;
+    static constexpr int TPI = H / R;
+    static_assert(MTILES % MT == 0 && NTILES % NT == 0 && THREADS <= 1024, "warp tiling");
+    static_assert(W == 8 ? R % 2 == 0 : W % 16 == 0, "an m-tile is 16 pixels of a row, or two rows of an 8-wide map");
+};
+
+template <class K>
+__global__ void __launch_bounds__(K::THREADS)
+conv3x3_mma_kernel(const float* __restrict__ x, const float* __restrict__ wm, float* __restrict__ y) {
+    constexpr int C = K::C, H = K::H, W = K::W, R = K::R, MT = K::MT, NT = K::NT, PW = K::PW;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int n = blockIdx.x / K::TPI, r0 = (blockIdx.x % K::TPI) * R;
+    const int mg = warp % K::MG, ng = warp / K::MG;
+
+    for (int i = tid; i < 2 * K::STAGE / 4; i += K::THREADS)
+        reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    auto load_chunk = [&](int chunk, int buf) {
+        float* in_s = smem + buf * K::STAGE;
+        float* w_s = in_s + K::IN_ELEMS;
+        const int ci0 = chunk * 8;
+        constexpr int NIN = 8 * K::ROWS * W;
+        for (int i = tid; i < NIN; i += K::THREADS) {
+            const int col = i % W, row = (i / W) % K::ROWS, c = i / (W * K::ROWS);
+            const int gr = r0 - 1 + row;
+            if (gr >= 0 && gr < H)
+                cp_async4(in_s + (row * PW + col + 1) * 8 + c, x + (static_cast<size_t>(n * C + ci0 + c) * H + gr) * W + col);
+        }
+        const float* wsrc = wm + static_cast<size_t>(chunk) * K::W_ELEMS;
+        for (int i = tid; i < K::W_ELEMS / 4; i += K::THREADS) cp_async16(w_s + 4 * i, wsrc + 4 * i);
+        cp_async_commit();
+    };
+
+    // pixel offsets (in floats) of the two row halves of each m-tile this warp owns, tap (0, 0)
+    int pa[MT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int mt = mg * MT + i;
+        int row0, col0, row1, col1;
+        if constexpr (W == 8) { row0 = 2 * mt; col0 = g; row1 = 2 * mt + 1; col1 = g; }
+        else { row0 = row1 = mt / (W / 16); col0 = (mt % (W / 16)) * 16 + g; col1 = col0 + 8; }
+        pa[i][0] = (row0 * PW + col0) * 8 + 2 * tig;
+        pa[i][1] = (row1 * PW + col1) * 8 + 2 * tig;
+    }
+
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+    load_chunk(0, 0);
+#pragma unroll 1
+    for (int ch = 0; ch < K::NCHUNK; ++ch) {
+        cp_async_wait_all();
+        __syncthreads();
+        if (ch + 1 < K::NCHUNK) load_chunk(ch + 1, (ch + 1) & 1);
+        const float* in_s = smem + (ch & 1) * K::STAGE;
+        const float* w_s = in_s + K::IN_ELEMS + (K::NPASS == 3 ? ((ng * NT) * 8 + g) * 16 + 4 * tig : ((ng * NT) * 8 + g) * 8 + 2 * tig);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int toff = ((t / 3) * PW + (t % 3)) * 8;
+            uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const float2 p0 = *reinterpret_cast<const float2*>(in_s + pa[i][0] + toff);   // (g,   k) , (g,   k+4)
+                const float2 p1 = *reinterpret_cast<const float2*>(in_s + pa[i][1] + toff);   // (g+8, k) , (g+8, k+4)
+                const float v[4] = {p0.x, p1.x, p0.y, p1.y};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ah[i][e] = tf32_hi(v[e]);
+                    if constexpr (K::NPASS == 3) al[i][e] = tf32_hi(v[e] - __uint_as_float(ah[i][e]));
+                }
+            }
+            uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                if constexpr (K::NPASS == 3) {
+                    const float4 b = *reinterpret_cast<const float4*>(w_s + (t * C + j * 8) * 16);   // hi(k), lo(k), hi(k+4), lo(k+4)
+                    bh[j][0] = __float_as_uint(b.x); bl[j][0] = __float_as_uint(b.y);
+                    bh[j][1] = __float_as_uint(b.z); bl[j][1] = __float_as_uint(b.w);
+                } else {
+                    const float2 b = *reinterpret_cast<const float2*>(w_s + (t * C + j * 8) * 8);    // hi(k), hi(k+4)
+                    bh[j][0] = __float_as_uint(b.x); bh[j][1] = __float_as_uint(b.y);
+                }
+            }
+            // the three passes of a tile are issued MT*NT MMAs apart, so consecutive MMAs never chain on one accumulator
+            if constexpr (K::NPASS == 3) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], al[i], bh[j][0], bh[j][1]);
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ah[i], bl[j][0], bl[j][1]);
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int i = 0; i < MT; ++i) mma_tf32(acc[i][j], ah[i], bh[j][0], bh[j][1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int mt = mg * MT + i;
+        int row0, col0, row1, col1;
+        if constexpr (W == 8) { row0 = 2 * mt; col0 = g; row1 = 2 * mt + 1; col1 = g; }
+        else { row0 = row1 = mt / (W / 16); col0 = (mt % (W / 16)) * 16 + g; col1 = col0 + 8; }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int co = (ng * NT + j) * 8 + 2 * tig;
+            float* y0 = y + (static_cast<size_t>(n * C + co) * H + r0) * W;
+            float* y1 = y0 + static_cast<size_t>(H) * W;
+            y0[row0 * W + col0] = acc[i][j][0];
+            y1[row0 * W + col0] = acc[i][j][1];
+            y0[row1 * W + col1] = acc[i][j][2];
+            y1[row1 * W + col1] = acc[i][j][3];
+        }
+    }
+}
+
+// W[co][ci][3][3] -> tensor-core packings [chunk = k / 8][tap][out][k % 8][hi, lo]: forward (k = ci, out = co, tap t) and
+// dgrad (k = co, out = ci, tap 8 - t).  hi = TF32 rounding of w, lo = TF32 rounding of (w - hi).
+__global__ void __launch_bounds__(kThreads) conv3x3_pack_mma_kernel(const ConvPackDesc* __restrict__ descs, int passes) {
+    const ConvPackDesc d = descs[blockIdx.y];
+    const int C = static_cast<int>(d.c), total = C * C * 9;
+    for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < total; idx += gridDim.x * kThreads) {
+        const int co = idx / (C * 9), ci = (idx / 9) % C, t = idx % 9;
+        const float v = d.w[idx];
+        const float hi = __uint_as_float(tf32_hi(v));
+        const float lo = __uint_as_float(tf32_hi(v - hi));
+        const int f = (((ci >> 3) * 9 + t) * C + co) * 8 + (ci & 7);
+        const int b = (((co >> 3) * 9 + (8 - t)) * C + ci) * 8 + (co & 7);
+        if (passes == 3) {
+            d.wf[2 * f] = hi; d.wf[2 * f + 1] = lo;
+            d.wd[2 * b] = hi; d.wd[2 * b + 1] = lo;
+        } else {
+            d.wf[f] = hi;
+            d.wd[b] = hi;
+        }
+    }
+}
+
+template <class K>
+static int launch_conv_mma(const float* x, const float* wm, float* y, int n, cudaStream_t st) {
+    static bool attr_set = false;      // benign race: idempotent
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv3x3_mma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            return AFAN_ERR_LAUNCH;
+        }
+        attr_set = true;
+    }
+    conv3x3_mma_kernel<K><<<static_cast<unsigned>(n * K::TPI), K::THREADS, K::SMEM_BYTES, st>>>(x, wm, y);
+    return launch_status();
+}
+
 // ---- wgrad ----------------------------------------------------------------------------------------------------
 // dW[co,ci,kh,kw] = sum over images and pixels of dy[n,co,h,w] * x[n,ci,h+kh-1,w+kw-1].  Persistent CTAs walk
 // "units" (an RB-row band of one image) through a 2-stage cp.async pipeline; a thread owns 4 output channels x 2
@@ -451,5 +644,44 @@ AFAN_EXPORT int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* d
     if (c == 64 && hw == 16) AFAN_WGRAD(64, 16, 2, 1, 2);
     if (c == 64 && hw == 8) AFAN_WGRAD(64, 8, 2, 1, 2);
 #undef AFAN_WGRAD
+    return AFAN_ERR_UNSUPPORTED;
+}
+
+/* Tensor-core twins.  Packed weights are 2*c*9*c floats per direction (hi/lo TF32 split). */
+AFAN_EXPORT int afan_conv3x3_pack_tc_f32(const void* descs_device, int64_t n_layers, int64_t c_max, int passes,
+                                         afan_stream_t stream) {
+    if (n_layers < 0 || c_max <= 0 || (passes != 1 && passes != 3)) return AFAN_ERR_SIZE;
+    if (n_layers == 0) return AFAN_OK;
+    if (!descs_device) return AFAN_ERR_NULL;
+    const long long total = c_max * c_max * 9;
+    const unsigned gx = static_cast<unsigned>((total + kThreads - 1) / kThreads);
+    conv3x3_pack_mma_kernel<<<dim3(gx < 16u ? gx : 16u, static_cast<unsigned>(n_layers)), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const ConvPackDesc*>(descs_device), passes);
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_conv3x3_tc_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
+                                    int passes, int variant, afan_stream_t stream) {
+    if (n < 0 || c <= 0 || hw <= 0 || (passes != 1 && passes != 3)) return AFAN_ERR_SIZE;
+    if (n == 0) return AFAN_OK;
+    if (!x || !w_packed || !y) return AFAN_ERR_NULL;
+    if (!aligned16(x) || !aligned16(w_packed) || !aligned16(y) || n * c * hw > (1ll << 30) / hw) return AFAN_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ni = static_cast<int>(n);
+#define AFAN_MMA(C, HW, R, MT, NT)                                                                   \
+    do {                                                                                             \
+        if (passes == 3) return launch_conv_mma<MmaCfg<C, HW, R, MT, NT, 3>>(x, w_packed, y, ni, st); \
+        return launch_conv_mma<MmaCfg<C, HW, R, MT, NT, 1>>(x, w_packed, y, ni, st);                  \
+    } while (0)
+    if (c == 16 && hw == 32) { if (variant == 1) AFAN_MMA(16, 32, 8, 2, 2); AFAN_MMA(16, 32, 16, 4, 2); }
+    if (c == 32 && hw == 16) { if (variant == 1) AFAN_MMA(32, 16, 16, 4, 4); AFAN_MMA(32, 16, 16, 2, 4); }
+    if (c == 64 && hw == 8) { if (variant == 1) AFAN_MMA(64, 8, 8, 4, 2); AFAN_MMA(64, 8, 8, 2, 2); }
+    if (c == 16 && hw == 16) AFAN_MMA(16, 16, 16, 2, 2);
+    if (c == 16 && hw == 8) AFAN_MMA(16, 8, 8, 2, 2);
+    if (c == 32 && hw == 32) AFAN_MMA(32, 32, 16, 4, 4);
+    if (c == 32 && hw == 8) AFAN_MMA(32, 8, 8, 2, 2);
+    if (c == 64 && hw == 16) AFAN_MMA(64, 16, 16, 2, 4);
+    if (c == 64 && hw == 32) AFAN_MMA(64, 32, 16, 4, 4);
+#undef AFAN_MMA
     return AFAN_ERR_UNSUPPORTED;
 }

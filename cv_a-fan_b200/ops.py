@@ -311,19 +311,32 @@ def conv3x3_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
             and tuple(weight.shape[2:]) == (3, 3))
 
 
-def conv3x3_pack(descs: torch.Tensor, c_max: int):
-    """Repack every layer listed in `descs` (int64 [L, 4] = weight ptr, fwd-packed ptr, dgrad-packed ptr, C) in ONE launch."""
-    check(_lib.lib().afan_conv3x3_pack_f32(_lib.dev_ptr(descs, torch.int64, "descs"), descs.shape[0], int(c_max), stream()),
-          "afan_conv3x3_pack_f32")
+def conv3x3_pack(descs: torch.Tensor, c_max: int, math: str = "fp32"):
+    """Repack every layer listed in `descs` (int64 [L, 4] = weight ptr, fwd-packed ptr, dgrad-packed ptr, C) in ONE launch.
+    math: "fp32" (FFMA kernels, C*9*C floats per packing), "tf32" (tensor cores, 1 pass, C*9*C floats) or
+    "3xtf32" (tensor cores, hi/lo split, 2*C*9*C floats)."""
+    d = _lib.dev_ptr(descs, torch.int64, "descs")
+    if math == "fp32":
+        check(_lib.lib().afan_conv3x3_pack_f32(d, descs.shape[0], int(c_max), stream()), "afan_conv3x3_pack_f32")
+    else:
+        check(_lib.lib().afan_conv3x3_pack_tc_f32(d, descs.shape[0], int(c_max), _TC_PASSES[math], stream()),
+              "afan_conv3x3_pack_tc_f32")
 
 
-def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0) -> torch.Tensor:
-    """y = conv2d(x, W, stride 1, pad 1) with W packed as [reduction channel][tap][output channel] (forward packing), or
-    the input gradient of that convolution when given dy and the dgrad packing."""
+_TC_PASSES = {"tf32": 1, "3xtf32": 3}
+
+
+def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0, math: str = "fp32") -> torch.Tensor:
+    """y = conv2d(x, W, stride 1, pad 1) with W packed by conv3x3_pack (forward packing), or the input gradient of that
+    convolution when given dy and the dgrad packing.  `math` must match the packing."""
     n, c, h, _ = x.shape
     y = torch.empty_like(x)
-    check(_lib.lib().afan_conv3x3_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), n, c, h, int(variant), stream()),
-          "afan_conv3x3_f32")
+    if math == "fp32":
+        check(_lib.lib().afan_conv3x3_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), n, c, h, int(variant), stream()),
+              "afan_conv3x3_f32")
+    else:
+        check(_lib.lib().afan_conv3x3_tc_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), n, c, h, _TC_PASSES[math],
+                                             int(variant), stream()), "afan_conv3x3_tc_f32")
     return y
 
 

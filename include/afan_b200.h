@@ -241,6 +241,13 @@ int afan_roi_align_bwd_f32(const float* dout, const float* rois, float* dfeat, i
 int afan_conv3x3_pack_f32(const void* descs_device, int64_t n_layers, int64_t c_max, afan_stream_t stream);
 int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
                      int variant, afan_stream_t stream);
+/* Tensor-core twins of the two calls above (mma.sync m16n8k8 TF32, fp32 accumulate).  passes = 3: "3xTF32" split
+ * (x = hi + lo; a_lo*b_hi + a_hi*b_lo + a_hi*b_hi) -- fp32-level accuracy on the tensor pipe; passes = 1: plain TF32.
+ * The packings are [k/8][tap][out][k%8][hi, lo] (passes = 3: 2*c*9*c floats per direction) or [k/8][tap][out][k%8]
+ * (passes = 1: c*9*c floats), hi = W rounded to TF32, lo = TF32 rounding of (W - hi). */
+int afan_conv3x3_pack_tc_f32(const void* descs_device, int64_t n_layers, int64_t c_max, int passes, afan_stream_t stream);
+int afan_conv3x3_tc_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
+                        int passes, int variant, afan_stream_t stream);
 int64_t afan_conv3x3_wgrad_workspace_bytes(int64_t c);
 int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
                            int64_t n, int64_t c, int64_t hw, int accumulate, afan_stream_t stream);

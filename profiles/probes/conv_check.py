@@ -72,6 +72,19 @@ for (n, c, h) in ((128, 16, 32), (128, 32, 16), (128, 64, 8), (256, 32, 16), (25
         if n >= 128:
             res[key][f"v{v}_us"] = round(graph_time(lambda: conv(x, wf, y, v)), 2)
     L = _lib.lib()
+    wtf, wtd = torch.empty(2 * c * 9 * c, device=dev), torch.empty(2 * c * 9 * c, device=dev)
+    desc = torch.tensor([[w.data_ptr(), wtf.data_ptr(), wtd.data_ptr(), c]], dtype=torch.int64, device=dev)
+    def tc(inp, wp, out, passes, variant):
+        _lib.check(L.afan_conv3x3_tc_f32(inp.data_ptr(), wp.data_ptr(), out.data_ptr(), n, c, h, passes, variant, _lib.stream()), "tc")
+    for passes in (3, 1):
+        _lib.check(L.afan_conv3x3_pack_tc_f32(desc.data_ptr(), 1, c, passes, _lib.stream()), "pack_tc")
+        for v in range(2 if n >= 128 else 1):
+            yt, dxt = torch.empty_like(x), torch.empty_like(x)
+            tc(x, wtf, yt, passes, v); tc(dy, wtd, dxt, passes, v)
+            res[key][f"tc{passes}_v{v}_fwd_err"] = (yt - ref).abs().max().item()
+            res[key][f"tc{passes}_v{v}_dgrad_err"] = (dxt - ref_dx).abs().max().item()
+            if n >= 128:
+                res[key][f"tc{passes}_v{v}_us"] = round(graph_time(lambda: tc(x, wtf, yt, passes, v)), 2)
     wsb = L.afan_conv3x3_wgrad_workspace_bytes(c)
     ws = torch.empty(wsb // 4, device=dev)
     dw = torch.empty_like(w)

@@ -70,3 +70,24 @@ def test_unsupported_shapes_use_the_library_convolution():
     x2 = torch.randn(2, 16, 12, 12, device=dev)              # 12x12 is not a covered map size
     assert torch.allclose(m2(x2), F.conv2d(x2, m2.weight, padding=1))
     assert ops.conv3x3_supported(torch.randn(2, 16, 16, 16, device=dev), m2.weight)
+
+
+@pytest.mark.parametrize("mode,tol", [("3xtf32", 6e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("n,c,h", [(16, 16, 32), (16, 32, 16), (16, 64, 8), (3, 64, 32), (5, 32, 8), (2, 16, 8)])
+def test_tensor_core_twins_vs_fp64(mode, tol, n, c, h, monkeypatch):
+    """mma.sync TF32 kernels: 3xTF32 split within ~1e-5 of fp64 (cuDNN's fp32 algorithms: 1e-5 .. 5e-5), one-pass TF32
+    within TF32's 2^-11 input rounding (opt-in mode)."""
+    monkeypatch.setattr(conv, "MODE", mode)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(n + c + h)
+    x = torch.randn(n, c, h, h, generator=g).to(dev).requires_grad_(True)
+    dy = torch.randn(n, c, h, h, generator=g).to(dev)
+    m = conv.Conv3x3(c, c, 1).to(dev)
+    y = m(x)
+    dx, dw = torch.autograd.grad(y, (x, m.weight), dy)
+    w = m.weight.detach()
+    ref = F.conv2d(x.detach().double(), w.double(), padding=1)
+    ref_dx = torch.nn.grad.conv2d_input(x.shape, w.double(), dy.double(), padding=1)
+    ref_dw = torch.nn.grad.conv2d_weight(x.detach().double(), w.shape, dy.double(), padding=1)
+    assert _rel(y, ref) < tol and _rel(dx, ref_dx) < tol
+    assert _rel(dw, ref_dw) < 2e-5                       # the weight gradient stays on the strict-fp32 kernel
