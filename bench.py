@@ -15,6 +15,7 @@ Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = the sa
 public API with pinned HOST inputs (H2D of images/labels and D2H of the loss inside the timed region).
 """
 import argparse
+import ctypes
 import importlib
 import json
 import os
@@ -171,7 +172,20 @@ def kernel_rooflines(pkg, dev, reps=10):
     side = torch.cuda.Stream(device=dev)
     res = []
 
-    def measure(name, bytes_per_launch, footprint, make_set, run, launches_per_iter, note):
+    # fp32 FFMA peak of this device at its current clocks (roofline denominator of the direct convolutions)
+    probe_out = torch.empty(2 * 148 * 256 * 2, dtype=torch.float32, device=dev)
+    fl = ctypes.c_double(0.0)
+    for _ in range(2):
+        pkg._lib.check(L.afan_ffma_probe(probe_out.data_ptr(), probe_out.numel(), 20000, ctypes.byref(fl), st()), "afan_ffma_probe")
+    torch.cuda.synchronize()
+    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    pkg._lib.check(L.afan_ffma_probe(probe_out.data_ptr(), probe_out.numel(), 20000, ctypes.byref(fl), st()), "afan_ffma_probe")
+    e0.record()
+    e0.synchronize()
+    ffma_peak = fl.value / (s0.elapsed_time(e0) * 1e-3) / 1e12
+
+    def measure(name, bytes_per_launch, footprint, make_set, run, launches_per_iter, note, flops=None):
         R = max(2, min(64, -(-4 * L2_BYTES // footprint)))
         sets = [make_set() for _ in range(R)]
         side.wait_stream(torch.cuda.current_stream())
@@ -203,11 +217,16 @@ def kernel_rooflines(pkg, dev, reps=10):
             e2.synchronize()
             if i >= 3:
                 iso.append(s2.elapsed_time(e2) * 1e-3)
-        res.append({"kernel": name, "family": name.split(" [")[0].split("+")[0].split(" clip")[0].split(" noclip")[0].strip(),
-                    "bytes": bytes_per_launch, "us": t * 1e6, "us_isolated": 1e6 * sum(iso) / len(iso),
-                    "achieved": bytes_per_launch / t / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": bytes_per_launch / t / 1e9 / peak, "rotating_sets": R,
-                    "launches_per_iter": launches_per_iter, "note": note})
+        row = {"kernel": name, "family": name.split(" [")[0].split("+")[0].split(" clip")[0].split(" noclip")[0].strip(),
+               "bytes": bytes_per_launch, "us": t * 1e6, "us_isolated": 1e6 * sum(iso) / len(iso),
+               "rotating_sets": R, "launches_per_iter": launches_per_iter, "note": note}
+        if flops is None:
+            row.update({"bound": "hbm", "achieved": bytes_per_launch / t / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": bytes_per_launch / t / 1e9 / peak})
+        else:
+            row.update({"bound": "fp32_ffma", "flops": flops, "achieved": flops / t / 1e12, "peak": ffma_peak, "unit": "TFLOP/s",
+                        "frac": flops / t / 1e12 / ffma_peak, "hbm_gbs": bytes_per_launch / t / 1e9})
+        res.append(row)
         del graph, sets
 
     w = WORKLOAD
@@ -269,6 +288,27 @@ def kernel_rooflines(pkg, dev, reps=10):
                 "read x + write y = 8 B/elem (16 B per clean+adv pair)")
         measure(f"dual_bn bwd+relu [{tag}]", 16 * E, 16 * E, mk_bwd, bwd, lpi,
                 "read dy,x,y + write dx = 16 B/elem (12 without the ReLU mask)")
+    # 3x3 convolutions of the step (ResNet-56, perturb_idx 13): stage-1 head at batch n, tail stages 2/3 at batch n in the
+    # ascent (forward + dgrad per PGD step) and at 2n in the final [adv; clean] pass
+    steps = w["steps"]
+    for (N, C, H), lpi_conv, lpi_wgrad in (((n, 16, 32), 36, 18), ((n, 32, 16), 34 * steps, 0), ((n, 64, 8), 34 * steps, 0),
+                                           ((2 * n, 32, 16), 34, 17), ((2 * n, 64, 8), 34, 17)):
+        E = N * C * H * H
+        fl_conv = 2.0 * E * C * 9
+
+        def mk():
+            m = pkg.conv.Conv3x3(C, C, 1).to(dev)
+            wf, wd = m.packed()
+            return dict(x=torch.randn(N, C, H, H, device=dev, generator=g), dy=torch.randn(N, C, H, H, device=dev, generator=g),
+                        wf=wf, m=m, ws=m.wgrad_workspace())
+        math = {"afan": "fp32", "tf32": "tf32", "3xtf32": "3xtf32"}.get(pkg.conv.MODE, "fp32")
+        measure(f"conv3x3 fwd/dgrad [{N}x{C}x{H}x{H}]", 8 * E + 4 * 9 * C * C, 8 * E, mk,
+                lambda t: ops.conv3x3(t["x"], t["wf"], math=math), lpi_conv,
+                "3x3 s1 p1 conv, forward and (other weight packing) input gradient: 18*C FLOP per output element; "
+                "read x + write y = 8 B/elem", flops=fl_conv)
+        measure(f"conv3x3 wgrad [{N}x{C}x{H}x{H}]", 8 * E + 4 * 9 * C * C, 8 * E, mk,
+                lambda t: ops.conv3x3_wgrad(t["x"], t["dy"], t["ws"]), lpi_wgrad,
+                "weight gradient (partials kernel + fixed-order fold kernel, both in the time)", flops=fl_conv)
     for tag, shape in (("cfg5 4x2048x33x33", (4, 2048, 33, 33)), ("cfg4 8x1024x38x63", (8, 1024, 38, 63)),
                        ("4x256x128x128", (4, 256, 128, 128))):
         E = 1
@@ -280,7 +320,7 @@ def kernel_rooflines(pkg, dev, reps=10):
             return dict(cl=cl, ad=cl + 0.01 * torch.randn(shape, device=dev, generator=g), out=torch.empty_like(cl))
         measure(f"mix_feature [{tag}]", 12 * E, 12 * E, mk, lambda t: ops.mix_feature(t["cl"], t["ad"], out=t["out"]), 0,
                 "read clean, adv + write out = 12 B/elem (Seg/Det normalisation; not in the Classification step)")
-    return res, peak_src
+    return res, peak_src, ffma_peak
 
 
 def exchange_microbench(pkg, dev, mailbox, pg, calls=100):
@@ -451,7 +491,7 @@ def main():
             "bn_exchange": args.bn_exchange if ((not args.no_sync_bn) and world > 1) else None, "final_loss": loss_dev}
 
     if rank == 0 and not args.skip_rooflines:
-        ks, peak_src = kernel_rooflines(pkg, dev)
+        ks, peak_src, ffma_peak = kernel_rooflines(pkg, dev)
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tmap = json.load(f)
@@ -459,13 +499,16 @@ def main():
             tmap = {}
         for k in ks:
             k["traffic"] = tmap.get(k["kernel"])
-        # the dominant hand-written kernel of the step = the kernel FAMILY (all its in-step shapes) with the largest
-        # share of the step; achieved = its algorithmic bytes per step / its device time per step
+        # Roofline per kernel FAMILY (all in-step shapes of a kernel, weighted by their launches in one step):
+        # achieved = algorithmic bytes (HBM-bound families) or FLOPs (the FFMA-bound convolutions) per step / device time
+        # per step.  `roofline` = the family with the largest share of the step; `roofline_hbm` = the largest HBM-bound one.
         step_us = 1e3 * sec / args.steps * 1e3
         fam = {}
         for k in ks:
             if k["launches_per_iter"] > 0:
-                f = fam.setdefault(k["family"], {"bytes": 0.0, "us": 0.0, "launches": 0, "traffic": 0.0, "traffic_ok": True, "shapes": []})
+                f = fam.setdefault(k["family"], {"bound": k["bound"], "peak": k["peak"], "unit": k["unit"], "work": 0.0, "bytes": 0.0,
+                                                 "us": 0.0, "launches": 0, "traffic": 0.0, "traffic_ok": True, "shapes": []})
+                f["work"] += (k["flops"] if k["bound"] == "fp32_ffma" else k["bytes"]) * k["launches_per_iter"]
                 f["bytes"] += k["bytes"] * k["launches_per_iter"]
                 f["us"] += k["us"] * k["launches_per_iter"]
                 f["launches"] += k["launches_per_iter"]
@@ -474,19 +517,35 @@ def main():
                     f["traffic_ok"] = False
                 else:
                     f["traffic"] += k["traffic"] * k["launches_per_iter"]
+
+        def fam_line(name, f):
+            scale = 1e12 if f["bound"] == "fp32_ffma" else 1e9
+            achieved = f["work"] / (f["us"] * 1e-6) / scale
+            d = {"bound": f["bound"], "kernel": name, "achieved": achieved, "peak": f["peak"], "unit": f["unit"],
+                 "frac": achieved / f["peak"], "traffic": f["traffic"] / f["launches"] if f["traffic_ok"] else None,
+                 "algorithmic_bytes": f["bytes"] / f["launches"], "launches_per_step": f["launches"],
+                 "avg_us_per_launch": f["us"] / f["launches"], "share_of_step": f["us"] / step_us, "shapes": f["shapes"]}
+            if f["bound"] == "fp32_ffma":
+                d["algorithmic_flops"] = f["work"] / f["launches"]
+                d["peak_source"] = ("fp32 FFMA rate measured live by afan_ffma_probe (8x8 outer-product loop, 2 CTAs x 256 "
+                                    "threads per SM) on this device at its current clocks; nominal 148 SMs x 128 lanes x 2 x "
+                                    "1.965 GHz = 74.4 TFLOP/s")
+            else:
+                d["peak_source"] = peak_src
+            return d
+        timing = ("per shape: CUDA events around a graph of back-to-back launches over rotating tensor sets (4x L2, every launch "
+                  "L2-cold), weighted by the launches of that shape in one step; traffic / algorithmic_bytes are per-launch averages")
         dom_name, dom = max(fam.items(), key=lambda kv: kv[1]["us"])
-        achieved = dom["bytes"] / (dom["us"] * 1e-6) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": ks[0]["peak"], "unit": "GB/s",
-                            "frac": achieved / ks[0]["peak"], "traffic": dom["traffic"] / dom["launches"] if dom["traffic_ok"] else None,
-                            "algorithmic_bytes": dom["bytes"] / dom["launches"], "launches_per_step": dom["launches"],
-                            "avg_us_per_launch": dom["us"] / dom["launches"], "share_of_step": dom["us"] / step_us,
-                            "shapes": dom["shapes"], "peak_source": peak_src,
-                            "timing": "per shape: CUDA events around a graph of back-to-back launches over rotating tensor sets "
-                                      "(4x L2, every launch L2-cold), weighted by the launches of that shape in one step; "
-                                      "traffic / algorithmic_bytes are per-launch averages",
-                            "families": {n: {"share_of_step": f["us"] / step_us, "launches_per_step": f["launches"],
-                                             "achieved": f["bytes"] / (f["us"] * 1e-6) / 1e9,
-                                             "frac": f["bytes"] / (f["us"] * 1e-6) / 1e9 / ks[0]["peak"]} for n, f in fam.items()}}
+        line["roofline"] = fam_line(dom_name, dom)
+        line["roofline"]["timing"] = timing
+        line["roofline"]["families"] = {n: {k2: v for k2, v in fam_line(n, f).items()
+                                            if k2 in ("bound", "achieved", "peak", "unit", "frac", "share_of_step", "launches_per_step")}
+                                        for n, f in fam.items()}
+        hbm = {n: f for n, f in fam.items() if f["bound"] == "hbm"}
+        if hbm and dom["bound"] != "hbm":
+            hn, hf = max(hbm.items(), key=lambda kv: kv[1]["us"])
+            line["roofline_hbm"] = fam_line(hn, hf)
+        line["ffma_peak_tflops_measured"] = ffma_peak
         line["kernels"] = ks
     if world > 1:
         torch.distributed.barrier()

@@ -32,9 +32,47 @@ sgd_momentum_kernel(float* __restrict__ param, const float* __restrict__ grad, f
     }
 }
 
+// FFMA pipe probe: 64 independent accumulators per thread, 8x8 outer-product updates (the inner-loop shape of the direct
+// convolutions).  bench.py times it to obtain the fp32 FFMA peak of THIS device at its current clocks, the roofline
+// denominator of the convolution kernels.
+__global__ void __launch_bounds__(kThreads) ffma_probe_kernel(float* __restrict__ out, int iters) {
+    float acc[8][8], a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 1.0f + 1e-3f * (threadIdx.x + i); b[i] = 1.0f - 1e-3f * (threadIdx.x + 2 * i); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] += 1e-9f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
+    out[blockIdx.x * kThreads + threadIdx.x] = s;
+}
+
 }  // namespace afan
 
 using namespace afan;
+
+// Launches the probe on 2 CTAs per SM; `out` holds 2 * sm_count * 256 floats.  Returns the FLOP count of the launch
+// (2 * 64 * iters per thread) through *flops_out so the caller can divide by its own CUDA-event time.
+AFAN_EXPORT int afan_ffma_probe(float* out, int64_t out_elems, int64_t iters, double* flops_out, afan_stream_t stream) {
+    if (!out || !flops_out) return AFAN_ERR_NULL;
+    const int grid = 2 * sm_count();
+    if (iters <= 0 || out_elems < static_cast<int64_t>(grid) * kThreads) return AFAN_ERR_SIZE;
+    ffma_probe_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(out, static_cast<int>(iters));
+    *flops_out = 2.0 * 64.0 * static_cast<double>(iters) * kThreads * grid;
+    return launch_status();
+}
 
 AFAN_EXPORT const char* afan_version(void) { return "afan_b200 0.1.0 (sm_100a)"; }
 

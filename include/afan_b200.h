@@ -42,6 +42,10 @@ const char* afan_version(void);
 const char* afan_strerror(int code);
 /* Fills SM count and compute capability of the current device; AFAN_ERR_UNSUPPORTED if not sm_100. */
 int afan_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Measurement aid: launches an FFMA-only kernel (64 independent accumulators per thread, 2 CTAs x 256 threads per SM,
+ * `iters` 8x8 outer-product updates) and returns its FLOP count in *flops_out (host pointer); the caller times it with
+ * CUDA events to get the fp32 FFMA peak of the device at its current clocks.  out: >= 2 * sm_count * 256 floats. */
+int afan_ffma_probe(float* out, int64_t out_elems, int64_t iters, double* flops_out, afan_stream_t stream);
 
 /* ---- a2: random start ------------------------------------------------------------------------
  * Replaces Classification/attack_algo.py:41-44 (== Segmentation/attack_algo.py:43-45,
