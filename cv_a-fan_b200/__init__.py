@@ -14,6 +14,6 @@ Public surface (mirrors the reference's Python interface for this path):
 """
 from . import _lib, ops  # noqa: F401
 from ._lib import AfanError, version  # noqa: F401
-from . import attack_algo, conv, detection, dual_bn, main_perturb, p2p, resnet_s, segmentation, sync, trainer, trainer_learnable  # noqa: F401,E402
+from . import attack_algo, conv, deeplab, detection, dual_bn, main_perturb, p2p, resnet_s, segmentation, sync, trainer, trainer_learnable, trainer_seg  # noqa: F401,E402
 
 __all__ = ["ops", "attack_algo", "segmentation", "detection", "dual_bn", "resnet_s", "trainer", "AfanError", "version"]

@@ -121,3 +121,14 @@ def test_two_rank_gloo_protocol_reproduces_global_batch_statistics(tmp_path):
     _, sm, si = orc.bn_fwd(x, np.ones(6, np.float32), np.zeros(6, np.float32), rm, rv, groups=2)    # single process, global batch
     np.testing.assert_allclose(r0["mean"].numpy(), sm, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(r0["invstd"].numpy(), si, rtol=1e-6)
+
+
+def test_seg_golden_matches_the_product_model_layout():
+    """tests/golden/seg_step.npz (reference execution) lists exactly the state-dict keys of cv_a-fan_b200.deeplab."""
+    import numpy as np
+    from oracle import seg_ref_step as ref
+    g = np.load(ref.GOLDEN, allow_pickle=False)
+    model = PKG.deeplab.deeplabv3plus_resnet50(num_classes=ref.NUM_CLASSES, output_stride=16)
+    assert [str(k) for k in g["keys"]] == list(model.state_dict().keys())
+    for name in ref.CASES:
+        assert np.isfinite(g[f"{name}/losses"]).all() and g[f"{name}/losses"].shape == (ref.ITERS, 5)

@@ -48,3 +48,35 @@ def test_mix_and_l2_oracle_vs_live_reference():
     t = cl + 0.1 * torch.randn(cl.shape, generator=gen)
     ref = cls.l2ball_proj(cl, 0.5, t.clone()).numpy()
     np.testing.assert_allclose(orc.l2ball_proj(cl.numpy(), 0.5, t.numpy()), ref, rtol=1e-6, atol=1e-7)
+
+
+def test_seg_iteration_restatement_equals_reference():
+    """oracle/seg_ref_step.TorchAttackAlgo + cv_a-fan_b200.deeplab on the CPU reproduce the golden losses that the
+    UNMODIFIED reference model + attack_algo produced (tests/golden/seg_step.npz): pins the on-device checker of
+    tests/test_gpu_seg.py and the product model in one go."""
+    import importlib
+    import numpy as np
+    from oracle import seg_ref_step as ref
+    pkg = importlib.import_module("cv_a-fan_b200")
+    g = np.load(ref.GOLDEN, allow_pickle=False)
+    for name, c in ref.CASES.items():
+        model = pkg.deeplab.deeplabv3plus_resnet50(num_classes=ref.NUM_CLASSES, output_stride=16)
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        ref.procedural_init(model, seed=7).train()
+        images, labels = ref.make_batches(seed=21)
+        opt = torch.optim.SGD(params=[{"params": model.backbone.parameters(), "lr": 0.1 * ref.LR},
+                                      {"params": model.classifier.parameters(), "lr": ref.LR}],
+                              lr=ref.LR, momentum=0.9, weight_decay=ref.WD)
+        crit = torch.nn.CrossEntropyLoss(ignore_index=255, reduction="mean")
+        it = 0                                            # one iteration is enough to pin every branch; keeps the CPU suite short
+        draws = []
+        if c["randinit"]:
+            draws += [torch.from_numpy(g[f"{name}/noise_se{it}"]), torch.from_numpy(g[f"{name}/noise_sd{it}"])]
+        if c["noise_sd"] != 0:
+            draws.append(torch.from_numpy(g[f"{name}/noise_n{it}"]))
+        q = iter(draws)
+        rand = lambda shape: next(q)
+        losses = ref.reference_iteration(model, ref.TorchAttackAlgo(rand), images[it], labels[it], c, crit, opt, rand=rand)
+        np.testing.assert_allclose(losses, g[f"{name}/losses"][it], rtol=1e-6)
