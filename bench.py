@@ -380,6 +380,7 @@ def main():
                     help="3x3 tail convolutions: hand-written sm_100a kernels (default; strict-fp32 FFMA, or the TF32 "
                          "tensor-core twin under --conv-math tf32), the cuDNN library path, or the 3xTF32 split kernels")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-variants", action="store_true", help="do not time the TF32 / cuDNN convolution variants of the step")
     ap.add_argument("--skip-rooflines", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager iteration between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
@@ -489,6 +490,27 @@ def main():
             "gpu_launches": per_iter * args.steps, "afan_kernels_per_step": per_iter,
             "cuda_graph": not args.no_graph, "sync_bn": (not args.no_sync_bn) and world > 1,
             "bn_exchange": args.bn_exchange if ((not args.no_sync_bn) and world > 1) else None, "final_loss": loss_dev}
+
+    # other convolution paths of the SAME step, for context only (never the headline): single GPU, device-resident inputs
+    if world == 1 and not args.skip_variants and args.conv == "afan" and args.conv_math == "fp32" and not args.no_graph:
+        variants = {}
+        for vname, mode, tf32 in (("conv_tf32_tensor_core_kernels", "tf32", True), ("conv_cudnn_fp32", "cudnn", False)):
+            pkg.conv.MODE = mode
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.manual_seed(3)
+            vm = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)
+            vt = pkg.trainer.AfanTrainer(vm, perturb_idx=w["perturb_idx"], steps=w["steps"], gamma=w["gamma"], eps=w["eps"],
+                                         randinit=w["randinit"], clip=w["clip"], rng="philox", seed=3, use_cuda_graph=True)
+            vt.step(dev_x[0], dev_y[0])
+            vsec, _ = timed_run(lambda i: vt.step(dev_x[i % 4], dev_y[i % 4]))
+            variants[vname] = {"value": n * args.steps / vsec, "unit": "img/s", "ms_per_step": 1e3 * vsec / args.steps}
+            vt.close()
+            del vm, vt
+        pkg.conv.MODE = "afan"
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        line["variants"] = variants
 
     if rank == 0 and not args.skip_rooflines:
         ks, peak_src, ffma_peak = kernel_rooflines(pkg, dev)
