@@ -57,9 +57,9 @@ SIGNATURES = {
     "afan_bn_affine_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "afan_sgd_momentum_f32": (_int, [_vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp]),
     "afan_conv3x3_pack_f32": (_int, [_vp, _i64, _i64, _vp]),
-    "afan_conv3x3_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "afan_conv3x3_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "afan_conv3x3_pack_tc_f32": (_int, [_vp, _i64, _i64, _int, _vp]),
-    "afan_conv3x3_tc_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
+    "afan_conv3x3_tc_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
     "afan_conv3x3_wgrad_workspace_bytes": (_i64, [_i64]),
     "afan_conv3x3_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
 }

@@ -51,6 +51,36 @@ class _Conv3x3Fn(torch.autograd.Function):
         return dx, dw, None
 
 
+class _Conv3x3TapFn(torch.autograd.Function):
+    """(conv(x), x) -- the second output is x itself, handed to the block's identity shortcut (resnet_s.py:75).  Both
+    gradients meet in ONE backward call, so the shortcut's gradient is added in the dgrad kernel's epilogue instead of
+    by an autograd accumulation launch."""
+
+    @staticmethod
+    def forward(ctx, x, weight, mod):
+        x = x.contiguous()
+        wf, wd = mod.packed()
+        ctx.save_for_backward(x)
+        ctx.mod, ctx.wd, ctx.math = mod, wd, _MATH[MODE]
+        return ops.conv3x3(x, wf, math=ctx.math), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dtap):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv3x3(dy, ctx.wd, math=ctx.math, addend=dtap.contiguous() if dtap is not None else None)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            mod = ctx.mod
+            if mod.grad_direct and mod.weight.grad is not None:
+                ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)
+            else:
+                dw = ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace())
+        return dx, dw, None
+
+
 class Conv3x3(nn.Conv2d):
     def __init__(self, in_planes: int, planes: int, stride: int = 1):
         super().__init__(in_planes, planes, 3, stride, 1, bias=False)
@@ -85,6 +115,16 @@ class Conv3x3(nn.Conv2d):
         if self._ws is None or self._ws.device != self.weight.device:
             self._ws = ops.conv3x3_wgrad_workspace(self.out_channels, self.weight.device)
         return self._ws
+
+    def hand_written(self, x) -> bool:
+        return (MODE in _MATH and self.stride == (1, 1) and self.in_channels == self.out_channels
+                and ops.conv3x3_supported(x, self.weight))
+
+    def forward_with_tap(self, x):
+        """(conv(x), x') where x' aliases x for the identity shortcut; see _Conv3x3TapFn."""
+        if self.hand_written(x) and torch.is_grad_enabled() and x.requires_grad:
+            return _Conv3x3TapFn.apply(x, self.weight, self)
+        return self.forward(x), x
 
     def forward(self, x):
         if MODE in _MATH and self.stride == (1, 1) and self.in_channels == self.out_channels \

@@ -53,7 +53,7 @@ struct ConvCfg {
 
 template <class K>
 __global__ void __launch_bounds__(K::THREADS)
-conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y) {
+conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wp, float* __restrict__ y, const float* __restrict__ addend) {
     constexpr int C = K::C, H = K::H, W = K::W, R = K::R, TQ = K::TQ, CK = K::CK, S = K::S;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,8 +140,13 @@ conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wp, float*
     for (int q = 0; q < TQ; ++q)
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            float* dst = y + (static_cast<size_t>(n * C + cg * TQ + q) * H + r0 + 2 * pby + r) * W + 4 * pbx;
-            *reinterpret_cast<float4*>(dst) = make_float4(acc[q][r][0], acc[q][r][1], acc[q][r][2], acc[q][r][3]);
+            const size_t off = (static_cast<size_t>(n * C + cg * TQ + q) * H + r0 + 2 * pby + r) * W + 4 * pbx;
+            float4 o = make_float4(acc[q][r][0], acc[q][r][1], acc[q][r][2], acc[q][r][3]);
+            if (addend != nullptr) {       // y = conv(x) + addend: the residual branch's gradient joins the dgrad here
+                const float4 a = *reinterpret_cast<const float4*>(addend + off);
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            *reinterpret_cast<float4*>(y + off) = o;
         }
 }
 
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) conv3x3_pack_kernel(const ConvPackDe
 }
 
 template <class K>
-static int launch_conv(const float* x, const float* wp, float* y, int n, cudaStream_t st) {
+static int launch_conv(const float* x, const float* wp, float* y, const float* addend, int n, cudaStream_t st) {
     static bool attr_set = false;      // benign race: idempotent
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv3x3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES) != cudaSuccess) {
@@ -176,7 +181,7 @@ static int launch_conv(const float* x, const float* wp, float* y, int n, cudaStr
     }
     // plain launches: with the PDL attribute the early-scheduled CTAs of these shared-memory-heavy kernels serialise
     // against their neighbours inside the captured step (measured: 27.4 ms/step with, 15.8 ms without)
-    conv3x3_kernel<K><<<static_cast<unsigned>(n * K::TPI), K::THREADS, K::SMEM_BYTES, st>>>(x, wp, y);
+    conv3x3_kernel<K><<<static_cast<unsigned>(n * K::TPI), K::THREADS, K::SMEM_BYTES, st>>>(x, wp, y, addend);
     return launch_status();
 }
 
@@ -219,7 +224,7 @@ struct MmaCfg {
 
 template <class K>
 __global__ void __launch_bounds__(K::THREADS)
-conv3x3_mma_kernel(const float* __restrict__ x, const float* __restrict__ wm, float* __restrict__ y) {
+conv3x3_mma_kernel(const float* __restrict__ x, const float* __restrict__ wm, float* __restrict__ y, const float* __restrict__ addend) {
     constexpr int C = K::C, H = K::H, W = K::W, R = K::R, MT = K::MT, NT = K::NT, PW = K::PW;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -328,12 +333,15 @@ conv3x3_mma_kernel(const float* __restrict__ x, const float* __restrict__ wm, fl
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int co = (ng * NT + j) * 8 + 2 * tig;
-            float* y0 = y + (static_cast<size_t>(n * C + co) * H + r0) * W;
-            float* y1 = y0 + static_cast<size_t>(H) * W;
-            y0[row0 * W + col0] = acc[i][j][0];
-            y1[row0 * W + col0] = acc[i][j][1];
-            y0[row1 * W + col1] = acc[i][j][2];
-            y1[row1 * W + col1] = acc[i][j][3];
+            const size_t o0 = (static_cast<size_t>(n * C + co) * H + r0) * W, o1 = o0 + static_cast<size_t>(H) * W;
+            const size_t e0 = o0 + row0 * W + col0, e1 = o1 + row0 * W + col0, e2 = o0 + row1 * W + col1, e3 = o1 + row1 * W + col1;
+            if (addend != nullptr) {
+                acc[i][j][0] += addend[e0]; acc[i][j][1] += addend[e1]; acc[i][j][2] += addend[e2]; acc[i][j][3] += addend[e3];
+            }
+            y[e0] = acc[i][j][0];
+            y[e1] = acc[i][j][1];
+            y[e2] = acc[i][j][2];
+            y[e3] = acc[i][j][3];
         }
     }
 }
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(kThreads) conv3x3_pack_mma_kernel(const ConvPa
 }
 
 template <class K>
-static int launch_conv_mma(const float* x, const float* wm, float* y, int n, cudaStream_t st) {
+static int launch_conv_mma(const float* x, const float* wm, float* y, const float* addend, int n, cudaStream_t st) {
     static bool attr_set = false;      // benign race: idempotent
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv3x3_mma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES) != cudaSuccess) {
@@ -370,7 +378,7 @@ static int launch_conv_mma(const float* x, const float* wm, float* y, int n, cud
         }
         attr_set = true;
     }
-    conv3x3_mma_kernel<K><<<static_cast<unsigned>(n * K::TPI), K::THREADS, K::SMEM_BYTES, st>>>(x, wm, y);
+    conv3x3_mma_kernel<K><<<static_cast<unsigned>(n * K::TPI), K::THREADS, K::SMEM_BYTES, st>>>(x, wm, y, addend);
     return launch_status();
 }
 
@@ -583,15 +591,16 @@ AFAN_EXPORT int afan_conv3x3_pack_f32(const void* descs_device, int64_t n_layers
 }
 
 // variant: 0 = default tiling for the shape; other values select tuning candidates (bench only)
-AFAN_EXPORT int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
-                                 int variant, afan_stream_t stream) {
+AFAN_EXPORT int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
+                                 int64_t hw, int variant, afan_stream_t stream) {
     if (n < 0 || c <= 0 || hw <= 0) return AFAN_ERR_SIZE;
     if (n == 0) return AFAN_OK;
     if (!x || !w_packed || !y) return AFAN_ERR_NULL;
-    if (!aligned16(x) || !aligned16(w_packed) || !aligned16(y) || n * c * hw > (1ll << 30) / hw) return AFAN_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(w_packed) || !aligned16(y) || (addend && !aligned16(addend)) || n * c * hw > (1ll << 30) / hw)
+        return AFAN_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int ni = static_cast<int>(n);
-#define AFAN_CONV(C, HW, R, TQ, CK) return launch_conv<ConvCfg<C, HW, R, TQ, CK>>(x, w_packed, y, ni, st)
+#define AFAN_CONV(C, HW, R, TQ, CK) return launch_conv<ConvCfg<C, HW, R, TQ, CK>>(x, w_packed, y, addend, ni, st)
     if (c == 16 && hw == 32) {
         if (variant == 1) AFAN_CONV(16, 32, 16, 4, 8);
         if (variant == 2) AFAN_CONV(16, 32, 32, 4, 4);
@@ -660,8 +669,8 @@ AFAN_EXPORT int afan_conv3x3_pack_tc_f32(const void* descs_device, int64_t n_lay
     return launch_status();
 }
 
-AFAN_EXPORT int afan_conv3x3_tc_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
-                                    int passes, int variant, afan_stream_t stream) {
+AFAN_EXPORT int afan_conv3x3_tc_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
+                                    int64_t hw, int passes, int variant, afan_stream_t stream) {
     if (n < 0 || c <= 0 || hw <= 0 || (passes != 1 && passes != 3)) return AFAN_ERR_SIZE;
     if (n == 0) return AFAN_OK;
     if (!x || !w_packed || !y) return AFAN_ERR_NULL;
@@ -670,8 +679,8 @@ AFAN_EXPORT int afan_conv3x3_tc_f32(const float* x, const float* w_packed, float
     const int ni = static_cast<int>(n);
 #define AFAN_MMA(C, HW, R, MT, NT)                                                                   \
     do {                                                                                             \
-        if (passes == 3) return launch_conv_mma<MmaCfg<C, HW, R, MT, NT, 3>>(x, w_packed, y, ni, st); \
-        return launch_conv_mma<MmaCfg<C, HW, R, MT, NT, 1>>(x, w_packed, y, ni, st);                  \
+        if (passes == 3) return launch_conv_mma<MmaCfg<C, HW, R, MT, NT, 3>>(x, w_packed, y, addend, ni, st); \
+        return launch_conv_mma<MmaCfg<C, HW, R, MT, NT, 1>>(x, w_packed, y, addend, ni, st);                  \
     } while (0)
     if (c == 16 && hw == 32) { if (variant == 1) AFAN_MMA(16, 32, 8, 2, 2); AFAN_MMA(16, 32, 16, 4, 2); }
     if (c == 32 && hw == 16) { if (variant == 1) AFAN_MMA(32, 16, 16, 4, 4); AFAN_MMA(32, 16, 16, 2, 4); }

@@ -326,17 +326,20 @@ def conv3x3_pack(descs: torch.Tensor, c_max: int, math: str = "fp32"):
 _TC_PASSES = {"tf32": 1, "3xtf32": 3}
 
 
-def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0, math: str = "fp32") -> torch.Tensor:
-    """y = conv2d(x, W, stride 1, pad 1) with W packed by conv3x3_pack (forward packing), or the input gradient of that
-    convolution when given dy and the dgrad packing.  `math` must match the packing."""
+def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0, math: str = "fp32",
+            addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = conv2d(x, W, stride 1, pad 1) (+ addend) with W packed by conv3x3_pack (forward packing), or the input gradient
+    of that convolution when given dy and the dgrad packing.  `math` must match the packing."""
     n, c, h, _ = x.shape
     y = torch.empty_like(x)
+    if addend is not None and addend.shape != x.shape:
+        raise AfanError("addend must have the shape of the output")
     if math == "fp32":
-        check(_lib.lib().afan_conv3x3_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), n, c, h, int(variant), stream()),
-              "afan_conv3x3_f32")
+        check(_lib.lib().afan_conv3x3_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), f32(addend, "addend"), n, c, h,
+                                          int(variant), stream()), "afan_conv3x3_f32")
     else:
-        check(_lib.lib().afan_conv3x3_tc_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), n, c, h, _TC_PASSES[math],
-                                             int(variant), stream()), "afan_conv3x3_tc_f32")
+        check(_lib.lib().afan_conv3x3_tc_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), f32(addend, "addend"), n, c, h,
+                                             _TC_PASSES[math], int(variant), stream()), "afan_conv3x3_tc_f32")
     return y
 
 

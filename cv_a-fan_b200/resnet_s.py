@@ -55,8 +55,12 @@ class BasicBlock(nn.Module):
         return F.pad(x[:, :, ::2, ::2], (0, 0, 0, 0, self.pad, self.pad), "constant", 0.0)
 
     def forward(self, x, groups: int = 1, replay: int = 1):
-        h = self.bn1(self.conv1(x), relu=True, groups=groups, replay=replay)
-        return self.bn2(self.conv2(h), residual=self._shortcut(x), relu=True, groups=groups, replay=replay)
+        if self.downsample:
+            c1, sc = self.conv1(x), self._shortcut(x)
+        else:
+            c1, sc = self.conv1.forward_with_tap(x)      # identity shortcut: its gradient joins conv1's dgrad in-kernel
+        h = self.bn1(c1, relu=True, groups=groups, replay=replay)
+        return self.bn2(self.conv2(h), residual=sc, relu=True, groups=groups, replay=replay)
 
 
 class ResNet(nn.Module):

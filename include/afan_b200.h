@@ -237,21 +237,23 @@ int afan_roi_align_bwd_f32(const float* dout, const float* rois, float* dfeat, i
  *     float* wd; int64 c}; repacks W[co][ci][3][3] of every layer in ONE launch into the forward packing
  *     wf[ci][tap][co] and the input-gradient packing wd[co][8-tap][ci] (c*9*c floats each).
  * afan_conv3x3_f32: y = conv(x, W) when given wf; dx = conv_transpose(dy, W) when given dy and wd.
+ *     addend (nullable, shape of y): y = conv(...) + addend in the epilogue -- the gradient of the identity shortcut
+ *     (resnet_s.py:75 `out += self.shortcut(x)`) joins the input gradient without an accumulation launch.
  *     variant 0 = tuned default; other values select alternative tilings (benchmarking only).
  * afan_conv3x3_wgrad_f32: dW[co][ci][3][3] = sum_{n,h,w} dy * shifted x.  Two launches: per-CTA partials
  *     into `workspace` (>= afan_conv3x3_wgrad_workspace_bytes(c), need not be zeroed), then a fixed-order fold
  *     that stores (accumulate = 0) or adds into dw (accumulate = 1: writes straight into a gradient arena
  *     instead of a temporary + autograd's accumulation launch). */
 int afan_conv3x3_pack_f32(const void* descs_device, int64_t n_layers, int64_t c_max, afan_stream_t stream);
-int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
-                     int variant, afan_stream_t stream);
+int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
+                     int64_t hw, int variant, afan_stream_t stream);
 /* Tensor-core twins of the two calls above (mma.sync m16n8k8 TF32, fp32 accumulate).  passes = 3: "3xTF32" split
  * (x = hi + lo; a_lo*b_hi + a_hi*b_lo + a_hi*b_hi) -- fp32-level accuracy on the tensor pipe; passes = 1: plain TF32.
  * The packings are [k/8][tap][out][k%8][hi, lo] (passes = 3: 2*c*9*c floats per direction) or [k/8][tap][out][k%8]
  * (passes = 1: c*9*c floats), hi = W rounded to TF32, lo = TF32 rounding of (W - hi). */
 int afan_conv3x3_pack_tc_f32(const void* descs_device, int64_t n_layers, int64_t c_max, int passes, afan_stream_t stream);
-int afan_conv3x3_tc_f32(const float* x, const float* w_packed, float* y, int64_t n, int64_t c, int64_t hw,
-                        int passes, int variant, afan_stream_t stream);
+int afan_conv3x3_tc_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
+                        int64_t hw, int passes, int variant, afan_stream_t stream);
 int64_t afan_conv3x3_wgrad_workspace_bytes(int64_t c);
 int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
                            int64_t n, int64_t c, int64_t hw, int accumulate, afan_stream_t stream);

@@ -23,7 +23,7 @@ def pack(w):
 
 def conv(x, wp, y, variant=0):
     n, c, h, w = x.shape
-    _lib.check(_lib.lib().afan_conv3x3_f32(x.data_ptr(), wp.data_ptr(), y.data_ptr(), n, c, h, variant, _lib.stream()), "conv")
+    _lib.check(_lib.lib().afan_conv3x3_f32(x.data_ptr(), wp.data_ptr(), y.data_ptr(), None, n, c, h, variant, _lib.stream()), "conv")
     return y
 
 
@@ -75,7 +75,7 @@ for (n, c, h) in ((128, 16, 32), (128, 32, 16), (128, 64, 8), (256, 32, 16), (25
     wtf, wtd = torch.empty(2 * c * 9 * c, device=dev), torch.empty(2 * c * 9 * c, device=dev)
     desc = torch.tensor([[w.data_ptr(), wtf.data_ptr(), wtd.data_ptr(), c]], dtype=torch.int64, device=dev)
     def tc(inp, wp, out, passes, variant):
-        _lib.check(L.afan_conv3x3_tc_f32(inp.data_ptr(), wp.data_ptr(), out.data_ptr(), n, c, h, passes, variant, _lib.stream()), "tc")
+        _lib.check(L.afan_conv3x3_tc_f32(inp.data_ptr(), wp.data_ptr(), out.data_ptr(), None, n, c, h, passes, variant, _lib.stream()), "tc")
     for passes in (3, 1):
         _lib.check(L.afan_conv3x3_pack_tc_f32(desc.data_ptr(), 1, c, passes, _lib.stream()), "pack_tc")
         for v in range(2 if n >= 128 else 1):

@@ -15,9 +15,9 @@ for (n, c, h) in ((128, 32, 16), (128, 64, 8), (128, 16, 32)):
     for passes in (1, 3):
         L.afan_conv3x3_pack_tc_f32(desc.data_ptr(), 1, c, passes, _lib.stream())
         for _ in range(2):
-            L.afan_conv3x3_tc_f32(x.data_ptr(), wtf.data_ptr(), y.data_ptr(), n, c, h, passes, 0, _lib.stream())
+            L.afan_conv3x3_tc_f32(x.data_ptr(), wtf.data_ptr(), y.data_ptr(), None, n, c, h, passes, 0, _lib.stream())
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        L.afan_conv3x3_tc_f32(x.data_ptr(), wtf.data_ptr(), y.data_ptr(), n, c, h, passes, 0, _lib.stream())
+        L.afan_conv3x3_tc_f32(x.data_ptr(), wtf.data_ptr(), y.data_ptr(), None, n, c, h, passes, 0, _lib.stream())
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()

@@ -91,3 +91,30 @@ def test_tensor_core_twins_vs_fp64(mode, tol, n, c, h, monkeypatch):
     ref_dw = torch.nn.grad.conv2d_weight(x.detach().double(), w.shape, dy.double(), padding=1)
     assert _rel(y, ref) < tol and _rel(dx, ref_dx) < tol
     assert _rel(dw, ref_dw) < 2e-5                       # the weight gradient stays on the strict-fp32 kernel
+
+
+def test_identity_shortcut_gradient_is_added_in_the_dgrad_epilogue(monkeypatch):
+    """BasicBlock (resnet_s.py:45-77): with the hand-written kernels the gradient of `out += shortcut(x)` joins conv1's
+    input gradient inside the dgrad kernel (`addend`); the block's gradients must equal the library-convolution block's."""
+    dev = torch.device("cuda:0")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        blk = pkg.resnet_s.BasicBlock(32, 32, 1).to(dev).train()
+        x0 = torch.randn(8, 32, 16, 16, device=dev)
+        dy = torch.randn(8, 32, 16, 16, device=dev)
+        res = {}
+        for mode in ("afan", "cudnn"):
+            monkeypatch.setattr(conv, "MODE", mode)
+            for m in blk.modules():
+                if isinstance(m, pkg.dual_bn.DualBatchNorm2d):
+                    m.running_mean.zero_(); m.running_var.fill_(1.0)
+            x = x0.clone().requires_grad_(True)
+            y = blk(x)
+            grads = torch.autograd.grad(y, (x, blk.conv1.weight, blk.conv2.weight, blk.bn1.weight, blk.bn2.bias), dy)
+            res[mode] = (y.detach(),) + grads
+        for a, b in zip(res["afan"], res["cudnn"]):
+            torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-4)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
