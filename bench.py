@@ -129,6 +129,7 @@ def config_dict(n_gpus, conv_math="fp32", conv="afan"):
             "conv3x3": {"afan": "hand-written sm_100a direct convolution (strict fp32 FFMA)" if conv_math == "fp32"
                         else "hand-written sm_100a mma.sync TF32 implicit GEMM (1 pass)",
                         "3xtf32": "hand-written sm_100a mma.sync 3xTF32 implicit GEMM", "cudnn": "cuDNN"}[conv],
+            "deterministic": "cudnn.deterministic=True (main_perturb.py:315) + deterministic hand-written kernels: bitwise-reproducible steps",
             "l2": "no flush between steps: per-step working set (saved activations ~0.9 GB) exceeds the 126 MB L2; "
                   "kernel rooflines are measured separately with an L2 flush between launches"}
 
@@ -405,6 +406,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = args.conv_math == "tf32"
     torch.backends.cuda.matmul.allow_tf32 = args.conv_math == "tf32"
     torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.deterministic = True                # the reference's setting (main_perturb.py:315): bitwise-reproducible steps
 
     pkg = importlib.import_module("cv_a-fan_b200")
     pkg.conv.MODE = "tf32" if (args.conv == "afan" and args.conv_math == "tf32") else args.conv

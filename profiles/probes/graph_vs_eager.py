@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 PKG = importlib.import_module("cv_a-fan_b200")
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
+if os.environ.get("AFAN_DET") == "1":
+    torch.backends.cudnn.deterministic = True
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(4)
 imgs = [torch.rand(8, 3, 32, 32, generator=g) for _ in range(3)]
