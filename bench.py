@@ -406,7 +406,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = args.conv_math == "tf32"
     torch.backends.cuda.matmul.allow_tf32 = args.conv_math == "tf32"
     torch.backends.cudnn.benchmark = True
-    torch.backends.cudnn.deterministic = True                # the reference's setting (main_perturb.py:315): bitwise-reproducible steps
+    torch.backends.cudnn.deterministic = os.environ.get("AFAN_BENCH_DET", "1") != "0"   # the reference's setting (main_perturb.py:315): bitwise-reproducible steps
 
     pkg = importlib.import_module("cv_a-fan_b200")
     pkg.conv.MODE = "tf32" if (args.conv == "afan" and args.conv_math == "tf32") else args.conv

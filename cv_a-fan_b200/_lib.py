@@ -58,6 +58,8 @@ SIGNATURES = {
     "afan_sgd_momentum_f32": (_int, [_vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp]),
     "afan_conv3x3_pack_f32": (_int, [_vp, _i64, _i64, _vp]),
     "afan_conv3x3_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "afan_conv3x3s2_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "afan_conv3x3s2_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
     "afan_conv3x3_pack_tc_f32": (_int, [_vp, _i64, _i64, _int, _vp]),
     "afan_conv3x3_tc_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
     "afan_conv3x3_wgrad_workspace_bytes": (_i64, [_i64]),
@@ -67,7 +69,7 @@ SIGNATURES = {
 AFAN_ERR_UNSUPPORTED = -5
 _lib = None
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); bumped by check() on success
-KERNELS_PER_CALL = {"afan_nms_f32": 2, "afan_conv3x3_wgrad_f32": 2}
+KERNELS_PER_CALL = {"afan_nms_f32": 2, "afan_conv3x3_wgrad_f32": 2, "afan_conv3x3s2_wgrad_f32": 2}
 launch_count = 0
 
 

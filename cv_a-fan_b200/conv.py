@@ -24,6 +24,7 @@ from . import ops
 #   "3xtf32" hand-written tensor-core kernels, hi/lo split (fp32-level accuracy; measured no faster than "afan")
 #   "cudnn"  the library convolution (benchmark comparisons)
 MODE = os.environ.get("AFAN_CONV", "afan")
+STRIDE2 = os.environ.get("AFAN_S2", "1") != "0"      # hand-written stride-2 transitions (0: library convolution, for A/B timing)
 _MATH = {"afan": "fp32", "tf32": "tf32", "3xtf32": "3xtf32"}
 
 
@@ -81,6 +82,33 @@ class _Conv3x3TapFn(torch.autograd.Function):
         return dx, dw, None
 
 
+class _Conv3x3S2Fn(torch.autograd.Function):
+    """Stride-2 stage transition (resnet_s.py:98): hand-written forward, input gradient and weight gradient (strict fp32
+    in every MODE, deterministic)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, mod):
+        x = x.contiguous()
+        wf, wd = mod.packed()
+        ctx.save_for_backward(x)
+        ctx.wd, ctx.mod = wd, mod
+        return ops.conv3x3s2(x, wf)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.conv3x3s2(dy, ctx.wd, dgrad=True) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            mod = ctx.mod
+            if mod.grad_direct and mod.weight.grad is not None:
+                ops.conv3x3s2_wgrad(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)
+            else:
+                dw = ops.conv3x3s2_wgrad(x, dy, mod.wgrad_workspace())
+        return dx, dw, None
+
+
 class Conv3x3(nn.Conv2d):
     def __init__(self, in_planes: int, planes: int, stride: int = 1):
         super().__init__(in_planes, planes, 3, stride, 1, bias=False)
@@ -97,9 +125,14 @@ class Conv3x3(nn.Conv2d):
             self._packed_key = None
         return self._packed
 
+    @property
+    def is_transition(self) -> bool:
+        return self.stride == (2, 2) and self.out_channels == 2 * self.in_channels
+
     def desc_row(self):
         p = self._buffers_for(self.weight.device)
-        return [self.weight.data_ptr(), p[0].data_ptr(), p[1].data_ptr(), self.out_channels]
+        c = -self.in_channels if self.is_transition else self.out_channels     # c < 0: stride-2 packing
+        return [self.weight.data_ptr(), p[0].data_ptr(), p[1].data_ptr(), c]
 
     def packed(self):
         p = self._buffers_for(self.weight.device)
@@ -127,6 +160,8 @@ class Conv3x3(nn.Conv2d):
         return self.forward(x), x
 
     def forward(self, x):
+        if MODE in _MATH and STRIDE2 and self.is_transition and ops.conv3x3s2_supported(x, self.weight):
+            return _Conv3x3S2Fn.apply(x, self.weight, self)
         if MODE in _MATH and self.stride == (1, 1) and self.in_channels == self.out_channels \
                 and ops.conv3x3_supported(x, self.weight):
             return _Conv3x3Fn.apply(x, self.weight, self)
@@ -138,8 +173,9 @@ class PackPlan:
     raw kernel).  The descriptor table is rebuilt when a weight moved (e.g. into the flat parameter arena)."""
 
     def __init__(self, model: nn.Module):
-        self.mods = [m for m in model.modules() if isinstance(m, Conv3x3) and m.stride == (1, 1)
-                     and m.in_channels == m.out_channels and m.out_channels in ops.CONV3X3_CHANNELS]
+        self.mods = [m for m in model.modules() if isinstance(m, Conv3x3)
+                     and ((m.stride == (1, 1) and m.in_channels == m.out_channels and m.out_channels in ops.CONV3X3_CHANNELS)
+                          or (m.is_transition and m.in_channels in (16, 32)))]
         self._ptrs, self._descs = None, None
         for m in self.mods:
             m._managed = True

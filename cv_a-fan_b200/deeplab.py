@@ -78,35 +78,13 @@ class SplitResNet(nn.Module):
         return out
 
 
-class ASPPConv(nn.Sequential):
-    def __init__(self, cin, cout, dilation):
-        super().__init__(nn.Conv2d(cin, cout, 3, padding=dilation, dilation=dilation, bias=False), nn.BatchNorm2d(cout),
-                         nn.ReLU(inplace=True))
-
-
-class ASPPPooling(nn.Sequential):
-    def __init__(self, cin, cout):
-        super().__init__(nn.AdaptiveAvgPool2d(1), nn.Conv2d(cin, cout, 1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
-
-    def forward(self, x):
-        size = x.shape[-2:]
-        return F.interpolate(super().forward(x), size=size, mode="bilinear", align_corners=False)
-
-
-class ASPP(nn.Module):
-    """network/_deeplab.py:174-207 (1x1, three dilated 3x3, image pooling; 1x1 projection + Dropout(0.1))."""
-
-    def __init__(self, cin, rates, cout: int = 256):
-        super().__init__()
-        mods = [nn.Sequential(nn.Conv2d(cin, cout, 1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))]
-        mods += [ASPPConv(cin, cout, r) for r in rates]
-        mods.append(ASPPPooling(cin, cout))
-        self.convs = nn.ModuleList(mods)
-        self.project = nn.Sequential(nn.Conv2d(5 * cout, cout, 1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
-                                     nn.Dropout(0.1))
-
-    def forward(self, x):
-        return self.project(torch.cat([c(x) for c in self.convs], dim=1))
+def _aspp(cin, rates):
+    """ASPP (1x1, three dilated 3x3, image pooling; 1x1 projection + Dropout): torchvision's module has exactly the
+    reference's sub-module names (network/_deeplab.py:174-207 is the same lineage); only its Dropout rate differs."""
+    from torchvision.models.segmentation.deeplabv3 import ASPP
+    m = ASPP(cin, list(rates), 256)
+    m.project[3].p = 0.1                                                # network/_deeplab.py:199
+    return m
 
 
 class DeepLabHeadV3Plus(nn.Module):
@@ -115,7 +93,7 @@ class DeepLabHeadV3Plus(nn.Module):
     def __init__(self, cin, low_level_channels, num_classes, aspp_dilate):
         super().__init__()
         self.project = nn.Sequential(nn.Conv2d(low_level_channels, 48, 1, bias=False), nn.BatchNorm2d(48), nn.ReLU(inplace=True))
-        self.aspp = ASPP(cin, aspp_dilate)
+        self.aspp = _aspp(cin, aspp_dilate)
         self.classifier = nn.Sequential(nn.Conv2d(304, 256, 3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
                                         nn.Conv2d(256, num_classes, 1))
         for m in self.modules():

@@ -343,6 +343,40 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0, math: str
     return y
 
 
+CONV3X3S2_SHAPES = ((16, 32), (32, 16))          # (C_in, H_in) of the two stride-2 stage transitions of the CIFAR ResNets
+
+
+def conv3x3s2_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[2] == x.shape[3]
+            and (x.shape[1], x.shape[2]) in CONV3X3S2_SHAPES and tuple(weight.shape) == (2 * x.shape[1], x.shape[1], 3, 3))
+
+
+def conv3x3s2(x: torch.Tensor, w_packed: torch.Tensor, dgrad: bool = False) -> torch.Tensor:
+    """Stride-2 transition convolution (C -> 2C, H -> H/2), or with dgrad=True its input gradient (x is then dy
+    [N, 2C, H/2, H/2] and the result [N, C, H, H])."""
+    n = x.shape[0]
+    if dgrad:
+        cin, ho = x.shape[1] // 2, x.shape[2]
+        out = torch.empty((n, cin, 2 * ho, 2 * ho), dtype=torch.float32, device=x.device)
+    else:
+        cin, ho = x.shape[1], x.shape[2] // 2
+        out = torch.empty((n, 2 * cin, ho, ho), dtype=torch.float32, device=x.device)
+    check(_lib.lib().afan_conv3x3s2_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(out), n, cin, ho, int(bool(dgrad)), stream()),
+          "afan_conv3x3s2_f32")
+    return out
+
+
+def conv3x3s2_wgrad(x: torch.Tensor, dy: torch.Tensor, ws: torch.Tensor, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW [2C, C, 3, 3] of the stride-2 transition (x [N, C, H, H], dy [N, 2C, H/2, H/2]); deterministic."""
+    n, cin, hin, _ = x.shape
+    dw = torch.empty((2 * cin, cin, 3, 3), dtype=torch.float32, device=x.device) if accumulate_into is None else accumulate_into
+    if dw.numel() != 18 * cin * cin:
+        raise AfanError("accumulate_into must hold 2C*C*9 floats")
+    check(_lib.lib().afan_conv3x3s2_wgrad_f32(f32(x, "x"), f32(dy, "dy"), f32(dw), ptr(ws), ws.numel() * 4, n, cin, hin // 2,
+                                              int(accumulate_into is not None), stream()), "afan_conv3x3s2_wgrad_f32")
+    return dw
+
+
 def conv3x3_wgrad_workspace(c: int, device) -> torch.Tensor:
     return torch.empty(_lib.lib().afan_conv3x3_wgrad_workspace_bytes(int(c)) // 4, dtype=torch.float32, device=device)
 

@@ -234,7 +234,7 @@ int afan_roi_align_bwd_f32(const float* dout, const float* rois, float* dfeat, i
  * AFAN_ERR_UNSUPPORTED (the caller keeps the library convolution for them).
  *
  * afan_conv3x3_pack_f32: descs_device = device array of n_layers records {const float* w; float* wf;
- *     float* wd; int64 c}; repacks W[co][ci][3][3] of every layer in ONE launch into the forward packing
+ *     float* wd; int64 c} (c < 0: stride-2 transition layer with cin = -c, see afan_conv3x3s2_f32); repacks W[co][ci][3][3] of every layer in ONE launch into the forward packing
  *     wf[ci][tap][co] and the input-gradient packing wd[co][8-tap][ci] (c*9*c floats each).
  * afan_conv3x3_f32: y = conv(x, W) when given wf; dx = conv_transpose(dy, W) when given dy and wd.
  *     addend (nullable, shape of y): y = conv(...) + addend in the epilogue -- the gradient of the identity shortcut
@@ -247,6 +247,15 @@ int afan_roi_align_bwd_f32(const float* dout, const float* rois, float* dfeat, i
 int afan_conv3x3_pack_f32(const void* descs_device, int64_t n_layers, int64_t c_max, afan_stream_t stream);
 int afan_conv3x3_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
                      int64_t hw, int variant, afan_stream_t stream);
+/* Stride-2 stage transitions (first block of stages 2 and 3, resnet_s.py:98): W[2*cin][cin][3][3], x [n][cin][2*ho][2*ho]
+ * -> y [n][2*cin][ho][ho]; dgrad != 0 computes dx from dy instead.  (cin, ho) in {(16, 16), (32, 8)}; the packings come
+ * from afan_conv3x3_pack_f32 with a descriptor whose c field is -cin (18*cin*cin floats each). */
+int afan_conv3x3s2_f32(const float* in, const float* w_packed, float* out, int64_t n, int64_t cin, int64_t ho, int dgrad,
+                       afan_stream_t stream);
+/* Weight gradient of the same transition: dw [2*cin][cin][3][3] stored (accumulate = 0) or added to (accumulate = 1);
+ * workspace >= afan_conv3x3_wgrad_workspace_bytes(2 * cin); two launches, fixed-order fold (deterministic). */
+int afan_conv3x3s2_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
+                             int64_t n, int64_t cin, int64_t ho, int accumulate, afan_stream_t stream);
 /* Tensor-core twins of the two calls above (mma.sync m16n8k8 TF32, fp32 accumulate).  passes = 3: "3xTF32" split
  * (x = hi + lo; a_lo*b_hi + a_hi*b_lo + a_hi*b_hi) -- fp32-level accuracy on the tensor pipe; passes = 1: plain TF32.
  * The packings are [k/8][tap][out][k%8][hi, lo] (passes = 3: 2*c*9*c floats per direction) or [k/8][tap][out][k%8]

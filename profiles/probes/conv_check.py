@@ -102,3 +102,16 @@ for (n, c, h) in ((128, 16, 32), (128, 32, 16), (128, 64, 8), (256, 32, 16), (25
         res[key]["cudnn_fwd_us"] = round(graph_time(lambda: F.conv2d(x, w, padding=1)), 2)
         res[key]["cudnn_dgrad_us"] = round(graph_time(lambda: torch.nn.grad.conv2d_input(x.shape, w, dy, padding=1)), 2)
     print(key, json.dumps(res[key]), flush=True)
+
+# stride-2 transitions: hand-written vs cuDNN
+for (n, cin, hin) in ((128, 16, 32), (128, 32, 16), (256, 16, 32), (256, 32, 16)):
+    m = pkg.conv.Conv3x3(cin, 2 * cin, 2).to(dev)
+    x = torch.randn(n, cin, hin, hin, device=dev)
+    dy = torch.randn(n, 2 * cin, hin // 2, hin // 2, device=dev)
+    wf, wd = m.packed()
+    ops = pkg.ops
+    r = {"s2_fwd_us": round(graph_time(lambda: ops.conv3x3s2(x, wf)), 2),
+         "s2_dgrad_us": round(graph_time(lambda: ops.conv3x3s2(dy, wd, dgrad=True)), 2),
+         "cudnn_fwd_us": round(graph_time(lambda: F.conv2d(x, m.weight, stride=2, padding=1)), 2),
+         "cudnn_dgrad_us": round(graph_time(lambda: torch.nn.grad.conv2d_input(x.shape, m.weight, dy, stride=2, padding=1)), 2)}
+    print(f"s2 {n}x{cin}x{hin}", json.dumps(r), flush=True)

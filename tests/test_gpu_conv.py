@@ -63,8 +63,8 @@ def test_conv3x3_is_deterministic_and_repacks_after_weight_update():
 def test_unsupported_shapes_use_the_library_convolution():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    m = conv.Conv3x3(16, 32, 2).to(dev)                      # stride-2 stage transition (resnet_s.py:98)
-    x = torch.randn(4, 16, 32, 32, device=dev)
+    m = conv.Conv3x3(16, 32, 2).to(dev)                      # a stride-2 convolution on a map size the kernels do not cover
+    x = torch.randn(4, 16, 24, 24, device=dev)
     assert torch.allclose(m(x), F.conv2d(x, m.weight, stride=2, padding=1))
     m2 = conv.Conv3x3(16, 16, 1).to(dev)
     x2 = torch.randn(2, 16, 12, 12, device=dev)              # 12x12 is not a covered map size
@@ -118,3 +118,25 @@ def test_identity_shortcut_gradient_is_added_in_the_dgrad_epilogue(monkeypatch):
             torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-4)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("n,cin,hin", [(128, 16, 32), (128, 32, 16), (3, 16, 32), (5, 32, 16), (256, 32, 16)])
+def test_stride2_transition_forward_and_dgrad_vs_fp64(n, cin, hin, monkeypatch):
+    """Stage transitions (resnet_s.py:98): C -> 2C, stride 2; forward, input gradient and weight gradient hand-written."""
+    dev = torch.device("cuda:0")
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)           # the library wgrad is compared at fp32 accuracy
+    g = torch.Generator(device="cpu").manual_seed(n + cin)
+    x = torch.randn(n, cin, hin, hin, generator=g).to(dev).requires_grad_(True)
+    dy = torch.randn(n, 2 * cin, hin // 2, hin // 2, generator=g).to(dev)
+    m = conv.Conv3x3(cin, 2 * cin, 2).to(dev)
+    y = m(x)
+    assert y.shape == (n, 2 * cin, hin // 2, hin // 2)
+    dx, dw = torch.autograd.grad(y, (x, m.weight), dy)
+    w = m.weight.detach().double()
+    ref = F.conv2d(x.detach().double(), w, stride=2, padding=1)
+    ref_dx = torch.nn.grad.conv2d_input(x.shape, w, dy.double(), stride=2, padding=1)
+    ref_dw = torch.nn.grad.conv2d_weight(x.detach().double(), w.shape, dy.double(), stride=2, padding=1)
+    assert _rel(y, ref) < 2e-5 and _rel(dx, ref_dx) < 2e-5 and _rel(dw, ref_dw) < 2e-5
+    outs = [torch.autograd.grad(m(x), (x, m.weight), dy) for _ in range(2)]
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], dx)          # deterministic
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][1], dw)
