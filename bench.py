@@ -310,6 +310,21 @@ def kernel_rooflines(pkg, dev, reps=10):
         measure(f"conv3x3 wgrad [{N}x{C}x{H}x{H}]", 8 * E + 4 * 9 * C * C, 8 * E, mk,
                 lambda t: ops.conv3x3_wgrad(t["x"], t["dy"], t["ws"]), lpi_wgrad,
                 "weight gradient (partials kernel + fixed-order fold kernel, both in the time)", flops=fl_conv)
+    # stride-2 stage transitions (first block of stages 2 and 3): forward + dgrad per PGD step at batch n, once at 2n
+    for (N, CIN, HIN), lpi in (((n, 16, 32), steps), ((n, 32, 16), steps), ((2 * n, 16, 32), 1), ((2 * n, 32, 16), 1)):
+        HO = HIN // 2
+        fl = 2.0 * N * HO * HO * (2 * CIN) * CIN * 9
+        nbytes = 4 * N * CIN * HIN * HIN + 4 * N * 2 * CIN * HO * HO
+
+        def mk():
+            m = pkg.conv.Conv3x3(CIN, 2 * CIN, 2).to(dev)
+            wf, wd = m.packed()
+            return dict(x=torch.randn(N, CIN, HIN, HIN, device=dev, generator=g), dy=torch.randn(N, 2 * CIN, HO, HO, device=dev, generator=g),
+                        wf=wf, wd=wd, m=m)
+        measure(f"conv3x3s2 fwd [{N}x{CIN}x{HIN}x{HIN}]", nbytes, nbytes, mk, lambda t: ops.conv3x3s2(t["x"], t["wf"]), lpi,
+                "stride-2 transition C -> 2C: 36*C FLOP per output element", flops=fl)
+        measure(f"conv3x3s2 dgrad [{N}x{CIN}x{HIN}x{HIN}]", nbytes, nbytes, mk, lambda t: ops.conv3x3s2(t["dy"], t["wd"], dgrad=True), lpi,
+                "input gradient of the stride-2 transition", flops=fl)
     for tag, shape in (("cfg5 4x2048x33x33", (4, 2048, 33, 33)), ("cfg4 8x1024x38x63", (8, 1024, 38, 63)),
                        ("4x256x128x128", (4, 256, 128, 128))):
         E = 1
@@ -496,10 +511,14 @@ def main():
     # other convolution paths of the SAME step, for context only (never the headline): single GPU, device-resident inputs
     if world == 1 and not args.skip_variants and args.conv == "afan" and args.conv_math == "fp32" and not args.no_graph:
         variants = {}
-        for vname, mode, tf32 in (("conv_tf32_tensor_core_kernels", "tf32", True), ("conv_cudnn_fp32", "cudnn", False)):
+        det = torch.backends.cudnn.deterministic
+        for vname, mode, tf32 in (("conv_tf32_tensor_core_kernels", "tf32", True), ("conv_cudnn_fp32_nondeterministic", "cudnn", False)):
             pkg.conv.MODE = mode
             torch.backends.cudnn.allow_tf32 = tf32
             torch.backends.cuda.matmul.allow_tf32 = tf32
+            # the library path is timed with its fastest (non-deterministic) algorithms: under cudnn.deterministic the same
+            # step takes 25.4 ms
+            torch.backends.cudnn.deterministic = det and mode != "cudnn"
             torch.manual_seed(3)
             vm = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)
             vt = pkg.trainer.AfanTrainer(vm, perturb_idx=w["perturb_idx"], steps=w["steps"], gamma=w["gamma"], eps=w["eps"],
@@ -512,6 +531,7 @@ def main():
         pkg.conv.MODE = "afan"
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.deterministic = det
         line["variants"] = variants
 
     if rank == 0 and not args.skip_rooflines:
