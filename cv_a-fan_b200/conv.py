@@ -191,5 +191,6 @@ class PackPlan:
         ops.conv3x3_pack(self._descs, max(m.out_channels for m in self.mods), _MATH[MODE])
 
     def release(self):
+        """Back to stand-alone mode: every module repacks its own weight on its next forward."""
         for m in self.mods:
             m._managed, m._packed_key = False, None

@@ -266,6 +266,10 @@ class AfanTrainer:
         torch.cuda.synchronize(self.device)
         self._graph = None
         self._static = {}
+        # hand the model back in stand-alone mode: modules repack their own weights again and gradients go through autograd
+        self._conv_pack.release()
+        for m in list(self._conv_pack.mods) + list(self._bn):
+            m.grad_direct = False
         if self.mailbox is not None:
             self.mailbox.check()
 
