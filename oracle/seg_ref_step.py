@@ -171,8 +171,14 @@ def reference_iteration(model, attack_algo, images, labels, c, criterion, optimi
 
 
 def _load_reference():
-    sys.path.insert(0, HERE)
-    import ref_shim
+    # load the shim WITHOUT putting oracle/ on sys.path (it would shadow the `oracle` package for spawned test workers)
+    try:
+        from oracle import ref_shim
+    except ImportError:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("afan_ref_shim", os.path.join(HERE, "ref_shim.py"))
+        ref_shim = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_shim)
     ref_shim._install_stubs()
     tvu = types.ModuleType("torchvision.models.utils")       # removed from torchvision; network/backbone/resnet.py:3 imports it
     tvu.load_state_dict_from_url = lambda *a, **k: {}

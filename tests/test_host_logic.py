@@ -132,3 +132,29 @@ def test_seg_golden_matches_the_product_model_layout():
     assert [str(k) for k in g["keys"]] == list(model.state_dict().keys())
     for name in ref.CASES:
         assert np.isfinite(g[f"{name}/losses"]).all() and g[f"{name}/losses"].shape == (ref.ITERS, 5)
+
+
+def test_stat_arena_replay_equals_repeated_batchnorm_updates():
+    """trainer_seg._StatArena.replay(k): the closed form new = a*after_one + b*before equals forwarding the SAME batch k
+    times through train-mode BatchNorm (what the reference's repeated clean passes do, main_aug_final.py:164,166,217)."""
+    torch.manual_seed(0)
+    bns = [torch.nn.BatchNorm2d(5, momentum=0.01), torch.nn.BatchNorm2d(3, momentum=0.01)]
+    refs = [torch.nn.BatchNorm2d(5, momentum=0.01), torch.nn.BatchNorm2d(3, momentum=0.01)]
+    for b, r in zip(bns, refs):
+        b.running_mean.copy_(torch.randn_like(b.running_mean)); b.running_var.copy_(torch.rand_like(b.running_var) + 0.5)
+        r.load_state_dict(b.state_dict())
+    arena = PKG.trainer_seg._StatArena(bns, torch.device("cpu"))
+    xs = [torch.randn(4, 5, 6, 6), torch.randn(4, 3, 6, 6)]
+    for k in (2, 3):
+        arena.snapshot()
+        for b, r, x in zip(bns, refs, xs):
+            b.train()(x)                                # one pass through the arena-backed layer
+            for _ in range(k):
+                r.train()(x)                            # k passes through the plain layer
+        arena.replay(k)
+        for b, r in zip(bns, refs):
+            torch.testing.assert_close(b.running_mean, r.running_mean, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(b.running_var, r.running_var, rtol=1e-5, atol=1e-6)
+            assert int(b.num_batches_tracked) == int(r.num_batches_tracked)
+    with pytest.raises(PKG.AfanError):
+        PKG.trainer_seg._StatArena([torch.nn.BatchNorm2d(2, momentum=0.1), torch.nn.BatchNorm2d(2, momentum=0.01)], torch.device("cpu"))

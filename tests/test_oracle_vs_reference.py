@@ -80,3 +80,39 @@ def test_seg_iteration_restatement_equals_reference():
         rand = lambda shape: next(q)
         losses = ref.reference_iteration(model, ref.TorchAttackAlgo(rand), images[it], labels[it], c, crit, opt, rand=rand)
         np.testing.assert_allclose(losses, g[f"{name}/losses"][it], rtol=1e-6)
+
+
+def test_split_deeplab_equals_reference_model_in_every_protocol_mode():
+    """cv_a-fan_b200.deeplab.SplitDeepLabV3Plus loads the reference model's state dict and reproduces it bit for bit in
+    all 13 modes of the dict protocol (network/utils.py:14-46, backbone/resnet.py:198-304, _deeplab.py:46-80)."""
+    import importlib
+    from oracle import seg_ref_step as ref
+    pkg = importlib.import_module("cv_a-fan_b200")
+    shim, _, network = ref._load_reference()
+    torch.manual_seed(0)
+    theirs = network.deeplabv3plus_resnet50(num_classes=5, output_stride=16, pretrained_backbone=False)
+    mine = pkg.deeplab.deeplabv3plus_resnet50(num_classes=5, output_stride=16)
+    assert list(mine.state_dict().keys()) == list(theirs.state_dict().keys())
+    mine.load_state_dict(theirs.state_dict())
+    for m in (theirs, mine):
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+    x = torch.rand(2, 3, 65, 65)
+    with shim.cpu_cuda_identity(), torch.no_grad():
+        for idx in (1, 2, 3, 4):
+            r = theirs({"x": x, "adv": None, "out_idx": idx, "flag": "head"})
+            m = mine({"x": x, "adv": None, "out_idx": idx, "flag": "head"})
+            assert torch.equal(r["out"], m["out"]) and torch.equal(r["low_level"], m["low_level"])
+            rt = theirs({"x": x, "adv": r["out"], "out_idx": idx, "flag": "tail", "low_level_feat": r["low_level"]})
+            mt = mine({"x": x, "adv": m["out"], "out_idx": idx, "flag": "tail", "low_level_feat": m["low_level"]})
+            assert torch.equal(rt, mt), idx
+        assert torch.equal(theirs({"x": x, "adv": None, "out_idx": 0, "flag": "clean"}),
+                           mine({"x": x, "adv": None, "out_idx": 0, "flag": "clean"}))
+        for sd in ("aspp", "concat"):
+            r = theirs({"x": x, "adv": None, "out_idx": sd + "_head", "flag": "clean"})
+            m = mine({"x": x, "adv": None, "out_idx": sd + "_head", "flag": "clean"})
+            assert torch.equal(r["adv"], m["adv"]), sd
+            assert torch.equal(theirs({"x": x, "adv": r, "out_idx": sd + "_tail", "flag": "clean"}),
+                               mine({"x": x, "adv": m, "out_idx": sd + "_tail", "flag": "clean"})), sd
