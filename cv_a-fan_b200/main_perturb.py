@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import resnet_s
+from . import conv, resnet_s
 from .trainer import AfanTrainer
 
 
@@ -48,6 +48,9 @@ def build_parser():
     # extras of this implementation
     p.add_argument("--norm", default="linf", choices=["linf", "l2"])
     p.add_argument("--rng", default="philox", choices=["philox", "reference"])
+    p.add_argument("--conv_math", default="fp32", choices=["fp32", "tf32", "3xtf32", "cudnn"],
+                   help="3x3 convolutions: hand-written strict-fp32 kernels (default), their TF32 / 3xTF32 tensor-core twins, "
+                        "or the cuDNN library path")
     p.add_argument("--no_graph", action="store_true")
     p.add_argument("--no_head_cache", action="store_true")
     p.add_argument("--no_sync_bn", action="store_true")
@@ -110,6 +113,8 @@ def main(argv=None):
         pg = torch.distributed.group.WORLD
     if args.seed:
         setup_seed(args.seed)
+    conv.MODE = {"fp32": "afan", "tf32": "tf32", "3xtf32": "3xtf32", "cudnn": "cudnn"}[args.conv_math]
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = args.conv_math == "tf32"
     model = (resnet_s.resnet56(num_classes=args.num_classes) if args.arch == "resnet56"
              else resnet_s.resnet20(num_classes=args.num_classes)).to(device)
     trainer = AfanTrainer(model, perturb_idx=args.perturb_idx, steps=args.steps, gamma=args.gamma, eps=args.eps,
