@@ -118,6 +118,41 @@ def cpu_reference(steps, warmup, batch=None):
             "ms_per_step": 1e3 * dt / steps}
 
 
+def gpu_reference(dev, steps=5, warmup=3):
+    """Context number: the reference iteration in plain PyTorch ON THE SAME B200 -- un-fused ATen PGD ops,
+    nn.BatchNorm2d, two head passes, torch.optim.SGD, eager launches, cuDNN's fastest fp32 algorithms.  This is what the
+    reference itself would run on this GPU; it is a baseline like `cpu_baseline`, never the product path."""
+    from oracle import afan_ref_torch as ref_t
+    w = WORKLOAD
+    det = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = False
+    try:
+        torch.manual_seed(3)
+        model = ref_t.CifarResNetRef(w["num_blocks"], w["num_classes"]).to(dev)
+        model.train()
+        opt, crit = ref_t.make_sgd(model), torch.nn.CrossEntropyLoss()
+        g = torch.Generator().manual_seed(3)
+        x = torch.rand(w["batch_per_gpu"], *w["image"], generator=g).to(dev)
+        y = torch.randint(0, w["num_classes"], (w["batch_per_gpu"],), generator=g).to(dev)
+        kw = dict(steps=w["steps"], gamma=w["gamma"], eps=w["eps"], perturb_idx=w["perturb_idx"], randinit=w["randinit"],
+                  clip=w["clip"])
+        for _ in range(warmup):
+            ref_t.afan_train_iteration(model, opt, crit, x, y, **kw)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            ref_t.afan_train_iteration(model, opt, crit, x, y, **kw)
+        e.record()
+        e.synchronize()
+        ms = s.elapsed_time(e) / steps
+        return {"value": 1e3 * w["batch_per_gpu"] / ms, "unit": "img/s", "ms_per_step": ms,
+                "what": "oracle/afan_ref_torch.py (plain-PyTorch port of main_perturb.py:173-201) on the same GPU: un-fused ATen "
+                        "PGD, nn.BatchNorm2d, head forwarded twice, torch.optim.SGD, eager, cuDNN benchmark mode, fp32"}
+    finally:
+        torch.backends.cudnn.deterministic = det
+
+
 def config_dict(n_gpus, conv_math="fp32", conv="afan"):
     w = WORKLOAD
     return {"workload": "BASELINE configs[1]: ResNet-56 CIFAR-100-shaped synthetic 32x32, A-FAN PGD-5 with dual BN",
@@ -596,6 +631,10 @@ def main():
         if not args.no_sync_bn:
             line["bn_fwd_us_per_call_G1_128x32x16x16"] = exchange_microbench(pkg, dev, trainer.mailbox, pg)
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        try:
+            line["reference_on_gpu"] = gpu_reference(dev)
+        except Exception as exc:                     # context number only: never fail the bench line over it
+            line["reference_on_gpu"] = {"error": repr(exc)[:200]}
         cb = cpu_reference(steps=4, warmup=1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
