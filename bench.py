@@ -22,6 +22,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import torch
@@ -45,24 +46,54 @@ def peaks():
 # clocks: sample nvidia-smi DURING the timed region
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread (10 ms period, so a 0.3 s
+    region still gets ~30 samples); `nvidia-smi -lms` in a subprocess when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.proc, self.path, self.thread, self.rows, self.max_mhz = index, None, None, None, [], None
+        self._stop = threading.Event()
+
+    def _nvml_loop(self, h, nv):
+        bits = (nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap)
+        while not self._stop.is_set():
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), [bool(r & b) for b in bits]))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(h, nv), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
         return self
 
     def __exit__(self, *a):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -73,14 +104,16 @@ class ClockSampler:
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         try:
-            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
-            sm = sorted(float(r[0]) for r in rows)
+            if self.thread is None:
+                rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+                self.rows = [(float(r[0]), ["Active" in r[2 + i] and "Not" not in r[2 + i] for i in range(4)]) for r in rows]
+                self.max_mhz = float(rows[0][1])
+            sm = sorted(r[0] for r in self.rows)
             out["sm_mhz"] = sm[len(sm) // 2]
-            out["sm_max_mhz"] = float(rows[0][1])
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            out["reasons"] = [n for i, n in enumerate(names) if any("Active" in r[2 + i] and "Not" not in r[2 + i] for r in rows)]
-            out["samples"] = len(rows)
-        except Exception as e:       # no nvidia-smi (CPU box) -> nulls
+            out["sm_max_mhz"] = self.max_mhz
+            out["reasons"] = [n for i, n in enumerate(self.NAMES) if any(r[1][i] for r in self.rows)]
+            out["samples"] = len(self.rows)
+        except Exception as e:       # no NVML / nvidia-smi (CPU box) -> nulls
             out["error"] = str(e)[:80]
         finally:
             if self.path and os.path.exists(self.path):
@@ -113,19 +146,22 @@ def cpu_reference(steps, warmup, batch=None):
         ref_t.afan_train_iteration(model, opt, crit, x, y, **kw)
     dt = time.perf_counter() - t0
     return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} full iterations (after {warmup} warm-up) of the same workload at batch {batch} "
-                      f"on {cores} host threads, oracle/afan_ref_torch.py (plain-PyTorch port of main_perturb.py:173-201)",
+            "sample": f"{steps} full iterations (after {warmup} warm-up) of this workload, batch {batch}, {cores} threads, "
+                      f"oracle/afan_ref_torch.py",
             "ms_per_step": 1e3 * dt / steps}
 
 
-def gpu_reference(dev, steps=5, warmup=3):
+def gpu_reference(dev, steps=5, warmup=3, tf32=False):
     """Context number: the reference iteration in plain PyTorch ON THE SAME B200 -- un-fused ATen PGD ops,
     nn.BatchNorm2d, two head passes, torch.optim.SGD, eager launches, cuDNN's fastest fp32 algorithms.  This is what the
     reference itself would run on this GPU; it is a baseline like `cpu_baseline`, never the product path."""
     from oracle import afan_ref_torch as ref_t
     w = WORKLOAD
     det = torch.backends.cudnn.deterministic
+    old_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.deterministic = False
+    torch.backends.cudnn.allow_tf32 = tf32           # stock PyTorch: cuDNN convolutions run in TF32 (allow_tf32 defaults to True)
+    torch.backends.cuda.matmul.allow_tf32 = False    # stock PyTorch keeps fp32 matmul
     try:
         torch.manual_seed(3)
         model = ref_t.CifarResNetRef(w["num_blocks"], w["num_classes"]).to(dev)
@@ -148,25 +184,22 @@ def gpu_reference(dev, steps=5, warmup=3):
         ms = s.elapsed_time(e) / steps
         return {"value": 1e3 * w["batch_per_gpu"] / ms, "unit": "img/s", "ms_per_step": ms,
                 "what": "oracle/afan_ref_torch.py (plain-PyTorch port of main_perturb.py:173-201) on the same GPU: un-fused ATen "
-                        "PGD, nn.BatchNorm2d, head forwarded twice, torch.optim.SGD, eager, cuDNN benchmark mode, fp32"}
+                        "PGD, nn.BatchNorm2d, head forwarded twice, torch.optim.SGD, eager, cuDNN benchmark mode, "
+                        + ("cuDNN TF32 convolutions (stock PyTorch defaults)" if tf32 else "strict fp32 convolutions")}
     finally:
         torch.backends.cudnn.deterministic = det
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
 
 
-def config_dict(n_gpus, conv_math="fp32", conv="afan"):
+def config_dict(n_gpus, conv_math="fp32", conv="afan", rng="philox"):
+    """Short on purpose: the driver keeps only the tail of stdout, the whole final line must stay under ~1.4 KB."""
     w = WORKLOAD
-    return {"workload": "BASELINE configs[1]: ResNet-56 CIFAR-100-shaped synthetic 32x32, A-FAN PGD-5 with dual BN",
+    return {"workload": "configs[1]: ResNet-56 CIFAR-100-shaped 32x32, A-FAN PGD-5 idx13 rand+clip, dual BN",
             "global_batch": w["batch_per_gpu"] * n_gpus, "batch_per_gpu": w["batch_per_gpu"],
-            "perturb_idx": w["perturb_idx"], "perturbed_feature": "128x16x32x32 fp32 per GPU",
-            "pgd_steps": w["steps"], "gamma_255": w["gamma"], "eps_255": w["eps"], "randinit": w["randinit"],
-            "clip": w["clip"], "parallelism": f"dp{n_gpus} (one process per GPU, NCCL)",
-            "conv_math": "fp32 (TF32 off)" if conv_math == "fp32" else "tf32 tensor cores (cuDNN), fp32 accumulate",
-            "conv3x3": {"afan": "hand-written sm_100a direct convolution (strict fp32 FFMA)" if conv_math == "fp32"
-                        else "hand-written sm_100a mma.sync TF32 implicit GEMM (1 pass)",
-                        "3xtf32": "hand-written sm_100a mma.sync 3xTF32 implicit GEMM", "cudnn": "cuDNN"}[conv],
-            "deterministic": "cudnn.deterministic=True (main_perturb.py:315) + deterministic hand-written kernels: bitwise-reproducible steps",
-            "l2": "no flush between steps: per-step working set (saved activations ~0.9 GB) exceeds the 126 MB L2; "
-                  "kernel rooflines are measured separately with an L2 flush between launches"}
+            "parallelism": f"dp{n_gpus}", "rng": rng,
+            "conv": {"afan": "afan fp32 FFMA" if conv_math == "fp32" else "afan mma.sync tf32", "3xtf32": "afan mma.sync 3xtf32",
+                     "tc3": "afan tcgen05 3xtf32", "cudnn": "cudnn " + conv_math}[conv],
+            "deterministic": True, "l2": "step working set > L2; kernel rooflines: rotating sets > 4x L2"}
 
 
 def run_reference(args):
@@ -181,7 +214,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(_r(line, 5), separators=(",", ":")), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -190,7 +223,7 @@ def run_reference(args):
 L2_BYTES = 126 * 1024 * 1024
 
 
-def kernel_rooflines(pkg, dev, reps=10):
+def kernel_rooflines(pkg, dev, reps=10, in_step_only=False):
     """Per-launch device time of each hand-written kernel with an L2-cold working set.
 
     Method ("inputs larger than L2"): every kernel gets R independent tensor sets with R x bytes >= 4 x L2;
@@ -222,6 +255,8 @@ def kernel_rooflines(pkg, dev, reps=10):
     ffma_peak = fl.value / (s0.elapsed_time(e0) * 1e-3) / 1e12
 
     def measure(name, bytes_per_launch, footprint, make_set, run, launches_per_iter, note, flops=None):
+        if in_step_only and launches_per_iter == 0:          # N > 1: only the shapes the timed step launches
+            return
         R = max(2, min(64, -(-4 * L2_BYTES // footprint)))
         sets = [make_set() for _ in range(R)]
         side.wait_stream(torch.cuda.current_stream())
@@ -415,6 +450,127 @@ def exchange_microbench(pkg, dev, mailbox, pg, calls=100):
 
 
 # ---------------------------------------------------------------------------------------------------
+# parity evidence carried by the bench line itself
+# ---------------------------------------------------------------------------------------------------
+def multi_gpu_parity(pkg, dev, pg, rank, world, exchange, graph, sync_bn):
+    """world > 1, before timing: 2 iterations of a sharded step (this run's exchange / graph mode) must (a) leave
+    bit-identical weights and BatchNorm buffers on every rank and (b) reproduce the SINGLE-process step at the GLOBAL
+    batch (the multi-GPU oracle; replaces nn.DataParallel of Segmentation/main_aug_final.py:119,131)."""
+    dist = torch.distributed
+    per_rank, iters = 32, 2
+    kw = dict(perturb_idx=5, steps=2, gamma=1.0, eps=2.0, randinit=True, clip=True)
+    g = torch.Generator().manual_seed(21)
+    B = per_rank * world
+    images = [torch.rand(B, 3, 32, 32, generator=g) for _ in range(iters)]
+    targets = [torch.randint(0, 10, (B,), generator=g) for _ in range(iters)]
+    noises = [torch.rand(B, 16, 32, 32, generator=g) for _ in range(iters)]
+    torch.manual_seed(3)
+    model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    tr = pkg.trainer.AfanTrainer(model, process_group=pg, sync_bn=sync_bn, use_cuda_graph=graph, bn_exchange=exchange, **kw)
+    sl = slice(rank * per_rank, (rank + 1) * per_rank)
+    losses = []
+    for i in range(iters):
+        out = tr.step(images[i][sl].to(dev), targets[i][sl].to(dev), noises[i][sl].to(dev))
+        l = out["loss"].detach().clone()
+        dist.all_reduce(l)
+        losses.append(float(l) / world)
+    tr.check()
+    sharded = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    flat = torch.cat([v.reshape(-1).double() for v in sharded.values()])
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    identical = bool((lo == hi).all())
+    tr.close()
+    res = {"ranks_bit_identical": identical, "exchange": tr.bn_exchange_used, "graph": graph, "per_rank_batch": per_rank}
+    if sync_bn:                       # per-replica statistics (--no-sync-bn) have no single-process equivalent
+        ref_model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
+        ref_model.load_state_dict(init)
+        ref = pkg.trainer.AfanTrainer(ref_model, use_cuda_graph=False, **kw)
+        ref_losses = [float(ref.step(images[i].to(dev), targets[i].to(dev), noises[i].to(dev))["loss"]) for i in range(iters)]
+        single = ref_model.state_dict()
+        ref.close()
+        worst, ok = ("", 0.0), True
+        for k, v in single.items():
+            if not v.dtype.is_floating_point:
+                ok &= bool((sharded[k] == v).all())
+                continue
+            err = float((sharded[k] - v).abs().max())
+            if err > worst[1]:
+                worst = (k, err)
+            ok &= err <= 2e-4 + 2e-3 * float(v.abs().max())
+        loss_rel = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
+        ok &= loss_rel <= 1e-4
+        res.update({"vs_global_batch_ok": ok, "loss_rel_err": loss_rel, "worst_abs_err": worst[1], "worst_key": worst[0],
+                    "losses": losses, "ref_losses": ref_losses})
+    flag = torch.tensor([1 if (identical and res.get("vs_global_batch_ok", True)) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["status"] = "ok" if int(flag) else "FAIL"
+    return res
+
+
+def parity_iter0(pkg, dev):
+    """N = 1: iteration 0 of the benchmarked workload (full size, injected random start) next to the CPU port of the
+    reference iteration on the same weights / inputs / noise."""
+    from oracle import afan_ref_torch as ref_t
+    w = WORKLOAD
+    torch.manual_seed(3)
+    model = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"])
+    ref = ref_t.CifarResNetRef(w["num_blocks"], w["num_classes"])
+    ref.load_state_dict(model.state_dict())
+    model.to(dev)
+    n = w["batch_per_gpu"]
+    g = torch.Generator().manual_seed(11)
+    x, y = torch.rand(n, *w["image"], generator=g), torch.randint(0, w["num_classes"], (n,), generator=g)
+    noise = torch.rand(n, 16, 32, 32, generator=g)
+    kw = dict(steps=w["steps"], gamma=w["gamma"], eps=w["eps"], perturb_idx=w["perturb_idx"], randinit=True, clip=True)
+    tr = pkg.trainer.AfanTrainer(model, use_cuda_graph=False, **kw)
+    out = tr.step(x.to(dev), y.to(dev), noise.to(dev))
+    got = float(out["loss"])
+    linf = float(out["linf"].max())
+    tr.close()
+    ref.train()
+    opt, crit = ref_t.make_sgd(ref), torch.nn.CrossEntropyLoss()
+    torch.set_num_threads(os.cpu_count() or 1)
+    loss_ref, _, _, linf_ref, _ = ref_t.afan_train_iteration(ref, opt, crit, x, y, noise=noise, **kw)
+    return {"loss": got, "port_loss": float(loss_ref), "rel_err": abs(got - float(loss_ref)) / abs(float(loss_ref)),
+            "linf_max": linf, "port_linf_max": float(linf_ref.max())}
+
+
+def _r(v, nd=4):
+    """Round floats for the compact line."""
+    if isinstance(v, float):
+        return float(f"{v:.{nd}g}") if abs(v) < 1e4 else round(v, 1)
+    if isinstance(v, dict):
+        return {k: _r(x, nd) for k, x in v.items()}
+    if isinstance(v, (list, tuple)):
+        return [_r(x, nd) for x in v]
+    return v
+
+
+def emit(line, detail, args, world):
+    """Full record -> file (gpurun_out/ is scratch; copy to profiles/ to keep); ONE compact JSON line -> stdout (last)."""
+    path = args.detail_file or os.path.join(ROOT, "gpurun_out", f"bench_detail_n{world}.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as f:
+            json.dump({**line, **detail}, f, indent=1)
+        line["detail_file"] = os.path.relpath(path, ROOT)
+    except OSError as e:
+        line["detail_file"] = f"unwritable: {e}"[:60]
+    text = json.dumps(_r(line, 5), separators=(",", ":"))
+    if len(text) > 1400:                  # the driver parses the tail of stdout: never let the line outgrow it
+        for k in ("variants_ms_per_step", "reference_on_gpu_ms", "multi_gpu_parity_err", "parity_iter0", "afan_kernels_per_step",
+                  "roofline_hbm"):
+            if k in line and len(text) > 1400:
+                line.pop(k)
+                text = json.dumps(_r(line, 5), separators=(",", ":"))
+    sys.stdout.flush()
+    print(text, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -427,12 +583,17 @@ def main():
                     help="multi-GPU dual-BN statistics: fused NVLink peer-memory exchange inside the kernel, or NCCL all-reduce")
     ap.add_argument("--conv-math", default="fp32", choices=["fp32", "tf32"],
                     help="cuDNN/cuBLAS math of the (library) convolutions / fc: strict fp32 (headline) or TF32 tensor cores")
-    ap.add_argument("--conv", default="afan", choices=["afan", "cudnn", "3xtf32"],
-                    help="3x3 tail convolutions: hand-written sm_100a kernels (default; strict-fp32 FFMA, or the TF32 "
-                         "tensor-core twin under --conv-math tf32), the cuDNN library path, or the 3xTF32 split kernels")
+    ap.add_argument("--conv", default=None, choices=["afan", "cudnn", "3xtf32", "tc3"],
+                    help="3x3 tail convolutions: hand-written sm_100a kernels (afan = strict-fp32 FFMA, or the mma.sync TF32 "
+                         "twin under --conv-math tf32; tc3 = tcgen05 3xTF32 implicit GEMM), the cuDNN library path, or the "
+                         "mma.sync 3xTF32 split kernels.  Default: the package default (AFAN_CONV)")
+    ap.add_argument("--rng", default="philox", choices=["philox", "injected"],
+                    help="random start: on-device Philox (fast path) or noise injected from the host generator (the reference's)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-variants", action="store_true", help="do not time the TF32 / cuDNN convolution variants of the step")
     ap.add_argument("--skip-rooflines", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true", help="skip the in-bench parity legs (multi_gpu_parity / parity_iter0)")
+    ap.add_argument("--detail-file", default=None, help="where the full record (kernel table, families, ...) is written")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager iteration between cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     args = ap.parse_args()
@@ -459,8 +620,20 @@ def main():
     torch.backends.cudnn.deterministic = os.environ.get("AFAN_BENCH_DET", "1") != "0"   # the reference's setting (main_perturb.py:315): bitwise-reproducible steps
 
     pkg = importlib.import_module("cv_a-fan_b200")
+    if args.conv is None:
+        args.conv = pkg.conv.MODE if pkg.conv.MODE in ("afan", "cudnn", "3xtf32", "tc3") else "afan"
     pkg.conv.MODE = "tf32" if (args.conv == "afan" and args.conv_math == "tf32") else args.conv
     w = WORKLOAD
+    detail = {}
+
+    # (0) parity legs, before any timing
+    parity = None
+    if world > 1 and not args.skip_parity:
+        parity = multi_gpu_parity(pkg, dev, pg, rank, world, args.bn_exchange, not args.no_graph, not args.no_sync_bn)
+        detail["multi_gpu_parity_detail"] = parity
+        if rank == 0:
+            print("MULTI_GPU_CHECK " + json.dumps(_r(parity, 4)), file=sys.stderr, flush=True)
+
     torch.manual_seed(3)                                     # identical weights on every rank
     model = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)
     trainer = pkg.trainer.AfanTrainer(model, perturb_idx=w["perturb_idx"], steps=w["steps"], gamma=w["gamma"],
@@ -471,7 +644,9 @@ def main():
     g = torch.Generator().manual_seed(3 + rank)              # per-rank data
     host_x = [torch.rand(n, *w["image"], generator=g).pin_memory() for _ in range(4)]
     host_y = [torch.randint(0, w["num_classes"], (n,), generator=g).pin_memory() for _ in range(4)]
+    host_u = [torch.rand(n, 16, 32, 32, generator=g).pin_memory() for _ in range(4)] if args.rng == "injected" else None
     dev_x, dev_y = [t.to(dev) for t in host_x], [t.to(dev) for t in host_y]
+    dev_u = [t.to(dev) for t in host_u] if host_u else None
 
     def barrier():
         if world > 1:
@@ -509,50 +684,67 @@ def main():
         return
 
     # (1) device-resident inputs
-    trainer.step(dev_x[0], dev_y[0])                         # builds arena, captures the graph
+    trainer.step(dev_x[0], dev_y[0], dev_u[0] if dev_u else None)       # builds arena, captures the graph
     out = {}
 
     def step_dev(i):
-        out["r"] = trainer.step(dev_x[i % 4], dev_y[i % 4])
+        out["r"] = trainer.step(dev_x[i % 4], dev_y[i % 4], dev_u[i % 4] if dev_u else None)
     sec, clocks = timed_run(step_dev)
     loss_dev = float(out["r"]["loss"])
 
     # (2) end to end: pinned host inputs -> H2D -> step -> D2H loss
     host_loss = torch.zeros(1).pin_memory()
     dx, dy = torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])
+    du = torch.empty_like(dev_u[0]) if dev_u else None
 
     def step_e2e(i):
         dx.copy_(host_x[i % 4], non_blocking=True)
         dy.copy_(host_y[i % 4], non_blocking=True)
-        r = trainer.step(dx, dy)
+        if du is not None:                                   # the reference's CPU-generator random start travels H2D too
+            du.copy_(host_u[i % 4], non_blocking=True)
+        r = trainer.step(dx, dy, du)
         host_loss.copy_(r["loss"].reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()            # the user reads the loss every step (main_perturb.py:208)
     sec_e2e, _ = timed_run(step_e2e)
+    trainer.check()                                          # a timed-out statistics exchange must fail the run, not pass silently
 
     per_iter = trainer.kernel_launches_per_iter      # afan kernels per iteration, counted at capture/trace time
 
     global_batch = n * world
+    h2d = (host_x[0].numel() * 4 + host_y[0].numel() * 8 + (host_u[0].numel() * 4 if host_u else 0)) * world
     line = {"metric": "A-FAN train img/s", "value": global_batch * args.steps / sec, "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(world, args.conv_math, args.conv), "clocks": clocks,
-            "e2e": {"value": global_batch * args.steps / sec_e2e, "unit": "img/s",
-                    "h2d_bytes_per_step": (host_x[0].numel() * 4 + host_y[0].numel() * 8) * world,
+            "config": config_dict(world, args.conv_math, args.conv, args.rng), "clocks": clocks,
+            "e2e": {"value": global_batch * args.steps / sec_e2e, "unit": "img/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * sec_e2e / args.steps},
-            "gpu_launches": per_iter * args.steps, "afan_kernels_per_step": per_iter,
-            "cuda_graph": not args.no_graph, "sync_bn": (not args.no_sync_bn) and world > 1,
-            "bn_exchange": args.bn_exchange if ((not args.no_sync_bn) and world > 1) else None, "final_loss": loss_dev}
+            "gpu_launches": per_iter * args.steps, "afan_kernels_per_step": per_iter}
+    detail.update({"cuda_graph": not args.no_graph, "sync_bn": (not args.no_sync_bn) and world > 1,
+                   "bn_exchange": trainer.bn_exchange_used, "final_loss": loss_dev})
+    if world > 1:
+        line["bn_exchange"] = trainer.bn_exchange_used
+        if parity is not None:
+            line["multi_gpu_parity"] = parity["status"]
+            if "worst_abs_err" in parity:
+                line["multi_gpu_parity_err"] = {"loss_rel": parity["loss_rel_err"], "weights_abs": parity["worst_abs_err"],
+                                                "ranks_bit_identical": parity["ranks_bit_identical"]}
 
     # other convolution paths of the SAME step, for context only (never the headline): single GPU, device-resident inputs
-    if world == 1 and not args.skip_variants and args.conv == "afan" and args.conv_math == "fp32" and not args.no_graph:
+    if world == 1 and not args.skip_variants and args.conv_math == "fp32" and not args.no_graph:
         variants = {}
         det = torch.backends.cudnn.deterministic
-        for vname, mode, tf32 in (("conv_tf32_tensor_core_kernels", "tf32", True), ("conv_cudnn_fp32_nondeterministic", "cudnn", False)):
+        head_mode = pkg.conv.MODE
+        cands = (("afan_fp32_ffma", "afan", False), ("afan_tcgen05_3xtf32", "tc3", False), ("afan_mma_sync_tf32", "tf32", True),
+                 ("cudnn_fp32_nondet", "cudnn", False), ("cudnn_tf32_nondet", "cudnn", True))
+        for vname, mode, tf32 in cands:
+            if mode == head_mode and not tf32:
+                continue
+            if mode == "tc3" and not getattr(pkg.ops, "CONV_TC_AVAILABLE", False):
+                continue
             pkg.conv.MODE = mode
             torch.backends.cudnn.allow_tf32 = tf32
             torch.backends.cuda.matmul.allow_tf32 = tf32
-            # the library path is timed with its fastest (non-deterministic) algorithms: under cudnn.deterministic the same
-            # step takes 25.4 ms
+            # the library path is timed with its fastest (non-deterministic) algorithms
             torch.backends.cudnn.deterministic = det and mode != "cudnn"
             torch.manual_seed(3)
             vm = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)
@@ -560,17 +752,17 @@ def main():
                                          randinit=w["randinit"], clip=w["clip"], rng="philox", seed=3, use_cuda_graph=True)
             vt.step(dev_x[0], dev_y[0])
             vsec, _ = timed_run(lambda i: vt.step(dev_x[i % 4], dev_y[i % 4]))
-            variants[vname] = {"value": n * args.steps / vsec, "unit": "img/s", "ms_per_step": 1e3 * vsec / args.steps}
+            variants[vname] = 1e3 * vsec / args.steps
             vt.close()
             del vm, vt
-        pkg.conv.MODE = "afan"
+        pkg.conv.MODE = head_mode
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.deterministic = det
-        line["variants"] = variants
+        line["variants_ms_per_step"] = variants
 
     if rank == 0 and not args.skip_rooflines:
-        ks, peak_src, ffma_peak = kernel_rooflines(pkg, dev)
+        ks, peak_src, ffma_peak = kernel_rooflines(pkg, dev, in_step_only=world > 1)
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tmap = json.load(f)
@@ -579,7 +771,7 @@ def main():
         for k in ks:
             k["traffic"] = tmap.get(k["kernel"])
         # Roofline per kernel FAMILY (all in-step shapes of a kernel, weighted by their launches in one step):
-        # achieved = algorithmic bytes (HBM-bound families) or FLOPs (the FFMA-bound convolutions) per step / device time
+        # achieved = algorithmic bytes (HBM-bound families) or FLOPs (the convolutions) per step / device time
         # per step.  `roofline` = the family with the largest share of the step; `roofline_hbm` = the largest HBM-bound one.
         step_us = 1e3 * sec / args.steps * 1e3
         fam = {}
@@ -587,7 +779,7 @@ def main():
             if k["launches_per_iter"] > 0:
                 f = fam.setdefault(k["family"], {"bound": k["bound"], "peak": k["peak"], "unit": k["unit"], "work": 0.0, "bytes": 0.0,
                                                  "us": 0.0, "launches": 0, "traffic": 0.0, "traffic_ok": True, "shapes": []})
-                f["work"] += (k["flops"] if k["bound"] == "fp32_ffma" else k["bytes"]) * k["launches_per_iter"]
+                f["work"] += (k["flops"] if k["bound"] != "hbm" else k["bytes"]) * k["launches_per_iter"]
                 f["bytes"] += k["bytes"] * k["launches_per_iter"]
                 f["us"] += k["us"] * k["launches_per_iter"]
                 f["launches"] += k["launches_per_iter"]
@@ -597,54 +789,64 @@ def main():
                 else:
                     f["traffic"] += k["traffic"] * k["launches_per_iter"]
 
-        def fam_line(name, f):
-            scale = 1e12 if f["bound"] == "fp32_ffma" else 1e9
+        def fam_line(name, f, full=False):
+            scale = 1e9 if f["bound"] == "hbm" else 1e12
             achieved = f["work"] / (f["us"] * 1e-6) / scale
-            d = {"bound": f["bound"], "kernel": name, "achieved": achieved, "peak": f["peak"], "unit": f["unit"],
+            d = {"kernel": name, "bound": f["bound"], "achieved": achieved, "peak": f["peak"], "unit": f["unit"],
                  "frac": achieved / f["peak"], "traffic": f["traffic"] / f["launches"] if f["traffic_ok"] else None,
                  "algorithmic_bytes": f["bytes"] / f["launches"], "launches_per_step": f["launches"],
-                 "avg_us_per_launch": f["us"] / f["launches"], "share_of_step": f["us"] / step_us, "shapes": f["shapes"]}
-            if f["bound"] == "fp32_ffma":
-                d["algorithmic_flops"] = f["work"] / f["launches"]
-                d["peak_source"] = ("fp32 FFMA rate measured live by afan_ffma_probe (8x8 outer-product loop, 2 CTAs x 256 "
-                                    "threads per SM) on this device at its current clocks; nominal 148 SMs x 128 lanes x 2 x "
-                                    "1.965 GHz = 74.4 TFLOP/s")
-            else:
-                d["peak_source"] = peak_src
+                 "avg_us": f["us"] / f["launches"], "share_of_step": f["us"] / step_us}
+            if full:
+                d["shapes"] = f["shapes"]
+                d["peak_source"] = peak_src if f["bound"] == "hbm" else k_peak_note(f["bound"])
             return d
-        timing = ("per shape: CUDA events around a graph of back-to-back launches over rotating tensor sets (4x L2, every launch "
-                  "L2-cold), weighted by the launches of that shape in one step; traffic / algorithmic_bytes are per-launch averages")
         dom_name, dom = max(fam.items(), key=lambda kv: kv[1]["us"])
         line["roofline"] = fam_line(dom_name, dom)
-        line["roofline"]["timing"] = timing
-        line["roofline"]["families"] = {n: {k2: v for k2, v in fam_line(n, f).items()
-                                            if k2 in ("bound", "achieved", "peak", "unit", "frac", "share_of_step", "launches_per_step")}
-                                        for n, f in fam.items()}
-        hbm = {n: f for n, f in fam.items() if f["bound"] == "hbm"}
+        hbm = {nm: f for nm, f in fam.items() if f["bound"] == "hbm"}
         if hbm and dom["bound"] != "hbm":
             hn, hf = max(hbm.items(), key=lambda kv: kv[1]["us"])
             line["roofline_hbm"] = fam_line(hn, hf)
-        line["ffma_peak_tflops_measured"] = ffma_peak
-        line["kernels"] = ks
+        detail["roofline_timing"] = ("per shape: CUDA events around a graph of back-to-back launches over rotating tensor sets (4x L2, "
+                                     "every launch L2-cold), weighted by the launches of that shape in one step; traffic / "
+                                     "algorithmic_bytes are per-launch averages")
+        detail["roofline_families"] = {nm: fam_line(nm, f, full=True) for nm, f in fam.items()}
+        detail["ffma_peak_tflops_measured"] = ffma_peak
+        detail["kernels"] = ks
     if world > 1:
         torch.distributed.barrier()
         if not args.no_sync_bn:
-            line["bn_fwd_us_per_call_G1_128x32x16x16"] = exchange_microbench(pkg, dev, trainer.mailbox, pg)
+            detail["bn_fwd_us_per_call_G1_128x32x16x16"] = exchange_microbench(pkg, dev, trainer.mailbox, pg)
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         try:
-            line["reference_on_gpu"] = gpu_reference(dev)
+            r32, rtf = gpu_reference(dev, tf32=False), gpu_reference(dev, tf32=True)
+            detail["reference_on_gpu"] = {"strict_fp32": r32, "stock_tf32_conv": rtf}
+            line["reference_on_gpu_ms"] = {"fp32": r32["ms_per_step"], "tf32_default": rtf["ms_per_step"]}
         except Exception as exc:                     # context number only: never fail the bench line over it
-            line["reference_on_gpu"] = {"error": repr(exc)[:200]}
+            detail["reference_on_gpu"] = {"error": repr(exc)[:200]}
+        if not args.skip_parity:
+            try:
+                line["parity_iter0"] = parity_iter0(pkg, dev)
+            except Exception as exc:
+                line["parity_iter0"] = {"error": repr(exc)[:120]}
         cb = cpu_reference(steps=4, warmup=1)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {"value": cb["value"], "unit": cb["unit"], "cores": cb["cores"], "kind": cb["kind"],
+                                "sample": f"4 iterations of this workload, batch {n}"}
+        detail["cpu_baseline_detail"] = cb
     if rank == 0:
-        print(json.dumps(line))
+        emit(line, detail, args, world)
     if world > 1:
         trainer.close()                      # a live graph with captured NCCL ops blocks communicator teardown
         torch.distributed.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
-        os._exit(0)
+        os._exit(0 if (parity is None or parity["status"] == "ok") else 3)
+
+
+def k_peak_note(bound):
+    if bound == "fp32_ffma":
+        return ("fp32 FFMA rate measured live by afan_ffma_probe (8x8 outer-product loop, 2 CTAs x 256 threads per SM) on this "
+                "device at its current clocks; nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s")
+    return "tensor: MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate; no measured TF32 peak exists)"
 
 
 if __name__ == "__main__":

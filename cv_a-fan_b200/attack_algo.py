@@ -7,7 +7,7 @@ Same names, positional order, defaults and return semantics as the reference:
 x_adv is returned as a LEAF tensor with requires_grad=True on x's device, like the reference's
 `Variable(x_adv, requires_grad=True)`.  Inside, every per-step elementwise span of the reference
 (sign, mul, add_, sub, add, lt, gt, nonzero, index, index_put_: 13 launches + 4 host syncs) is ONE
-launch of the fused sm_100a kernel; results are bit-identical (tests/test_pgd_parity.py).
+launch of the fused sm_100a kernel; results are bit-identical (tests/test_gpu_pgd.py).
 
 Keyword-only extras (defaults reproduce the reference):
     noise        the U[0,1) draw for the random start.  None -> torch.rand(x.shape) on the CPU generator,

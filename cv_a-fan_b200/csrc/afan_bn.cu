@@ -18,6 +18,7 @@
 // the 126 MB L2 for every shape in BASELINE.json's configs.  bwd: 12 algorithmic (+4 for y if relu).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "afan_common.cuh"
@@ -647,13 +648,18 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
 // -----------------------------------------------------------------------------------------------------
 constexpr int kP2PMaxWorld = 8;
 constexpr int kP2PRing = 4;
-constexpr long long kP2PTimeoutCycles = 4000000000LL;      // ~2 s: a lost peer sets state[2] instead of hanging the GPU
+// A lost peer must neither hang the GPU nor go unnoticed: after `timeout_cycles` (AFAN_P2P_TIMEOUT_S, default 60 s --
+// the bound on tolerated inter-rank skew, e.g. rank 0 writing a checkpoint) the waiting rank sets state[2] AND poisons
+// the folded statistics with NaN, so every later loss on that rank is NaN instead of silently wrong.
+constexpr double kP2PDefaultTimeoutS = 60.0;
+constexpr double kP2PCyclesPerSecond = 1.9e9;
 
 struct P2PParams {
     void* peers[kP2PMaxWorld];        // peer-mapped mailbox base of every rank (peers[rank] = own mailbox)
     unsigned long long* state;        // local: {seq, ticket, error}
     int world, rank;
     unsigned int cmax;
+    long long timeout_cycles;
 };
 
 // LL-style in-band flags (the idea of NCCL's low-latency protocol): every double travels as one 16-byte word
@@ -714,7 +720,11 @@ __device__ __forceinline__ double2 cluster_fold_p2p(cg::cluster_group& cluster, 
             const long long t0 = clock64();
             uint4 r = ld_sys_u32x4(src);
             while (r.y != tag || r.w != tag) {
-                if (clock64() - t0 > kP2PTimeoutCycles) { q.state[2] = 1ULL; break; }     // peer lost: flag it, never hang
+                if (clock64() - t0 > q.timeout_cycles) {                                  // peer lost: never hang, never pass silently
+                    q.state[2] = 1ULL;
+                    r.x = 0u; r.z = 0x7ff80000u;                                          // quiet NaN poisons this layer's statistics
+                    break;
+                }
                 r = ld_sys_u32x4(src);
             }
             s_recv[peer][g][k] = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(r.z) << 32) | r.x));
@@ -1386,6 +1396,13 @@ static int fill_p2p(P2PParams& q, int world, int rank, void* const* peer_mailbox
     }
     q.state = static_cast<unsigned long long*>(state);
     q.world = world; q.rank = rank; q.cmax = static_cast<unsigned int>(cmax);
+    static const long long timeout = [] {
+        const char* e = std::getenv("AFAN_P2P_TIMEOUT_S");
+        double sec = e ? std::atof(e) : kP2PDefaultTimeoutS;
+        if (!(sec > 0.0)) sec = kP2PDefaultTimeoutS;
+        return static_cast<long long>(sec * kP2PCyclesPerSecond);
+    }();
+    q.timeout_cycles = timeout;
     return AFAN_OK;
 }
 

@@ -3,7 +3,7 @@
 Identical hot-path flags and defaults (main_perturb.py:28-49): --steps 5 --perturb_idx 13 --gamma 1.5
 --eps 2 --randinit --clip, plus the base / optimiser flags (--batch_size --lr --momentum --weight_decay
 --epochs --decreasing_lr --seed --gpu --print_freq --save_dir --resume).  Extras: --norm {linf,l2},
---rng {philox,reference}, --no_graph, --no_head_cache, --num_classes, --arch, --synthetic N (no dataset on
+--rng {reference,philox}, --no_graph, --no_head_cache, --num_classes, --arch, --synthetic N (no dataset on
 this box: N synthetic CIFAR-shaped batches per epoch), --bench.
 
     python -m torch.distributed.run --nproc-per-node 8 -m afan_b200.main_perturb --synthetic 50 ...   # data parallel
@@ -47,10 +47,12 @@ def build_parser():
     p.add_argument("--clip", action="store_true", help="whether using clip")
     # extras of this implementation
     p.add_argument("--norm", default="linf", choices=["linf", "l2"])
-    p.add_argument("--rng", default="philox", choices=["philox", "reference"])
-    p.add_argument("--conv_math", default="fp32", choices=["fp32", "tf32", "3xtf32", "cudnn"],
-                   help="3x3 convolutions: hand-written strict-fp32 kernels (default), their TF32 / 3xTF32 tensor-core twins, "
-                        "or the cuDNN library path")
+    p.add_argument("--rng", default="reference", choices=["philox", "reference"],
+                   help="random start (--randinit): 'reference' = torch.rand on the CPU generator + H2D like attack_algo.py:44 "
+                        "(default, same stream as the reference under the same seed); 'philox' = on-device generator")
+    p.add_argument("--conv_math", default="fp32", choices=["fp32", "tf32", "3xtf32", "tc3", "cudnn"],
+                   help="3x3 convolutions: hand-written strict-fp32 kernels (default), their mma.sync TF32 / 3xTF32 twins, "
+                        "the tcgen05 3xTF32 implicit GEMM (tc3), or the cuDNN library path")
     p.add_argument("--no_graph", action="store_true")
     p.add_argument("--no_head_cache", action="store_true")
     p.add_argument("--no_sync_bn", action="store_true")
@@ -88,15 +90,68 @@ def synthetic_loader(n_batches, batch, num_classes, seed, device):
                torch.randint(0, num_classes, (batch,), generator=g).to(device, non_blocking=True))
 
 
-def cifar_loader(args, train, device):
-    import torchvision
-    import torchvision.transforms as T
-    tf = T.Compose([T.RandomCrop(32, padding=4), T.RandomHorizontalFlip(), T.ToTensor()]) if train else T.ToTensor()
-    ds = torchvision.datasets.CIFAR10(args.data, train=train, transform=tf, download=False)
-    dl = torch.utils.data.DataLoader(ds, batch_size=args.batch_size, shuffle=train, num_workers=2, pin_memory=True,
-                                     drop_last=train)
-    for x, y in dl:
+class CifarLoaders:
+    """The reference's splits (Classification/dataset.py:34-55): train = first 45000 training images (augmented, shuffled,
+    drop_last), val = training images 45000..49999, test = the 10000 test images.  Data parallel: the TRAIN split is
+    sharded with a DistributedSampler (every rank sees 1/world of each epoch, reshuffled per epoch); val / test are
+    evaluated in full on every rank (identical weights -> identical numbers, no collective)."""
+
+    def __init__(self, args, rank, world):
+        import torchvision
+        import torchvision.transforms as T
+        from torch.utils.data import DataLoader, Subset
+        from torch.utils.data.distributed import DistributedSampler
+        aug = T.Compose([T.RandomCrop(32, padding=4), T.RandomHorizontalFlip(), T.ToTensor()])
+        cifar = torchvision.datasets.CIFAR100 if args.num_classes == 100 else torchvision.datasets.CIFAR10
+        train = Subset(cifar(args.data, train=True, transform=aug, download=False), list(range(45000)))
+        val = Subset(cifar(args.data, train=True, transform=T.ToTensor(), download=False), list(range(45000, 50000)))
+        test = cifar(args.data, train=False, transform=T.ToTensor(), download=False)
+        self.sampler = DistributedSampler(train, num_replicas=world, rank=rank, shuffle=True, drop_last=True,
+                                          seed=args.seed or 0) if world > 1 else None
+        self.train = DataLoader(train, batch_size=args.batch_size, shuffle=self.sampler is None, sampler=self.sampler,
+                                num_workers=2, pin_memory=True, drop_last=True)
+        self.val = DataLoader(val, batch_size=args.batch_size, shuffle=False, num_workers=2, pin_memory=True)
+        self.test = DataLoader(test, batch_size=args.batch_size, shuffle=False, num_workers=2, pin_memory=True)
+
+    def set_epoch(self, epoch):
+        if self.sampler is not None:
+            self.sampler.set_epoch(epoch)
+
+
+def to_device(loader, device):
+    for x, y in loader:
         yield x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+
+
+def validate(trainer, loader, print_freq, tag, rank):
+    """main_perturb.py:227-262: eval-mode top-1 / mean loss, sample-weighted; one host sync per print_freq batches."""
+    loss_sum = torch.zeros((), device=trainer.device)
+    correct = torch.zeros((), device=trainer.device)
+    seen = 0
+    n = None
+    try:
+        n = len(loader)
+    except TypeError:
+        pass
+    for i, (x, y) in enumerate(loader):
+        loss, out = trainer.evaluate(x, y)
+        loss_sum += loss * x.shape[0]
+        correct += (out.argmax(1) == y).sum()
+        seen += x.shape[0]
+        if i % print_freq == 0 and rank == 0:
+            print(f"{tag}: [{i}/{n}]\tLoss {float(loss):.4f} ({float(loss_sum) / seen:.4f})\t"
+                  f"Accuracy ({100.0 * float(correct) / seen:.3f})")
+    acc = 100.0 * float(correct) / max(seen, 1)
+    if rank == 0:
+        print(f"valid_accuracy {acc:.3f}")
+    return acc, float(loss_sum) / max(seen, 1)
+
+
+def scheduler_state(milestones, gamma, base_lr, epoch_done, lr_now):
+    """A state dict torch.optim.lr_scheduler.MultiStepLR.load_state_dict accepts (main_perturb.py:86,133)."""
+    from collections import Counter
+    return {"milestones": Counter(milestones), "gamma": gamma, "base_lrs": [base_lr], "last_epoch": epoch_done,
+            "_step_count": epoch_done + 1, "_get_lr_called_within_step": False, "_last_lr": [lr_now]}
 
 
 def main(argv=None):
@@ -112,54 +167,91 @@ def main(argv=None):
         torch.distributed.init_process_group("nccl", device_id=device)
         pg = torch.distributed.group.WORLD
     if args.seed:
-        setup_seed(args.seed)
-    conv.MODE = {"fp32": "afan", "tf32": "tf32", "3xtf32": "3xtf32", "cudnn": "cudnn"}[args.conv_math]
+        setup_seed(args.seed)            # same seed on every rank: identical initial weights; data differs via the sampler
+    conv.MODE = {"fp32": "afan", "tf32": "tf32", "3xtf32": "3xtf32", "tc3": "tc3", "cudnn": "cudnn"}[args.conv_math]
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = args.conv_math == "tf32"
     model = (resnet_s.resnet56(num_classes=args.num_classes) if args.arch == "resnet56"
              else resnet_s.resnet20(num_classes=args.num_classes)).to(device)
     trainer = AfanTrainer(model, perturb_idx=args.perturb_idx, steps=args.steps, gamma=args.gamma, eps=args.eps,
                           randinit=args.randinit, clip=args.clip, lr=args.lr, momentum=args.momentum,
-                          weight_decay=args.weight_decay, norm=args.norm, rng=args.rng, seed=(args.seed or 0) + rank,
+                          weight_decay=args.weight_decay, norm=args.norm, rng="philox", seed=(args.seed or 0) + rank,
                           process_group=pg, sync_bn=not args.no_sync_bn, head_cache=not args.no_head_cache,
                           use_cuda_graph=not args.no_graph)
     milestones = list(map(int, args.decreasing_lr.split(",")))
     os.makedirs(args.save_dir, exist_ok=True)
     start_epoch, best_prec1 = 0, 0.0
     ckpt_path = os.path.join(args.save_dir, "checkpoint.pt")
-    if args.resume and os.path.exists(ckpt_path):
-        ck = torch.load(ckpt_path, map_location=device)
+    if args.resume:
+        if rank == 0:
+            print("resume from checkpoint")
+        ck = torch.load(ckpt_path, map_location=device, weights_only=False)
+        best_prec1, start_epoch = ck["best_prec1"], ck["epoch"]
         model.load_state_dict(ck["state_dict"])
-        start_epoch, best_prec1 = ck["epoch"], ck["best_prec1"]
-        if "momentum_buffer" in ck and trainer._arena_built:
-            trainer.flat_buf.copy_(ck["momentum_buffer"])
-    all_norm = {"l2": {}, "linf": {}}
+        trainer.load_optimizer_state_dict(ck["optimizer"])       # momentum buffers: applied once the arena exists
+    # the reference draws the random start on the CPU generator and copies it H2D (attack_algo.py:44): that is the
+    # default here too (--rng reference); --rng philox is the on-device fast path (distributionally equal only)
+    noise_shape = None
+    if args.randinit and args.rng == "reference":
+        with torch.no_grad():
+            was = model.training
+            model.eval()
+            noise_shape = tuple(model(torch.zeros(1, 3, 32, 32, device=device), end_point=args.perturb_idx).shape[1:])
+            model.train(was)
+    loaders = None if args.synthetic else CifarLoaders(args, rank, world)
+    all_norm, all_result = {"l2": {}, "linf": {}}, {"train": [], "ta": [], "test_ta": []}
     for epoch in range(start_epoch, args.epochs):
         base_lr = multistep_lr(epoch, args.lr, milestones)
-        n_batches = args.synthetic if args.synthetic else None
-        loader = (synthetic_loader(args.synthetic, args.batch_size, args.num_classes, 1000 * epoch + rank, device)
-                  if args.synthetic else cifar_loader(args, True, device))
-        wp_steps = args.synthetic if args.synthetic else 50000 // (args.batch_size * world)
+        if rank == 0:
+            print(base_lr)
+        if loaders is None:
+            loader = synthetic_loader(args.synthetic, args.batch_size, args.num_classes, 1000 * epoch + rank, device)
+            n_batches = args.synthetic
+        else:
+            loaders.set_epoch(epoch)
+            loader, n_batches = to_device(loaders.train, device), len(loaders.train)
+        wp_steps = n_batches                                             # main_perturb.py:160 `len(train_loader)`
         t0, seen = time.time(), 0
-        l2s, linfs, loss_sum, acc_sum, count = [], [], 0.0, 0.0, 0
+        l2s, linfs = [], []
+        loss_sum = torch.zeros((), device=device)
+        correct = torch.zeros((), device=device)
         for i, (x, y) in enumerate(loader):
             trainer.set_lr(warmup_lr(i, wp_steps, args.lr) if epoch == 0 else base_lr)     # :167-168
-            out = trainer.step(x, y)
+            noise = torch.rand((x.shape[0],) + noise_shape).pin_memory().to(device, non_blocking=True) if noise_shape else None
+            out = trainer.step(x, y, noise)
             l2s.append(out["l2"].clone()); linfs.append(out["linf"].clone())
-            seen += x.shape[0] * world
+            loss_sum += out["loss"] * x.shape[0]
+            correct += (out["output_clean"].argmax(1) == y).sum()
+            seen += x.shape[0]
             if i % args.print_freq == 0:                                                   # the only host sync
-                loss, prec = float(out["loss"]), float(accuracy(out["output_clean"], y))
-                loss_sum += loss; acc_sum += prec; count += 1
+                trainer.check()                                                            # lost peer in the BN exchange -> raise
                 if rank == 0:
-                    print(f"Epoch: [{epoch}][{i}/{n_batches}]\tLoss {loss:.4f}\tAccuracy {prec:.3f}\t"
-                          f"{seen / (time.time() - t0):.0f} img/s")
+                    print(f"Epoch: [{epoch}][{i}/{n_batches}]\tLoss {float(out['loss']):.4f} ({float(loss_sum) / seen:.4f})\t"
+                          f"Accuracy {float(accuracy(out['output_clean'], y)):.3f} ({100.0 * float(correct) / seen:.3f})\t"
+                          f"{seen * world / (time.time() - t0):.0f} img/s")
+        train_acc = 100.0 * float(correct) / max(seen, 1)
         all_norm["l2"][epoch + 1] = float(torch.cat(l2s).mean()) if l2s else 0.0
         all_norm["linf"][epoch + 1] = float(torch.cat(linfs).mean()) if linfs else 0.0
         if rank == 0:
-            print(f"l2 mean = {all_norm['l2'][epoch + 1]}\nlinf mean = {all_norm['linf'][epoch + 1]}")
-            state = {"epoch": epoch + 1, "state_dict": model.state_dict(), "best_prec1": best_prec1}
-            if trainer._arena_built:
-                state["momentum_buffer"] = trainer.flat_buf.clone()
-            torch.save(state, ckpt_path)
+            print(f"train_accuracy {train_acc:.3f}\nl2 mean = {all_norm['l2'][epoch + 1]}\nlinf mean = {all_norm['linf'][epoch + 1]}")
+        if loaders is None:                                               # synthetic data: a held-out synthetic batch set
+            val = list(synthetic_loader(max(1, args.synthetic // 8), args.batch_size, args.num_classes, 7, device))
+            test = list(synthetic_loader(max(1, args.synthetic // 8), args.batch_size, args.num_classes, 8, device))
+        else:
+            val, test = to_device(loaders.val, device), to_device(loaders.test, device)
+        tacc, _ = validate(trainer, val, args.print_freq, "Test", rank)                   # :106
+        test_tacc, _ = validate(trainer, test, args.print_freq, "Test", rank)             # :109
+        all_result["train"].append(train_acc); all_result["ta"].append(tacc); all_result["test_ta"].append(test_tacc)
+        is_best = tacc > best_prec1
+        best_prec1 = max(tacc, best_prec1)
+        if rank == 0:
+            lr_next = multistep_lr(epoch + 1, args.lr, milestones)
+            state = {"epoch": epoch + 1, "state_dict": model.state_dict(), "best_prec1": best_prec1,
+                     "optimizer": trainer.optimizer_state_dict(lr=lr_next),
+                     "scheduler": scheduler_state(milestones, 0.1, args.lr, epoch + 1, lr_next)}
+            if is_best:
+                torch.save(state, os.path.join(args.save_dir, "best_model.pt"))           # :122-129
+            torch.save(state, ckpt_path)                                                  # :131-137
+            pickle.dump(all_result, open(os.path.join(args.save_dir, "result.pkl"), "wb"))
             pickle.dump(all_norm, open(os.path.join(args.save_dir, "result_norm.pkl"), "wb"))
     trainer.close()
     return trainer

@@ -47,7 +47,9 @@ class AfanTrainer:
         if self.device.type != "cuda":
             raise AfanError("AfanTrainer needs the model on a CUDA device: there is no CPU path")
         self.mailbox = None
+        self.bn_exchange_used = None                 # "p2p" | "nccl" | None (single process / per-replica statistics)
         if sync_bn and self.world > 1:
+            self.bn_exchange_used = bn_exchange
             if bn_exchange == "p2p":                 # fused exchange over NVLink peer memory inside the BN kernels
                 from .p2p import PeerMailbox
                 cmax = max(m.num_features for m in model.modules() if isinstance(m, DualBatchNorm2d))
@@ -63,6 +65,7 @@ class AfanTrainer:
                     warnings.warn("afan_b200: peer-mapped mailboxes unavailable on some rank; dual-BN statistics fall "
                                   "back to NCCL all-reduce (stats -> all-reduce -> finalize -> apply)")
                     self.mailbox = None
+                    self.bn_exchange_used = "nccl"
             elif bn_exchange != "nccl":
                 raise AfanError(f"bn_exchange must be 'p2p' or 'nccl', got {bn_exchange!r}")
             for m in model.modules():
@@ -73,6 +76,7 @@ class AfanTrainer:
         self._lr = float(lr)
         self.rng_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._arena_built = False
+        self._pending_opt_state = None
         self._graph = None
         self._static = {}
         self._bn = [m for m in model.modules() if isinstance(m, DualBatchNorm2d)]
@@ -80,6 +84,48 @@ class AfanTrainer:
         self._conv_pack = conv.PackPlan(model)     # one-launch weight repack for the hand-written 3x3 convolutions
         self.iterations = 0
         self.kernel_launches_per_iter = None       # afan kernels per iteration (counted at trace time)
+
+    # ---- optimizer state in torch.optim.SGD's format (main_perturb.py:85,119-136 checkpoints) ----------------
+    def optimizer_state_dict(self, lr: Optional[float] = None):
+        """What `torch.optim.SGD(model.parameters(), ...).state_dict()` holds: momentum buffers keyed by the parameter's
+        index in model.parameters() (parameters that never received a gradient, e.g. resnet_s.py:113 `w`, have no state,
+        as under torch.optim.SGD) + one param group.  The reference can load_state_dict() it and vice versa."""
+        params = list(self.model.parameters())
+        state = {}
+        if self._arena_built:
+            index = {id(p): i for i, p in enumerate(params)}
+            off = 0
+            for p in self._params:
+                k = p.numel()
+                state[index[id(p)]] = {"momentum_buffer": self.flat_buf[off:off + k].view_as(p.data).clone()}
+                off += k
+        elif self._pending_opt_state is not None:
+            state = self._pending_opt_state["state"]
+        group = {"lr": self._lr if lr is None else float(lr), "momentum": self.momentum, "dampening": 0,
+                 "weight_decay": self.weight_decay, "nesterov": False, "maximize": False, "foreach": None,
+                 "differentiable": False, "fused": None, "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        """Accepts the reference's `optimizer.state_dict()`.  The arena is built on the first step(), so the buffers are
+        stashed until then (a resume must not silently reset momentum)."""
+        if "param_groups" in sd and sd["param_groups"]:
+            self.set_lr(float(sd["param_groups"][0].get("lr", self._lr)))
+        if self._arena_built:
+            self._apply_optimizer_state(sd)
+        else:
+            self._pending_opt_state = sd
+
+    def _apply_optimizer_state(self, sd):
+        params = list(self.model.parameters())
+        index = {id(p): i for i, p in enumerate(params)}
+        off = 0
+        for p in self._params:
+            k = p.numel()
+            st = sd["state"].get(index[id(p)])
+            if st is not None and st.get("momentum_buffer") is not None:
+                self.flat_buf[off:off + k].copy_(st["momentum_buffer"].reshape(-1))
+            off += k
 
     # ---- learning rate lives on the device so a captured graph follows the schedule --------------
     def set_lr(self, lr: float):
@@ -103,6 +149,9 @@ class AfanTrainer:
             off += k
         self._params = used
         self._arena_built = True
+        if self._pending_opt_state is not None:        # --resume: momentum buffers loaded before the arena existed
+            self._apply_optimizer_state(self._pending_opt_state)
+            self._pending_opt_state = None
         # the arena is zeroed before every backward: gradient kernels may write straight into it.  Convolution weight
         # gradients ADD (safe for any number of uses); BatchNorm d(weight)/d(bias) are STORED, which needs the layer to
         # run exactly once per differentiated pass -- true for the head-cached [adv; clean] schedule of this trainer.
@@ -259,6 +308,13 @@ class AfanTrainer:
         self._bn_per_iter = [m._pending_batches - p0 for m, p0 in zip(self._bn, pend0)]
         for m, p0 in zip(self._bn, pend0):
             m._pending_batches = p0                 # capture records launches, it does not run them
+
+    def check(self):
+        """Raise if a fused BN statistics exchange timed out on this rank (synchronises the device).  The kernels already
+        poison the statistics with NaN on a timeout; this turns the condition into an exception.  Call it wherever the
+        host synchronises anyway (main_perturb does at every print_freq; bench.py after each timed region)."""
+        if self.mailbox is not None:
+            self.mailbox.check()
 
     def close(self):
         """Drop the captured graph (it pins NCCL communicator resources: destroy_process_group() blocks

@@ -177,7 +177,9 @@ int afan_bn_bwd_apply_f32(const float* dy, const float* x, const float* y, float
  *   peer_mailboxes: HOST array of `world` device pointers, [i] = rank i's mailbox mapped into this process
  *                   (afan_p2p_* below); each mailbox is afan_bn_mailbox_bytes(world, cmax) bytes, zeroed.
  *   state:          LOCAL device memory, 3 x uint64 {call sequence, ticket, error}, zeroed once.  error != 0
- *                   after a launch means a peer did not arrive within ~2 s (the kernel never hangs).
+ *                   after a launch means a peer did not arrive within AFAN_P2P_TIMEOUT_S seconds (environment,
+ *                   default 60: the tolerated inter-rank skew).  The kernel never hangs; on a timeout it also folds
+ *                   NaN into the statistics so the failure cannot pass silently.
  * Every rank must issue the same sequence of calls.  AFAN_ERR_UNSUPPORTED (shape does not fit the
  * register-resident cluster kernel) is returned identically on all ranks: fall back to the split form. */
 int64_t afan_bn_mailbox_bytes(int world, int64_t cmax);

@@ -15,6 +15,7 @@ we hand PGD a "model" whose output is a scalar with a prescribed gradient (inclu
 +-inf, denormals) and `loss_fn = lambda out, y: out`.
 """
 import argparse
+import json
 import os
 import sys
 
@@ -309,6 +310,45 @@ def gen_train_cases():
         print(name, "ce:", per_iter[-1], "l2/linf mean:", float(l2m), float(linfm))
 
 
+from full_case import FULL_RECIPE, full_case_inputs  # noqa: E402
+
+
+def gen_train_full_case():
+    """BASELINE configs[1] at FULL size: ResNet-56 / 100 classes / batch 128 / PGD-5 / perturb_idx 13 /
+    rand + clip, two iterations of the unmodified reference loop (Classification/main_perturb.py:153-225).  Inputs come from
+    seeds (full_case_inputs), initial weights from torch.manual_seed(3) (the product model reproduces the reference init
+    stream: tests/test_host_logic.py; a checksum guards it).  Stored: every CE value, the norm means, the full small final
+    tensors and every 8th element of the large ones."""
+    r = FULL_RECIPE
+    rs = ref_shim.load("Classification", "resnet_s")
+    mp = ref_shim.load("Classification", "main_perturb")
+    torch.manual_seed(r["weight_seed"])
+    model = rs.ResNet(rs.BasicBlock, r["num_blocks"], num_classes=r["num_classes"])
+    init_sum = float(sum(v.double().sum() for v in model.state_dict().values()))
+    images, targets, noises = full_case_inputs(r)
+    # the reference draws torch.rand(x.shape) from the GLOBAL CPU generator (attack_algo.py:44): seed it like noise_seed
+    torch.manual_seed(r["noise_seed"])
+    mp.args = argparse.Namespace(perturb_idx=r["perturb_idx"], steps=r["steps"], gamma=r["gamma"], eps=r["eps"],
+                                 randinit=True, clip=True, print_freq=10 ** 9, lr=0.1)
+    mp.layer_number = len(model.sequential_model)
+    crit = _RecordingCE()
+    opt = torch.optim.SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=5e-4)
+    with ref_shim.cpu_cuda_identity():
+        top1, loss_avg, l2m, linfm = mp.train(list(zip(images, targets)), model, crit, opt, r["epoch"])
+    per_iter = np.array(crit.values, dtype=np.float64).reshape(r["iters"], r["steps"] + 2)
+    out = {"recipe": np.array(json.dumps(r)), "init_checksum": np.float64(init_sum), "ce_values": per_iter,
+           "top1_avg": np.float64(top1), "loss_avg": np.float64(loss_avg), "l2_mean": np.float64(l2m),
+           "linf_mean": np.float64(linfm), "noise_checksum": np.float64(sum(float(n.double().sum()) for n in noises))}
+    for k, v in model.state_dict().items():
+        a = v.detach().numpy()
+        if a.size <= 7000:
+            out["final/" + k] = a
+        else:
+            out["final_sub/" + k] = a.reshape(-1)[::r["sub"]].copy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "cls_train_full.npz"), **out)
+    print("cls_train_full ce:", per_iter, "l2/linf mean:", float(l2m), float(linfm))
+
+
 def gen_learnable_case():
     """Execute the unmodified reference learnable-eta loop (Classification/main_learnable.py:175-300) on a
     [3,3,3] net (16 layers) with 9 perturbation layers 4..12.  Initial weights are NOT stored: the product model
@@ -356,13 +396,15 @@ def gen_nms_case():
 if __name__ == "__main__":
     assert ref_shim.available(), "reference not mounted; goldens can only be generated where it is"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    which = sys.argv[1:] or ["pgd", "helpers", "train", "f1", "learnable", "nms"]
+    which = sys.argv[1:] or ["pgd", "helpers", "train", "train_full", "f1", "learnable", "nms"]
     if "pgd" in which:
         gen_pgd_cases()
     if "helpers" in which:
         gen_helper_cases()
     if "train" in which:
         gen_train_cases()
+    if "train_full" in which:
+        gen_train_full_case()
     if "f1" in which:
         gen_f1_cases()
     if "learnable" in which:

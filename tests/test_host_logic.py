@@ -158,3 +158,64 @@ def test_stat_arena_replay_equals_repeated_batchnorm_updates():
             assert int(b.num_batches_tracked) == int(r.num_batches_tracked)
     with pytest.raises(PKG.AfanError):
         PKG.trainer_seg._StatArena([torch.nn.BatchNorm2d(2, momentum=0.1), torch.nn.BatchNorm2d(2, momentum=0.01)], torch.device("cpu"))
+
+
+def test_alias_package_shares_module_objects_with_the_real_package():
+    """ADVICE r1 (high): `python -m afan_b200.main_perturb` must see the SAME trainer / dual_bn classes as the model's
+    modules -- a second copy makes every isinstance(m, DualBatchNorm2d) in the trainer fail silently."""
+    import runpy
+    sys.path.insert(0, ROOT)
+    import afan_b200
+    assert afan_b200 is PKG
+    ns = runpy.run_module("afan_b200.main_perturb", run_name="not_main")        # what `python -m` executes
+    assert ns["AfanTrainer"] is PKG.trainer.AfanTrainer
+    assert ns["resnet_s"] is PKG.resnet_s and ns["conv"] is PKG.conv
+    import afan_b200.dual_bn as alias_dual_bn
+    assert alias_dual_bn.DualBatchNorm2d is PKG.dual_bn.DualBatchNorm2d
+    model = ns["resnet_s"].resnet20()
+    assert sum(isinstance(m, PKG.dual_bn.DualBatchNorm2d) for m in model.modules()) == 19
+
+
+def test_scheduler_state_loads_into_the_reference_scheduler():
+    """main_perturb.py:86 `scheduler.load_state_dict(checkpoint['scheduler'])` must accept our checkpoint."""
+    mpf = PKG.main_perturb
+    opt = torch.optim.SGD(torch.nn.Linear(1, 1).parameters(), 0.1)
+    sch = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[50, 150], gamma=0.1)
+    sch.load_state_dict(mpf.scheduler_state([50, 150], 0.1, 0.1, 60, 0.01))
+    assert sch.last_epoch == 60 and sch.get_last_lr() == [0.01]
+    opt.step(); sch.step()
+    assert sch.last_epoch == 61
+
+
+def test_bench_line_stays_parseable_from_a_short_stdout_tail(tmp_path, capsys):
+    """VERDICT r1 #1: the driver keeps only the tail of stdout -- the final line must be ONE compact JSON object."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    fam = {"kernel": "conv3x3 fwd/dgrad", "bound": "tensor", "achieved": 123.456789, "peak": 819.55, "unit": "TFLOP/s",
+           "frac": 0.150641, "traffic": 4200000.0, "algorithmic_bytes": 4204000.0, "launches_per_step": 444,
+           "avg_us": 8.123456, "share_of_step": 0.41234}
+    line = {"metric": "A-FAN train img/s", "value": 12345.678901, "unit": "img/s", "n_gpus": 8, "steps": 20, "warmup": 5,
+            "ms_per_step": 10.123456789, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": bench.config_dict(8), "clocks": {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0,
+            "reasons": ["sw_power_cap"], "samples": 31},
+            "e2e": {"value": 12000.123, "unit": "img/s", "h2d_bytes_per_step": 12591104, "d2h_bytes_per_step": 32, "ms_per_step": 10.5},
+            "gpu_launches": 21100, "afan_kernels_per_step": 1055, "bn_exchange": "p2p", "multi_gpu_parity": "ok",
+            "multi_gpu_parity_err": {"loss_rel": 1.2e-6, "weights_abs": 3.4e-6, "ranks_bit_identical": True},
+            "variants_ms_per_step": {"afan_fp32_ffma": 15.1, "afan_mma_sync_tf32": 10.4, "cudnn_fp32_nondet": 19.3, "cudnn_tf32_nondet": 12.0},
+            "roofline": fam, "roofline_hbm": dict(fam, kernel="dual_bn bwd+relu", bound="hbm", unit="GB/s"),
+            "reference_on_gpu_ms": {"fp32": 52.1, "tf32_default": 40.2},
+            "parity_iter0": {"loss": 4.7123, "port_loss": 4.7124, "rel_err": 2e-5, "linf_max": 0.00784, "port_linf_max": 0.00784},
+            "cpu_baseline": {"value": 337.0, "unit": "img/s", "cores": 16, "kind": "port",
+                             "sample": "4 full iterations of this workload, batch 128, oracle port, 16 threads"}}
+
+    class A:
+        detail_file = str(tmp_path / "detail.json")
+    bench.emit(line, {"kernels": [{"x": 1}] * 50}, A, 8)
+    out = capsys.readouterr().out.strip().splitlines()
+    assert len(out) == 1 and len(out[0]) <= 1400, len(out[0])
+    parsed = json.loads(out[0][-1400:])
+    for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "e2e", "roofline", "cpu_baseline", "clocks", "gpu_launches", "config"):
+        assert k in parsed, k
+    assert parsed["value"] > 0 and parsed["e2e"]["value"] > 0
+    assert json.load(open(A.detail_file))["kernels"]

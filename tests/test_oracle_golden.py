@@ -155,6 +155,45 @@ def test_torch_port_replays_reference_training(golden_dir, name):
             np.testing.assert_allclose(v.numpy(), final[k], rtol=2e-3, atol=2e-5, err_msg=k)
 
 
+def test_torch_port_replays_reference_training_at_full_size(golden_dir):
+    """the port pinned at the BENCHMARKED scale -- ResNet-56 / 100 classes / batch 128 / PGD-5 /
+    perturb_idx 13 / rand + clip, two iterations of the unmodified reference loop (tests/golden/cls_train_full.npz;
+    inputs regenerated from seeds by oracle/full_case.py)."""
+    import json
+    from oracle.full_case import full_case_inputs
+    z = np.load(os.path.join(golden_dir, "cls_train_full.npz"))
+    r = json.loads(str(z["recipe"]))
+    torch.manual_seed(r["weight_seed"])
+    model = ref_t.CifarResNetRef(tuple(r["num_blocks"]), r["num_classes"])
+    assert abs(float(sum(v.double().sum() for v in model.state_dict().values())) - float(z["init_checksum"])) < 1e-6
+    images, targets, noises = full_case_inputs(r)
+    assert abs(sum(float(n.double().sum()) for n in noises) - float(z["noise_checksum"])) < 1e-6
+    model.train()
+    opt, crit = ref_t.make_sgd(model), torch.nn.CrossEntropyLoss()
+    l2s, linfs = [], []
+    for i in range(r["iters"]):
+        loss, _, l2, linf, _ = ref_t.afan_train_iteration(
+            model, opt, crit, images[i], targets[i], steps=r["steps"], gamma=r["gamma"], eps=r["eps"],
+            perturb_idx=r["perturb_idx"], randinit=True, clip=True, noise=noises[i])
+        ce_adv, ce_clean = z["ce_values"][i][-2:]
+        np.testing.assert_allclose(float(loss), (ce_adv + ce_clean) / 2, rtol=2e-5)
+        l2s.append(l2); linfs.append(linf)
+    np.testing.assert_allclose(float(torch.cat(l2s).mean()), float(z["l2_mean"]), rtol=1e-5)
+    np.testing.assert_allclose(float(torch.cat(linfs).mean()), float(z["linf_mean"]), rtol=1e-6)
+    sd = model.state_dict()
+    for k in z.files:
+        if k.startswith("final/"):
+            got, ref = sd[k[6:]].numpy(), z[k]
+        elif k.startswith("final_sub/"):
+            got, ref = sd[k[10:]].numpy().reshape(-1)[::r["sub"]], z[k]
+        else:
+            continue
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(ref), k
+        else:
+            np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-5, err_msg=k)
+
+
 def test_nms_oracle_reproduces_the_references_own_golden(golden_dir):
     """Detection/test/nms/test_nms.py:39-52: 9770 boxes -> 1934 kept at threshold 0.7 (the reference's only unit test)."""
     z = np.load(os.path.join(golden_dir, "nms_large.npz"))
