@@ -194,12 +194,12 @@ def gpu_reference(dev, steps=5, warmup=3, tf32=False):
 def config_dict(n_gpus, conv_math="fp32", conv="afan", rng="philox"):
     """Short on purpose: the driver keeps only the tail of stdout, the whole final line must stay under ~1.4 KB."""
     w = WORKLOAD
-    return {"workload": "configs[1]: ResNet-56 CIFAR-100-shaped 32x32, A-FAN PGD-5 idx13 rand+clip, dual BN",
+    return {"workload": "configs[1]: ResNet-56 CIFAR-100-shaped, A-FAN PGD-5 idx13 rand+clip, dual BN",
             "global_batch": w["batch_per_gpu"] * n_gpus, "batch_per_gpu": w["batch_per_gpu"],
             "parallelism": f"dp{n_gpus}", "rng": rng,
             "conv": {"afan": "afan fp32 FFMA" if conv_math == "fp32" else "afan mma.sync tf32", "3xtf32": "afan mma.sync 3xtf32",
                      "tc3": "afan tcgen05 3xtf32", "cudnn": "cudnn " + conv_math}[conv],
-            "deterministic": True, "l2": "step working set > L2; kernel rooflines: rotating sets > 4x L2"}
+            "deterministic": True, "l2": "step set > L2; kernel rooflines: rotating sets > 4x L2"}
 
 
 def run_reference(args):
@@ -534,8 +534,7 @@ def parity_iter0(pkg, dev):
     opt, crit = ref_t.make_sgd(ref), torch.nn.CrossEntropyLoss()
     torch.set_num_threads(os.cpu_count() or 1)
     loss_ref, _, _, linf_ref, _ = ref_t.afan_train_iteration(ref, opt, crit, x, y, noise=noise, **kw)
-    return {"loss": got, "port_loss": float(loss_ref), "rel_err": abs(got - float(loss_ref)) / abs(float(loss_ref)),
-            "linf_max": linf, "port_linf_max": float(linf_ref.max())}
+    return {"loss": round(got, 6), "port_loss": round(float(loss_ref), 6), "linf_max": linf, "port_linf_max": float(linf_ref.max())}
 
 
 def _r(v, nd=4):
@@ -559,13 +558,13 @@ def emit(line, detail, args, world):
         line["detail_file"] = os.path.relpath(path, ROOT)
     except OSError as e:
         line["detail_file"] = f"unwritable: {e}"[:60]
-    text = json.dumps(_r(line, 5), separators=(",", ":"))
+    text = json.dumps(_r(line, 4), separators=(",", ":"))
     if len(text) > 1400:                  # the driver parses the tail of stdout: never let the line outgrow it
-        for k in ("variants_ms_per_step", "reference_on_gpu_ms", "multi_gpu_parity_err", "parity_iter0", "afan_kernels_per_step",
+        for k in ("afan_kernels_per_step", "variants_ms_per_step", "multi_gpu_parity_err", "parity_iter0", "reference_on_gpu_ms",
                   "roofline_hbm"):
             if k in line and len(text) > 1400:
                 line.pop(k)
-                text = json.dumps(_r(line, 5), separators=(",", ":"))
+                text = json.dumps(_r(line, 4), separators=(",", ":"))
     sys.stdout.flush()
     print(text, flush=True)
 
@@ -796,6 +795,8 @@ def main():
                  "frac": achieved / f["peak"], "traffic": f["traffic"] / f["launches"] if f["traffic_ok"] else None,
                  "algorithmic_bytes": f["bytes"] / f["launches"], "launches_per_step": f["launches"],
                  "avg_us": f["us"] / f["launches"], "share_of_step": f["us"] / step_us}
+            if not full:
+                d.pop("launches_per_step"); d.pop("avg_us")
             if full:
                 d["shapes"] = f["shapes"]
                 d["peak_source"] = peak_src if f["bound"] == "hbm" else k_peak_note(f["bound"])
