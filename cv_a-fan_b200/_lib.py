@@ -62,6 +62,9 @@ SIGNATURES = {
     "afan_conv3x3s2_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
     "afan_conv3x3_pack_tc_f32": (_int, [_vp, _i64, _i64, _int, _vp]),
     "afan_conv3x3_tc_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
+    "afan_conv3x3_umma_supported": (_int, [_i64, _i64, _i64]),
+    "afan_conv3x3_pack_umma_f32": (_int, [_vp, _i64, _i64, _vp]),
+    "afan_conv3x3_umma_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "afan_conv3x3_wgrad_workspace_bytes": (_i64, [_i64]),
     "afan_conv3x3_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
 }

@@ -22,10 +22,22 @@ from . import ops
 #   "afan"   hand-written kernels, strict fp32 FFMA accumulation (default)
 #   "tf32"   hand-written tensor-core kernels, one TF32 pass (PyTorch's default conv math on Ampere+; opt-in here)
 #   "3xtf32" hand-written tensor-core kernels, hi/lo split (fp32-level accuracy; measured no faster than "afan")
+#   "tc3"    tcgen05 implicit GEMM (Blackwell tensor cores, TMEM accumulators, bulk-copy fed), 3xTF32 split: fp32-grade
+#            accuracy; covers the tail shapes (C, H) in {(32, 16), (64, 8)}, the C = 16 layers stay on the FFMA kernel
 #   "cudnn"  the library convolution (benchmark comparisons)
 MODE = os.environ.get("AFAN_CONV", "afan")
 STRIDE2 = os.environ.get("AFAN_S2", "1") != "0"      # hand-written stride-2 transitions (0: library convolution, for A/B timing)
-_MATH = {"afan": "fp32", "tf32": "tf32", "3xtf32": "3xtf32"}
+_MATH = {"afan": "fp32", "tf32": "tf32", "3xtf32": "3xtf32", "tc3": "umma"}      # MODE -> weight packing
+
+
+def _call_math(c: int, x) -> str:
+    """Kernel family for one call (None: library convolution).  In "tc3" mode the packing is per layer (by C), the kernel
+    per call: a C in {32, 64} layer on a map the tcgen05 kernel does not cover falls back to the library."""
+    if MODE == "tc3":
+        if c in (32, 64):
+            return "umma" if ops.conv3x3_umma_supported(x.shape[0], c, x.shape[2]) else None
+        return "fp32"
+    return _MATH.get(MODE)
 
 
 class _Conv3x3Fn(torch.autograd.Function):
@@ -34,7 +46,7 @@ class _Conv3x3Fn(torch.autograd.Function):
         x = x.contiguous()
         wf, wd = mod.packed()
         ctx.save_for_backward(x)
-        ctx.mod, ctx.wd, ctx.math = mod, wd, _MATH[MODE]
+        ctx.mod, ctx.wd, ctx.math = mod, wd, _call_math(mod.out_channels, x)
         return ops.conv3x3(x, wf, math=ctx.math)
 
     @staticmethod
@@ -62,7 +74,7 @@ class _Conv3x3TapFn(torch.autograd.Function):
         x = x.contiguous()
         wf, wd = mod.packed()
         ctx.save_for_backward(x)
-        ctx.mod, ctx.wd, ctx.math = mod, wd, _MATH[MODE]
+        ctx.mod, ctx.wd, ctx.math = mod, wd, _call_math(mod.out_channels, x)
         return ops.conv3x3(x, wf, math=ctx.math), x.view_as(x)
 
     @staticmethod
@@ -151,7 +163,7 @@ class Conv3x3(nn.Conv2d):
 
     def hand_written(self, x) -> bool:
         return (MODE in _MATH and self.stride == (1, 1) and self.in_channels == self.out_channels
-                and ops.conv3x3_supported(x, self.weight))
+                and ops.conv3x3_supported(x, self.weight) and _call_math(self.out_channels, x) is not None)
 
     def forward_with_tap(self, x):
         """(conv(x), x') where x' aliases x for the identity shortcut; see _Conv3x3TapFn."""
@@ -162,8 +174,7 @@ class Conv3x3(nn.Conv2d):
     def forward(self, x):
         if MODE in _MATH and STRIDE2 and self.is_transition and ops.conv3x3s2_supported(x, self.weight):
             return _Conv3x3S2Fn.apply(x, self.weight, self)
-        if MODE in _MATH and self.stride == (1, 1) and self.in_channels == self.out_channels \
-                and ops.conv3x3_supported(x, self.weight):
+        if self.hand_written(x):
             return _Conv3x3Fn.apply(x, self.weight, self)
         return super().forward(x)
 

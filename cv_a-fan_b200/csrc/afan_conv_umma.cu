@@ -1,0 +1,432 @@
+// afan_conv_umma.cu -- the tail's 3x3 / stride 1 / pad 1 convolutions as a tcgen05 implicit GEMM (sm_100a).
+//
+// Replaces nn.Conv2d `conv1` / `conv2` of BasicBlock (Classification/resnet_s.py:53,55) in the passes the PGD ascent
+// re-executes (attack_algo.py:49-52) -- forward and, with the other weight packing, the input gradient -- at fp32-grade
+// accuracy on the 5th-generation tensor cores: 3xTF32 split (x = hi + lo; a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32
+// accumulation in TMEM).  The strict-FFMA kernel of afan_conv.cu stays the reference implementation of the same call.
+//
+// GEMM view, per image:  D[pixel][co] = sum_{tap, ci} X[pixel + tap][ci] * W[co][ci][tap]   (M = pixels, N = co, K = 9*C).
+//
+// The layout that makes nine shifted taps ONE staged tile.  tcgen05 reads A from shared memory in "core matrices" of
+// 8 rows x 16 bytes; the 8 rows of a core matrix are 16 bytes apart, groups of 8 rows are SBO bytes apart, 16-byte K
+// slices LBO bytes apart (K-major, no swizzle).  A shifted tap is a shift of the pixel index, which for consecutive
+// pixels in the 8 rows of a core matrix is NOT a 16-byte-aligned address offset.  So the 8 rows of every core matrix are
+// made 8 DIFFERENT ROW BANDS of the image (band b = rows [b*R, b*R+R), each staged with its own halo), and consecutive
+// 8-row groups are consecutive pixel POSITIONS inside the bands:
+//
+//     smem offset(position q, K slice j, band b, channel c4) = q * SBO + j * 128 + b * 16 + c4 * 4
+//
+// One MMA (M = 128) covers 16 consecutive positions x 8 bands; a tap (ky, kx) moves the start address by
+// ((r + ky) * PW + kx * XS) * SBO bytes -- always a multiple of 16 -- so all 9 taps, all output rows and both halves of
+// the 3xTF32 split read the SAME staged tile through different descriptors.  Halos (zero padding) are zero-filled once.
+// For 8x8 maps two images are interleaved position-wise (XS = 2) so the 16 positions are 8 columns x 2 images.
+//
+// Pipeline per CTA (one image, or two 8x8 images x half of the output channels):
+//   warp 9   loader:   cp.async.bulk (TMA bulk copy, UBLKCP) of the raw NCHW channel chunks (8 channels = one K step of
+//                      every tap; contiguous in NCHW) and of the packed weight chunk -> mbarrier complete_tx
+//   warps 0-7 staging: raw chunk -> {hi, lo} TF32 tiles in the layout above (generic stores + fence.proxy.async)
+//   warp 8   MMA:      one thread issues MT x 9 taps x 3 tcgen05.mma.kind::tf32 per chunk, accumulators in TMEM;
+//                      tcgen05.commit releases the staging / weight buffers and finally publishes the accumulator
+//   warps 0-7 epilogue: tcgen05.ld (TMEM -> registers), optional addend (identity-shortcut gradient), store NCHW.
+// Accumulation order is fixed by the issue order: results are bitwise reproducible run to run.
+#include "afan_common.cuh"
+
+namespace afan {
+namespace umma {
+
+constexpr int kStageThreads = 256;                 // warps 0-7
+constexpr int kThreadsTotal = kStageThreads + 64;  // + MMA warp + loader warp
+#ifndef AFAN_UMMA_SBO
+#define AFAN_UMMA_SBO 272
+#endif
+constexpr uint32_t kSboA = AFAN_UMMA_SBO;                    // bytes between consecutive positions (17 x 16: conflict-free 128-bit stores)
+constexpr uint32_t kLbo = 128;                     // bytes between the two 16-byte K slices of one K = 8 step
+constexpr uint32_t kSboB = 256;
+constexpr int kNT = 32;                            // MMA N (output channels per CTA)
+constexpr uint32_t kWChunkBytes = 9 * 2 * kNT * 32;   // taps x {hi, lo} x N x 8 reduction channels x 4 B
+constexpr int kAStages = 3;                        // staging ring: hides the MMA completion latency behind the next chunks
+constexpr long long kSpinLimit = 4000000000LL;     // ~2 s: a protocol bug traps instead of hanging the GPU
+
+template <int C, int H>
+struct Cfg {
+    static_assert((C == 32 && H == 16) || (C == 64 && H == 8), "shapes of the ResNet tail");
+    static constexpr int IMG = H == 8 ? 2 : 1;             // images per CTA
+    static constexpr int NSPLIT = C / kNT;                 // CTAs sharing one image group (output-channel halves)
+    static constexpr int R = H / 8;                        // rows per band
+    static constexpr int MT = R;                           // M tiles: output row r of every band
+    static constexpr int XS = IMG;                         // positions per column
+    static constexpr int PW = (H + 2) * IMG;               // positions per padded band row
+    static constexpr int NQ = (R + 2) * PW;
+    static constexpr int NCHUNK = C / 8;
+    static constexpr int WS = NCHUNK < 4 ? NCHUNK : (C == 32 ? 4 : 3);    // weight ring (C = 32: all four chunks resident)
+    static constexpr uint32_t A_TILE = NQ * kSboA;         // one of {hi, lo}
+    static constexpr uint32_t A_STAGE = 2 * A_TILE;
+    static constexpr uint32_t RAW_IMG = 8 * H * H * 4;     // one image, one chunk of 8 channels
+    static constexpr uint32_t RAW_SLOT = IMG * RAW_IMG + 64;   // second image skewed by 16 words: conflict-free reads
+    static constexpr uint32_t OFF_RAW = 0;
+    static constexpr uint32_t OFF_W = OFF_RAW + NCHUNK * RAW_SLOT;
+    static constexpr uint32_t OFF_A = OFF_W + WS * kWChunkBytes;
+    static constexpr uint32_t OFF_BAR = OFF_A + kAStages * A_STAGE;
+    static constexpr uint32_t SMEM = OFF_BAR + 256;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    static constexpr uint32_t TMEM_COLS = MT * 2 * kNT;       // per M tile: [A*B_hi | A_hi*B_lo]
+    static_assert(OFF_W % 128 == 0 && OFF_A % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one elected lane of a converged warp: the compiler then knows the region is single-threaded and emits the
+// warp-level tcgen05 / bulk-copy instructions directly (a plain `lane == 0` test wraps each one in an ELECT loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major, no swizzle: start address, leading (K slice) and stride (8-row group) byte offsets in 16-byte units;
+// bits [46,48) = 1 is the sm_100 descriptor version (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+           (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46);
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M = 128, N = kNT
+constexpr uint32_t idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+constexpr uint32_t kIdescN = idesc_tf32(kNT), kIdesc2N = idesc_tf32(2 * kNT);
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    const float rest = __fsub_rn(v, __uint_as_float(hi));          // exact
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+template <int C, int H>
+__global__ void __launch_bounds__(kThreadsTotal, 1)
+conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, float* __restrict__ y,
+                    const float* __restrict__ addend, const int dbg) {
+    using K = Cfg<C, H>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * K::IMG, ns = blockIdx.y;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BAR);
+    const uint32_t bar0 = sbase + K::OFF_BAR;
+    auto raw_full = [&](int i) { return bar0 + 8u * i; };                                    // [NCHUNK]
+    constexpr int kWStages = K::WS;
+    auto w_full = [&](int i) { return bar0 + 8u * (K::NCHUNK + i); };                                // [WS]
+    auto w_empty = [&](int i) { return bar0 + 8u * (K::NCHUNK + kWStages + i); };                    // [WS]
+    auto a_full = [&](int i) { return bar0 + 8u * (K::NCHUNK + 2 * kWStages + i); };                 // [kAStages]
+    auto a_empty = [&](int i) { return bar0 + 8u * (K::NCHUNK + 2 * kWStages + kAStages + i); };     // [kAStages]
+    const uint32_t acc_full = bar0 + 8u * (K::NCHUNK + 2 * kWStages + 2 * kAStages);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + (K::NCHUNK + 2 * kWStages + 2 * kAStages + 1));
+    static_assert((K::NCHUNK + 2 * kWStages + 2 * kAStages + 2) * 8 <= 256, "barrier block");
+
+    // ---- prologue: the loader thread initialises the barriers and starts every load that needs no waiting, while the
+    //      other warps allocate TMEM and zero the halo positions (the zero padding; never written again) ----
+    const size_t plane8 = static_cast<size_t>(8) * H * H;
+    auto load_raw = [&](int kc) {
+        mbar_expect_tx(raw_full(kc), K::IMG * K::RAW_IMG);
+#pragma unroll
+        for (int im = 0; im < K::IMG; ++im)
+            bulk_g2s(sbase + K::OFF_RAW + kc * K::RAW_SLOT + im * (K::RAW_IMG + 64),
+                     x + (static_cast<size_t>(n0 + im) * (C / 8) + kc) * plane8, K::RAW_IMG, raw_full(kc));
+    };
+    auto load_w = [&](int kc) {
+        const int s = kc % kWStages;
+        if (kc >= kWStages) mbar_wait(w_empty(s), ((kc / kWStages) - 1) & 1);
+        mbar_expect_tx(w_full(s), kWChunkBytes);
+        bulk_g2s(sbase + K::OFF_W + s * kWChunkBytes,
+                 reinterpret_cast<const unsigned char*>(wpk) + (static_cast<size_t>(kc) * K::NSPLIT + ns) * kWChunkBytes,
+                 kWChunkBytes, w_full(s));
+    };
+    if (warp == 9 && elect_one()) {
+        for (int i = 0; i < K::NCHUNK; ++i) mbar_init(raw_full(i), 1);
+        for (int i = 0; i < kWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), kStageThreads / 32); mbar_init(a_empty(i), 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // programmatic dependent launch: everything up to here (barriers, TMEM allocation, halo zero-fill) overlaps the
+        // previous kernel's tail; global memory -- its output (our x), and the packed weights, which a stand-alone module
+        // call packs in the kernel right before this one -- is read only after the wait
+        pdl_wait();
+        for (int kc = 0; kc < kWStages && kc < K::NCHUNK; ++kc) { load_raw(kc); load_w(kc); }
+        for (int kc = kWStages; kc < K::NCHUNK; ++kc) load_raw(kc);
+    }
+    if (warp == 8) {        // TMEM allocation is a warp-wide operation; the same warp frees it at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(tmem_slot))), "r"(K::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < kStageThreads) {
+        constexpr int NHP = (K::R + 2) * 2 * K::XS;            // positions left / right of the image, every band
+        constexpr int NI = K::PW - 2 * K::XS;                  // interior positions of a band row (16)
+        constexpr int PER_TILE = NHP * 16 + 2 * NI * 2;        // 16-byte units
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < 2 * kAStages * PER_TILE; i += kStageThreads) {
+            const int tile = i / PER_TILE, r = i - tile * PER_TILE;
+            uint32_t off;
+            if (r < NHP * 16) {
+                const int k = r >> 4, row = k / (2 * K::XS), c = k - row * (2 * K::XS);
+                off = static_cast<uint32_t>(row * K::PW + (c < K::XS ? c : K::PW - 2 * K::XS + c)) * kSboA + (r & 15) * 16;
+            } else {                                           // row above the image (band 0) / below it (band 7)
+                const int e = r - NHP * 16, bot = e / (NI * 2), f = e - bot * (NI * 2), p = f >> 1, j = f & 1;
+                off = static_cast<uint32_t>((bot ? (K::R + 1) * K::PW : 0) + K::XS + p) * kSboA + j * kLbo + (bot ? 7 * 16 : 0);
+            }
+            *reinterpret_cast<uint4*>(smem + K::OFF_A + tile * K::A_TILE + off) = z;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+
+    if (warp == 9) {
+        // ================= loader: raw activation chunks + packed weight chunks, all by bulk copy =================
+        if (elect_one()) {
+            for (int kc = kWStages; kc < K::NCHUNK; ++kc) load_w(kc);
+        }
+        __syncwarp();
+    } else if (warp == 8) {
+        // ================= MMA issuer: one thread, MT x 9 taps x 2 instructions per chunk =================
+        if (elect_one()) {
+            for (int kc = 0; kc < K::NCHUNK; ++kc) {
+                const int s = kc % kAStages, ws = kc % kWStages;
+                mbar_wait(a_full(s), (kc / kAStages) & 1);
+                mbar_wait(w_full(ws), (kc / kWStages) & 1);
+                tc_fence_after();
+                // descriptors differ only in their 14-bit start-address field: one base per operand, compile-time offsets
+                const uint64_t dA_hi = smem_desc(sbase + K::OFF_A + s * K::A_STAGE, kLbo, kSboA);
+                const uint64_t dA_lo = dA_hi + (K::A_TILE >> 4);
+                const uint64_t dB = smem_desc(sbase + K::OFF_W + ws * kWChunkBytes, kLbo, kSboB);
+                const uint32_t acc0 = kc != 0;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap - 3 * ky;
+                    // [B_hi ; B_lo] are adjacent: ONE N = 64 operand for the A_hi pass (A_hi is read once, not twice)
+                    const uint64_t b_hi = dB + ((tap * 2 * kNT * 32) >> 4);
+#pragma unroll
+                    for (int mt = 0; mt < K::MT; ++mt) {
+                        const uint32_t q0 = (static_cast<uint32_t>((mt + ky) * K::PW + kx * K::XS) * kSboA) >> 4;
+                        const uint32_t dcol = tmem + mt * 2 * kNT;
+                        // cols [0, 32): A_hi*B_hi + A_lo*B_hi;  cols [32, 64): A_hi*B_lo -- summed by the epilogue
+                        tc_mma_tf32(dcol, dA_hi + q0, b_hi, kIdesc2N, tap == 0 ? acc0 : 1u);
+                        tc_mma_tf32(dcol, dA_lo + q0, b_hi, kIdescN, 1u);
+                    }
+                }
+                tc_commit(a_empty(s));          // staging stage s may be overwritten once these MMAs have read it
+                tc_commit(w_empty(ws));
+            }
+            tc_commit(acc_full);
+        }
+        __syncwarp();
+    } else {
+        // ================= staging: raw fp32 chunk -> {hi, lo} TF32 tiles in the band-interleaved layout =================
+        for (int kc = 0; kc < K::NCHUNK; ++kc) {
+            const int s = kc % kAStages;
+            mbar_wait(raw_full(kc), 0);
+            if (kc >= kAStages) mbar_wait(a_empty(s), ((kc / kAStages) - 1) & 1);
+            const float* raw = reinterpret_cast<const float*>(smem + K::OFF_RAW + kc * K::RAW_SLOT);
+            unsigned char* a_hi = smem + K::OFF_A + s * K::A_STAGE;
+            unsigned char* a_lo = a_hi + K::A_TILE;
+            auto put = [&](int q, int j, int b, const uint4& hi, const uint4& lo) {
+                const uint32_t off = q * kSboA + j * kLbo + b * 16;
+                *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                *reinterpret_cast<uint4*>(a_lo + off) = lo;
+            };
+            if (dbg & 4) {                          // dbg bit 2: timing probe, no staging work
+            } else if constexpr (H == 16) {
+                const int py = tid >> 4, px = tid & 15, b = py >> 1, odd = py & 1;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    uint4 hi, lo;
+                    split_tf32(raw[(4 * j + 0) * 256 + tid], hi.x, lo.x);
+                    split_tf32(raw[(4 * j + 1) * 256 + tid], hi.y, lo.y);
+                    split_tf32(raw[(4 * j + 2) * 256 + tid], hi.z, lo.z);
+                    split_tf32(raw[(4 * j + 3) * 256 + tid], hi.w, lo.w);
+                    put((odd + 1) * K::PW + px + 1, j, b, hi, lo);
+                    if (!odd && b > 0) put(3 * K::PW + px + 1, j, b - 1, hi, lo);     // bottom halo row of the band above
+                    if (odd && b < 7) put(px + 1, j, b + 1, hi, lo);                  // top halo row of the band below
+                }
+            } else {
+                const int j = tid >> 7, r = tid & 127, im = r & 1, px = (r >> 1) & 7, py = r >> 4;
+                const float* src = raw + im * (K::RAW_IMG / 4 + 16) + py * 8 + px;
+                uint4 hi, lo;
+                split_tf32(src[(4 * j + 0) * 64], hi.x, lo.x);
+                split_tf32(src[(4 * j + 1) * 64], hi.y, lo.y);
+                split_tf32(src[(4 * j + 2) * 64], hi.z, lo.z);
+                split_tf32(src[(4 * j + 3) * 64], hi.w, lo.w);
+                const int qx = (px + 1) * 2 + im;
+                put(K::PW + qx, j, py, hi, lo);
+                if (py > 0) put(2 * K::PW + qx, j, py - 1, hi, lo);
+                if (py < 7) put(qx, j, py + 1, hi, lo);
+            }
+            fence_proxy_async();               // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(s));
+        }
+        // ================= epilogue: TMEM -> registers -> (+ addend) -> NCHW =================
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        pdl_wait();                            // returns at once (the loader waited long ago): orders the addend reads
+        if (dbg & 2) goto done;                // probe only: no epilogue
+        {
+        const int wq = warp & 3, bnd = lane & 7, g = 4 * wq + (lane >> 3);
+        const uint32_t lane_base = static_cast<uint32_t>(32 * wq) << 16;
+        if constexpr (H == 16) {
+            const int mt = warp >> 2, oy = bnd * 2 + mt, ox = g;
+            const size_t o = (static_cast<size_t>(n0) * C * H + oy) * H + ox;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[16], v2[16];
+                tc_ld16(tmem + lane_base + mt * 2 * kNT + half * 16, v);
+                tc_ld16(tmem + lane_base + mt * 2 * kNT + kNT + half * 16, v2);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = __fadd_rn(v[i], v2[i]);
+                    const size_t oi = o + static_cast<size_t>(half * 16 + i) * H * H;
+                    y[oi] = addend ? __fadd_rn(v[i], __ldg(addend + oi)) : v[i];
+                }
+            }
+        } else {
+            const int half = warp >> 2, oy = bnd, ox = g >> 1, im = g & 1;
+            const size_t o = ((static_cast<size_t>(n0 + im) * C + ns * kNT + half * 16) * H + oy) * H + ox;
+            float v[16], v2[16];
+            tc_ld16(tmem + lane_base + half * 16, v);
+            tc_ld16(tmem + lane_base + kNT + half * 16, v2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = __fadd_rn(v[i], v2[i]);
+                const size_t oi = o + static_cast<size_t>(i) * H * H;
+                y[oi] = addend ? __fadd_rn(v[i], __ldg(addend + oi)) : v[i];
+            }
+        }
+        }
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(K::TMEM_COLS) : "memory");
+    }
+}
+
+// ---- weight packing: W[co][ci][3][3] -> per chunk of 8 reduction channels, per output-channel group of 32, per tap, {hi, lo}:
+//      core matrices [n/8][k slice j][n%8][k%4] (K-major B operand, LBO 128, SBO 256); forward and input-gradient flavours ----
+struct PackDesc { const float* w; float* wf; float* wd; long long c; };
+
+__global__ void conv3x3_pack_umma_kernel(const PackDesc* __restrict__ descs, int n_layers) {
+    const int layer = blockIdx.y;
+    if (layer >= n_layers) return;
+    const PackDesc d = descs[layer];
+    const int c = static_cast<int>(d.c);
+    if (c != 32 && c != 64) return;                       // other layers keep the FFMA packing (afan_conv.cu)
+    const int nsplit = c / kNT, total = c * c * 9;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 2 * total; e += gridDim.x * blockDim.x) {
+        const int dir = e / total, i = e - dir * total;  // i = (n * c + k) * 9 + tap
+        const int tap = i % 9, k = (i / 9) % c, n = i / (9 * c);
+        // forward: B[n = co][k = ci] = W[co][ci][tap];  input gradient: B[n = ci][k = co] = W[co][ci][8 - tap]
+        const float v = dir == 0 ? d.w[(n * c + k) * 9 + tap] : d.w[(k * c + n) * 9 + (8 - tap)];
+        uint32_t hi, lo;
+        split_tf32(v, hi, lo);
+        const int kc = k >> 3, j = (k & 7) >> 2, k4 = k & 3, nsi = n / kNT, nn = n % kNT;
+        const size_t off = ((static_cast<size_t>(kc) * nsplit + nsi) * 9 + tap) * 2 * (kNT * 8) + ((nn >> 3) * 2 + j) * 32 + (nn & 7) * 4 + k4;
+        float* out = dir == 0 ? d.wf : d.wd;
+        out[off] = __uint_as_float(hi);
+        out[off + kNT * 8] = __uint_as_float(lo);
+    }
+}
+
+template <int C, int H>
+static int launch_conv(const float* x, const float* wpk, float* y, const float* addend, int64_t n, cudaStream_t st) {
+    static const int dbg = [] { const char* e = getenv("AFAN_UMMA_DBG"); return e ? atoi(e) : 0; }();
+    using K = Cfg<C, H>;
+    static bool configured = false;      // benign race: idempotent
+    if (!configured) {
+        if (cudaFuncSetAttribute(conv3x3_umma_kernel<C, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM) != cudaSuccess)
+            return (cudaGetLastError(), AFAN_ERR_LAUNCH);
+        configured = true;
+    }
+    if (n % K::IMG) return AFAN_ERR_UNSUPPORTED;
+    static const bool pdl = [] { const char* e = getenv("AFAN_UMMA_PDL"); return !(e && e[0] == '0'); }();
+    const dim3 grid(static_cast<unsigned int>(n / K::IMG), K::NSPLIT);
+    if (pdl) return launch_pdl(conv3x3_umma_kernel<C, H>, grid, dim3(kThreadsTotal), K::SMEM, st, x, wpk, y, addend, dbg);
+    conv3x3_umma_kernel<C, H><<<grid, kThreadsTotal, K::SMEM, st>>>(x, wpk, y, addend, dbg);
+    return launch_status();
+}
+
+}  // namespace umma
+}  // namespace afan
+
+using namespace afan;
+
+AFAN_EXPORT int afan_conv3x3_umma_supported(int64_t n, int64_t c, int64_t hw) {
+    return (n > 0 && n < (1 << 30) && ((c == 32 && hw == 16) || (c == 64 && hw == 8 && n % 2 == 0))) ? 1 : 0;
+}
+
+AFAN_EXPORT int afan_conv3x3_pack_umma_f32(const void* descs_device, int64_t n_layers, int64_t c_max, afan_stream_t stream) {
+    if (!descs_device) return AFAN_ERR_NULL;
+    if (n_layers < 0 || c_max < 1) return AFAN_ERR_SIZE;
+    if (n_layers == 0) return AFAN_OK;
+    const int per = static_cast<int>((2 * c_max * c_max * 9 + 255) / 256);
+    umma::conv3x3_pack_umma_kernel<<<dim3(per < 1 ? 1 : per, static_cast<unsigned int>(n_layers)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const umma::PackDesc*>(descs_device), static_cast<int>(n_layers));
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_conv3x3_umma_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
+                                      int64_t hw, afan_stream_t stream) {
+    if (!x || !w_packed || !y) return AFAN_ERR_NULL;
+    if (n < 0) return AFAN_ERR_SIZE;
+    if (n == 0) return AFAN_OK;
+    if (!aligned16(x) || !aligned16(w_packed)) return AFAN_ERR_UNSUPPORTED;
+    if (!afan_conv3x3_umma_supported(n, c, hw)) return AFAN_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (c == 32) return umma::launch_conv<32, 16>(x, w_packed, y, addend, n, st);
+    return umma::launch_conv<64, 8>(x, w_packed, y, addend, n, st);
+}

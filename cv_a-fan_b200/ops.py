@@ -311,13 +311,26 @@ def conv3x3_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
             and tuple(weight.shape[2:]) == (3, 3))
 
 
+CONV_TC_AVAILABLE = True          # the tcgen05 (UMMA) convolution is built into libafan_b200.so
+
+
+def conv3x3_umma_supported(n: int, c: int, h: int) -> bool:
+    """Shapes of the tcgen05 implicit-GEMM convolution: (C, H) in {(32, 16), (64, 8)} (even N for 8x8 maps)."""
+    return bool(_lib.lib().afan_conv3x3_umma_supported(int(n), int(c), int(h)))
+
+
 def conv3x3_pack(descs: torch.Tensor, c_max: int, math: str = "fp32"):
     """Repack every layer listed in `descs` (int64 [L, 4] = weight ptr, fwd-packed ptr, dgrad-packed ptr, C) in ONE launch.
     math: "fp32" (FFMA kernels, C*9*C floats per packing), "tf32" (tensor cores, 1 pass, C*9*C floats) or
-    "3xtf32" (tensor cores, hi/lo split, 2*C*9*C floats)."""
+    "3xtf32" (tensor cores, hi/lo split, 2*C*9*C floats), or "umma" (tcgen05 3xTF32 implicit GEMM for C in {32, 64},
+    2*C*9*C floats; the other layers get the "fp32" packing)."""
     d = _lib.dev_ptr(descs, torch.int64, "descs")
     if math == "fp32":
         check(_lib.lib().afan_conv3x3_pack_f32(d, descs.shape[0], int(c_max), stream()), "afan_conv3x3_pack_f32")
+    elif math == "umma":
+        # layers the tcgen05 kernel does not cover (C = 16, the stride-2 transitions) keep the FFMA packing
+        check(_lib.lib().afan_conv3x3_pack_f32(d, descs.shape[0], int(c_max), stream()), "afan_conv3x3_pack_f32")
+        check(_lib.lib().afan_conv3x3_pack_umma_f32(d, descs.shape[0], int(c_max), stream()), "afan_conv3x3_pack_umma_f32")
     else:
         check(_lib.lib().afan_conv3x3_pack_tc_f32(d, descs.shape[0], int(c_max), _TC_PASSES[math], stream()),
               "afan_conv3x3_pack_tc_f32")
@@ -337,6 +350,9 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0, math: str
     if math == "fp32":
         check(_lib.lib().afan_conv3x3_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), f32(addend, "addend"), n, c, h,
                                           int(variant), stream()), "afan_conv3x3_f32")
+    elif math == "umma":
+        check(_lib.lib().afan_conv3x3_umma_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), f32(addend, "addend"), n, c, h,
+                                               stream()), "afan_conv3x3_umma_f32")
     else:
         check(_lib.lib().afan_conv3x3_tc_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), f32(addend, "addend"), n, c, h,
                                              _TC_PASSES[math], int(variant), stream()), "afan_conv3x3_tc_f32")

@@ -265,6 +265,16 @@ int afan_conv3x3s2_wgrad_f32(const float* x, const float* dy, float* dw, void* w
 int afan_conv3x3_pack_tc_f32(const void* descs_device, int64_t n_layers, int64_t c_max, int passes, afan_stream_t stream);
 int afan_conv3x3_tc_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
                         int64_t hw, int passes, int variant, afan_stream_t stream);
+/* tcgen05 implicit GEMM of the same convolution (Blackwell 5th-generation tensor cores, accumulators in TMEM, operands
+ * staged by cp.async.bulk): kind::tf32 with the 3xTF32 hi/lo split, i.e. fp32-grade accuracy (1-3e-5 of fp64 like the
+ * FFMA kernel's fixed-order fp32 sum), deterministic.  Replaces the same nn.Conv2d spans (resnet_s.py:53,55) for
+ * (c, hw) in {(32, 16), (64, 8)} -- the tail shapes every PGD step re-executes; (64, 8) needs an even n.
+ * afan_conv3x3_pack_umma_f32 takes the descriptor table of afan_conv3x3_pack_f32 and repacks the layers with c in
+ * {32, 64} (2*c*9*c floats per direction: [k/8][n/32][tap][hi, lo][n/8][k slice][n%8][k%4]); other layers are left alone. */
+int afan_conv3x3_umma_supported(int64_t n, int64_t c, int64_t hw);
+int afan_conv3x3_pack_umma_f32(const void* descs_device, int64_t n_layers, int64_t c_max, afan_stream_t stream);
+int afan_conv3x3_umma_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
+                          int64_t hw, afan_stream_t stream);
 int64_t afan_conv3x3_wgrad_workspace_bytes(int64_t c);
 int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
                            int64_t n, int64_t c, int64_t hw, int accumulate, afan_stream_t stream);

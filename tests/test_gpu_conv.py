@@ -140,3 +140,53 @@ def test_stride2_transition_forward_and_dgrad_vs_fp64(n, cin, hin, monkeypatch):
     outs = [torch.autograd.grad(m(x), (x, m.weight), dy) for _ in range(2)]
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], dx)          # deterministic
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][1], dw)
+
+
+@pytest.mark.parametrize("n,c,h", [(128, 32, 16), (3, 32, 16), (1, 32, 16), (128, 64, 8), (6, 64, 8), (256, 64, 8), (256, 32, 16)])
+def test_tcgen05_conv_vs_fp64(n, c, h, monkeypatch):
+    """tcgen05 (UMMA) implicit-GEMM convolution, 3xTF32 split, TMEM accumulators: forward and input gradient within
+    6e-5 of an fp64 convolution (the FFMA kernel and cuDNN's fp32 algorithms measure 1e-5 .. 5e-5); the weight gradient
+    stays on the FFMA kernel."""
+    monkeypatch.setattr(conv, "MODE", "tc3")
+    dev = torch.device("cuda:0")
+    assert ops.conv3x3_umma_supported(n, c, h)
+    g = torch.Generator(device="cpu").manual_seed(n * 1000 + c + h)
+    x = torch.randn(n, c, h, h, generator=g).to(dev)
+    w = (torch.randn(c, c, 3, 3, generator=g) * (2.0 / (9 * c)) ** 0.5).to(dev)
+    dy = torch.randn(n, c, h, h, generator=g).to(dev)
+    m = conv.Conv3x3(c, c, 1).to(dev)
+    with torch.no_grad():
+        m.weight.copy_(w)
+    xr = x.clone().requires_grad_(True)
+    y, tap = m.forward_with_tap(xr)                      # identity-shortcut flavour: dgrad epilogue adds the tap gradient
+    dtap = torch.randn(n, c, h, h, generator=g).to(dev)
+    dx, dw = torch.autograd.grad((y, tap), (xr, m.weight), (dy, dtap))
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    ref_dx = torch.nn.grad.conv2d_input(x.shape, w.double(), dy.double(), padding=1) + dtap.double()
+    ref_dw = torch.nn.grad.conv2d_weight(x.double(), w.shape, dy.double(), padding=1)
+    assert _rel(y, ref) < 6e-5, _rel(y, ref)
+    assert _rel(dx, ref_dx) < 6e-5, _rel(dx, ref_dx)
+    assert _rel(dw, ref_dw) < 2e-5
+    # bitwise reproducible (fixed issue order of the MMAs)
+    y2, _ = m.forward_with_tap(xr)
+    assert torch.equal(y, y2)
+    # zero padding: an all-ones kernel on a constant image counts the taps inside the image (exact in TF32)
+    with torch.no_grad():
+        m.weight.fill_(1.0)
+    ones = m(torch.ones(2, c, h, h, device=dev))
+    assert ones[0, 0, 0, 0].item() == 4 * c and ones[1, 0, 1, 1].item() == 9 * c and ones[0, -1, -1, 0].item() == 4 * c
+    assert ones[1, 0, 0, 1].item() == 6 * c and ones[1, c // 2, h - 1, h - 1].item() == 4 * c
+
+
+def test_tcgen05_mode_falls_back_outside_its_shapes(monkeypatch):
+    """tc3 mode: C = 16 layers run the FFMA kernel, C in {32, 64} on maps the tcgen05 kernel does not cover (or an odd
+    batch of 8x8 maps) run the library convolution -- never a wrong result."""
+    monkeypatch.setattr(conv, "MODE", "tc3")
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)       # the library fallback in strict fp32 too
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    for n, c, h in [(4, 16, 32), (5, 64, 8), (3, 32, 8), (2, 64, 16)]:
+        m = conv.Conv3x3(c, c, 1).to(dev)
+        x = torch.randn(n, c, h, h, device=dev)
+        ref = F.conv2d(x.double(), m.weight.double(), padding=1)
+        assert _rel(m(x), ref) < 6e-5, (n, c, h)
