@@ -253,8 +253,14 @@ def kernel_rooflines(pkg, dev, reps=10, in_step_only=False):
     e0.record()
     e0.synchronize()
     ffma_peak = fl.value / (s0.elapsed_time(e0) * 1e-3) / 1e12
+    # tensor-pipe denominator: the driver measures dense bf16 (cuBLAS); kind::tf32 runs at half that rate
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tensor_peak = float(json.load(f)["bf16_tflops"]) / 2
+    except Exception:
+        tensor_peak = 1590.0 / 2          # fallback (B200_PROFILING.md)
 
-    def measure(name, bytes_per_launch, footprint, make_set, run, launches_per_iter, note, flops=None):
+    def measure(name, bytes_per_launch, footprint, make_set, run, launches_per_iter, note, flops=None, bound="fp32_ffma"):
         if in_step_only and launches_per_iter == 0:          # N > 1: only the shapes the timed step launches
             return
         R = max(2, min(64, -(-4 * L2_BYTES // footprint)))
@@ -295,8 +301,9 @@ def kernel_rooflines(pkg, dev, reps=10, in_step_only=False):
             row.update({"bound": "hbm", "achieved": bytes_per_launch / t / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": bytes_per_launch / t / 1e9 / peak})
         else:
-            row.update({"bound": "fp32_ffma", "flops": flops, "achieved": flops / t / 1e12, "peak": ffma_peak, "unit": "TFLOP/s",
-                        "frac": flops / t / 1e12 / ffma_peak, "hbm_gbs": bytes_per_launch / t / 1e9})
+            pk = ffma_peak if bound == "fp32_ffma" else tensor_peak
+            row.update({"bound": bound, "flops": flops, "achieved": flops / t / 1e12, "peak": pk, "unit": "TFLOP/s",
+                        "frac": flops / t / 1e12 / pk, "hbm_gbs": bytes_per_launch / t / 1e9})
         res.append(row)
         del graph, sets
 
@@ -372,11 +379,19 @@ def kernel_rooflines(pkg, dev, reps=10, in_step_only=False):
             wf, wd = m.packed()
             return dict(x=torch.randn(N, C, H, H, device=dev, generator=g), dy=torch.randn(N, C, H, H, device=dev, generator=g),
                         wf=wf, m=m, ws=m.wgrad_workspace())
-        math = {"afan": "fp32", "tf32": "tf32", "3xtf32": "3xtf32"}.get(pkg.conv.MODE, "fp32")
-        measure(f"conv3x3 fwd/dgrad [{N}x{C}x{H}x{H}]", 8 * E + 4 * 9 * C * C, 8 * E, mk,
-                lambda t: ops.conv3x3(t["x"], t["wf"], math=math), lpi_conv,
-                "3x3 s1 p1 conv, forward and (other weight packing) input gradient: 18*C FLOP per output element; "
-                "read x + write y = 8 B/elem", flops=fl_conv)
+        umma = pkg.conv.MODE == "tc3" and ops.conv3x3_umma_supported(N, C, H)
+        math = "umma" if umma else {"afan": "fp32", "tf32": "tf32", "3xtf32": "3xtf32"}.get(pkg.conv.MODE, "fp32")
+        if umma:
+            measure(f"conv3x3 tcgen05 fwd/dgrad [{N}x{C}x{H}x{H}]", 8 * E + 4 * 9 * C * C, 8 * E, mk,
+                    lambda t: ops.conv3x3(t["x"], t["wf"], math="umma"), lpi_conv,
+                    "3x3 s1 p1 conv as a tcgen05 implicit GEMM (kind::tf32, 3xTF32 split, TMEM accumulators): 18*C FLOP per "
+                    "output element (the split issues 3x that on the tensor pipe); read x + write y = 8 B/elem",
+                    flops=fl_conv, bound="tensor")
+        else:
+            measure(f"conv3x3 fwd/dgrad [{N}x{C}x{H}x{H}]", 8 * E + 4 * 9 * C * C, 8 * E, mk,
+                    lambda t: ops.conv3x3(t["x"], t["wf"], math=math), lpi_conv,
+                    "3x3 s1 p1 conv, forward and (other weight packing) input gradient: 18*C FLOP per output element; "
+                    "read x + write y = 8 B/elem", flops=fl_conv)
         measure(f"conv3x3 wgrad [{N}x{C}x{H}x{H}]", 8 * E + 4 * 9 * C * C, 8 * E, mk,
                 lambda t: ops.conv3x3_wgrad(t["x"], t["dy"], t["ws"]), lpi_wgrad,
                 "weight gradient (partials kernel + fixed-order fold kernel, both in the time)", flops=fl_conv)
@@ -620,7 +635,7 @@ def main():
 
     pkg = importlib.import_module("cv_a-fan_b200")
     if args.conv is None:
-        args.conv = pkg.conv.MODE if pkg.conv.MODE in ("afan", "cudnn", "3xtf32", "tc3") else "afan"
+        args.conv = pkg.conv.MODE if pkg.conv.MODE in ("afan", "cudnn", "3xtf32", "tc3") else "tc3"
     pkg.conv.MODE = "tf32" if (args.conv == "afan" and args.conv_math == "tf32") else args.conv
     w = WORKLOAD
     detail = {}
@@ -847,7 +862,8 @@ def k_peak_note(bound):
     if bound == "fp32_ffma":
         return ("fp32 FFMA rate measured live by afan_ffma_probe (8x8 outer-product loop, 2 CTAs x 256 threads per SM) on this "
                 "device at its current clocks; nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s")
-    return "tensor: MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate; no measured TF32 peak exists)"
+    return ("tensor: MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate; no measured TF32 peak exists); "
+            "achieved counts the convolution's algorithmic FLOPs once, the 3xTF32 split issues 3x that")
 
 
 if __name__ == "__main__":

@@ -50,9 +50,9 @@ def build_parser():
     p.add_argument("--rng", default="reference", choices=["philox", "reference"],
                    help="random start (--randinit): 'reference' = torch.rand on the CPU generator + H2D like attack_algo.py:44 "
                         "(default, same stream as the reference under the same seed); 'philox' = on-device generator")
-    p.add_argument("--conv_math", default="fp32", choices=["fp32", "tf32", "3xtf32", "tc3", "cudnn"],
-                   help="3x3 convolutions: hand-written strict-fp32 kernels (default), their mma.sync TF32 / 3xTF32 twins, "
-                        "the tcgen05 3xTF32 implicit GEMM (tc3), or the cuDNN library path")
+    p.add_argument("--conv_math", default="tc3", choices=["fp32", "tf32", "3xtf32", "tc3", "cudnn"],
+                   help="3x3 convolutions: tcgen05 3xTF32 implicit GEMM (tc3, default: fp32-grade accuracy on the tensor cores), "
+                        "hand-written strict-fp32 FFMA kernels (fp32), their mma.sync TF32 / 3xTF32 twins, or the cuDNN library path")
     p.add_argument("--no_graph", action="store_true")
     p.add_argument("--no_head_cache", action="store_true")
     p.add_argument("--no_sync_bn", action="store_true")

@@ -21,7 +21,8 @@ def _rel(a, ref):
 
 
 @pytest.mark.parametrize("n,c,h", SHAPES)
-def test_conv3x3_forward_dgrad_wgrad_vs_fp64(n, c, h):
+def test_conv3x3_forward_dgrad_wgrad_vs_fp64(n, c, h, monkeypatch):
+    monkeypatch.setattr(conv, "MODE", "afan")            # the strict-fp32 FFMA kernels
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(n * 1000 + c + h)
     x = torch.randn(n, c, h, h, generator=g).to(dev)
@@ -45,7 +46,9 @@ def test_conv3x3_forward_dgrad_wgrad_vs_fp64(n, c, h):
     assert ones[0, 0, 0, 1].item() == 6 * c
 
 
-def test_conv3x3_is_deterministic_and_repacks_after_weight_update():
+@pytest.mark.parametrize("mode", ["afan", "tc3"])
+def test_conv3x3_is_deterministic_and_repacks_after_weight_update(mode, monkeypatch):
+    monkeypatch.setattr(conv, "MODE", mode)
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     m = conv.Conv3x3(32, 32, 1).to(dev)
