@@ -69,7 +69,11 @@ def main():
             ok &= bool((sharded[k] == v).all())
             continue
         err = float((sharded[k] - v).abs().max())
-        tol = 1e-3 + 1e-2 * float(v.abs().max())
+        # fused NVLink exchange: every rank folds the SAME float64 sums in rank order -> statistics bit-identical across ranks
+        # (checked exactly below) and equal to the single-process ones up to the fp32 rounding of the per-rank partials; the
+        # weights additionally see the NCCL sum order of `world` partial weight gradients.  Measured after 3 iterations:
+        # 2.4e-7 (2 B200s), 4.3e-5 (8 B200s); the NCCL split form (two-launch reduce kernels, other summation order): 2.6e-4
+        tol = (1e-4 + 1e-4 * float(v.abs().max())) if exchange == "p2p" else (1e-3 + 1e-3 * float(v.abs().max()))
         if err > worst[1]:
             worst = (k, err)
         ok &= err <= tol
