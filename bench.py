@@ -337,7 +337,11 @@ def kernel_rooflines(pkg, dev, reps=10, in_step_only=False):
                                       ("G1 128x32x16x16", (1, n, 32, 16, 16), 18 * w["steps"]),
                                       ("G1 128x64x8x8", (1, n, 64, 8, 8), 18 * w["steps"]),
                                       ("G1 128x16x32x32", (1, n, 16, 32, 32), 19),
-                                      ("G2 256x64x56x56", (2, 256, 64, 56, 56), 0)):
+                                      ("G2 256x64x56x56", (2, 256, 64, 56, 56), 0),
+                                      # BASELINE config 5 (DeepLabv3+ R101, 4 x 513^2): ASPP input / ASPP branch / decoder
+                                      ("cfg5 G1 4x2048x33x33", (1, 4, 2048, 33, 33), 0),
+                                      ("cfg5 G2 4x256x33x33", (2, 4, 256, 33, 33), 0),
+                                      ("cfg5 G2 4x256x129x129", (2, 4, 256, 129, 129), 0)):
         E = G * N * C * H * W
         nb = L.afan_bn_workspace_bytes(G, C)
 

@@ -74,40 +74,21 @@ mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ ad
             for (int v = 0; v < VEC; ++v) { wc[q * VEC + v].push(fc[v], r); wa[q * VEC + v].push(fa[v], r); }
         }
     };
-    // software pipeline: the loads of batch i+1 are issued BEFORE the (dependent) Welford chains of batch i run, so two
-    // batches of kB channels x 2 tensors are in flight per thread -- the sweep is latency-bound otherwise
-    // (ncu r1: long_scoreboard 48-63 %, DRAM 31-48 % of peak)
-    constexpr int kB = VEC == 4 ? kMixUnroll / 2 : kMixUnroll;      // batch: the register budget is 64 (2 CTAs x 512 threads)
     unsigned int done = 0;
-    auto load_batch = [&](V (&xc)[kB][NP], V (&xa)[kB][NP]) {
+    for (; done + kMixUnroll <= my_channels; done += kMixUnroll) {
+        V xc[kMixUnroll][NP] = {}, xa[kMixUnroll][NP] = {};
 #pragma unroll
-        for (int u = 0; u < kB; ++u)
+        for (int u = 0; u < kMixUnroll; ++u)
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                xc[u][q] = V{};
-                xa[u][q] = V{};
+            for (int q = 0; q < NP; ++q)
                 if (active[q]) {
-                    xc[u][q] = ld_stream(reinterpret_cast<const V*>(pc + u * cstride + q * 32 * VEC));
-                    xa[u][q] = ld_stream(reinterpret_cast<const V*>(pa + u * cstride + q * 32 * VEC));
+                    xc[u][q] = *reinterpret_cast<const V*>(pc + u * cstride + q * 32 * VEC);
+                    xa[u][q] = *reinterpret_cast<const V*>(pa + u * cstride + q * 32 * VEC);
                 }
-            }
-        pc += kB * cstride;
-        pa += kB * cstride;
-    };
-    if (my_channels >= kB) {
-        V cur_c[kB][NP], cur_a[kB][NP], nxt_c[kB][NP], nxt_a[kB][NP];
-        load_batch(cur_c, cur_a);
-        for (done = kB; done + kB <= my_channels; done += kB) {
-            load_batch(nxt_c, nxt_a);
 #pragma unroll
-            for (int u = 0; u < kB; ++u) push_all(cur_c[u], cur_a[u]);
-#pragma unroll
-            for (int u = 0; u < kB; ++u)
-#pragma unroll
-                for (int q = 0; q < NP; ++q) { cur_c[u][q] = nxt_c[u][q]; cur_a[u][q] = nxt_a[u][q]; }
-        }
-#pragma unroll
-        for (int u = 0; u < kB; ++u) push_all(cur_c[u], cur_a[u]);
+        for (int u = 0; u < kMixUnroll; ++u) push_all(xc[u], xa[u]);
+        pc += kMixUnroll * cstride;
+        pa += kMixUnroll * cstride;
     }
     for (; done < my_channels; ++done) {
         V xc[NP] = {}, xa[NP] = {};
@@ -179,32 +160,17 @@ mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ ad
             }
     };
     done = 0;
-    auto load_clean = [&](V (&xc)[kB][NP]) {
+    for (; done + kMixUnroll <= my_channels; done += kMixUnroll) {
+        V xc[kMixUnroll][NP] = {};
 #pragma unroll
-        for (int u = 0; u < kB; ++u)
+        for (int u = 0; u < kMixUnroll; ++u)
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                xc[u][q] = V{};
+            for (int q = 0; q < NP; ++q)
                 if (active[q]) xc[u][q] = *reinterpret_cast<const V*>(pc + u * cstride + q * 32 * VEC);
-            }
-        pc += kB * cstride;
-    };
-    if (my_channels >= kB) {
-        V cur[kB][NP], nxt[kB][NP];
-        load_clean(cur);
-        for (done = kB; done + kB <= my_channels; done += kB) {
-            load_clean(nxt);
 #pragma unroll
-            for (int u = 0; u < kB; ++u) emit(cur[u], po + u * cstride);
-            po += kB * cstride;
-#pragma unroll
-            for (int u = 0; u < kB; ++u)
-#pragma unroll
-                for (int q = 0; q < NP; ++q) cur[u][q] = nxt[u][q];
-        }
-#pragma unroll
-        for (int u = 0; u < kB; ++u) emit(cur[u], po + u * cstride);
-        po += kB * cstride;
+        for (int u = 0; u < kMixUnroll; ++u) emit(xc[u], po + u * cstride);
+        pc += kMixUnroll * cstride;
+        po += kMixUnroll * cstride;
     }
     for (; done < my_channels; ++done) {
         V xc[NP] = {};

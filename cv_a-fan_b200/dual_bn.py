@@ -7,6 +7,7 @@ statistics, shared weight/bias, one running average updated in pass order.  Dual
 exactly that for a concatenated [adv; clean] batch in ONE sweep (`groups=2`), and degenerates to a plain
 train-mode BatchNorm2d for `groups=1` (the PGD inner-loop passes).  state_dict keys equal nn.BatchNorm2d's.
 """
+import contextlib
 from typing import Optional
 
 import torch
@@ -14,6 +15,35 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import AfanError
+
+
+_DEFAULT_GROUPS = 1
+
+
+@contextlib.contextmanager
+def statistic_groups(k: int):
+    """Inside this context every DualBatchNorm2d called WITHOUT an explicit `groups=` treats its batch as k statistic groups
+    along N -- how a library model whose forward calls `self.bn(x)` (torchvision's Bottleneck / ASPP in the DeepLab tail)
+    runs k tail passes as ONE batched pass with per-pass statistics."""
+    global _DEFAULT_GROUPS
+    old, _DEFAULT_GROUPS = _DEFAULT_GROUPS, int(k)
+    try:
+        yield
+    finally:
+        _DEFAULT_GROUPS = old
+
+
+def convert_batchnorm(module: nn.Module) -> nn.Module:
+    """Replace every nn.BatchNorm2d below `module` (in place) by a DualBatchNorm2d that SHARES its Parameter / buffer
+    objects (optimizer arenas, state_dict keys and checkpoints are unaffected).  Returns `module`."""
+    for name, child in list(module.named_children()):
+        if isinstance(child, nn.BatchNorm2d) and not isinstance(child, DualBatchNorm2d):
+            if not (child.affine and child.track_running_stats) or child.momentum is None:
+                raise AfanError("convert_batchnorm needs affine BatchNorm2d layers with running statistics and a momentum")
+            setattr(module, name, DualBatchNorm2d.from_batchnorm(child))
+        else:
+            convert_batchnorm(child)
+    return module
 
 
 class _DualBNTrainFn(torch.autograd.Function):
@@ -85,6 +115,14 @@ class DualBatchNorm2d(nn.Module):
         self.grad_direct = False
         self._register_state_dict_hook(_flush_hook)
 
+    @classmethod
+    def from_batchnorm(cls, bn: nn.BatchNorm2d) -> "DualBatchNorm2d":
+        m = cls(bn.num_features, bn.eps, bn.momentum)
+        m.weight, m.bias = bn.weight, bn.bias                        # the same Parameter objects
+        m.running_mean, m.running_var, m.num_batches_tracked = bn.running_mean, bn.running_var, bn.num_batches_tracked
+        m.train(bn.training)
+        return m
+
     def _workspace(self, groups: int, device):
         ws = self._ws.get((groups, device))
         if ws is None:
@@ -96,10 +134,12 @@ class DualBatchNorm2d(nn.Module):
             self.num_batches_tracked += self._pending_batches * multiplier
             self._pending_batches = 0
 
-    def forward(self, x, residual: Optional[torch.Tensor] = None, relu: bool = False, groups: int = 1,
+    def forward(self, x, residual: Optional[torch.Tensor] = None, relu: bool = False, groups: Optional[int] = None,
                 replay: int = 1):
         if x.dim() != 4 or x.shape[1] != self.num_features:
             raise AfanError(f"expected [N, {self.num_features}, H, W], got {tuple(x.shape)}")
+        if groups is None:
+            groups = _DEFAULT_GROUPS
         if self.training:
             self._pending_batches += groups * replay
             grad_out = None

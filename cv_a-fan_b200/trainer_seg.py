@@ -20,15 +20,28 @@ B200 design.
     in-register Philox generator unless `noise=` injects the reference's CPU draws.
   * parameters live in two flat arenas (backbone / classifier: the reference's two SGD groups) with one fused SGD
     launch each; learning rates sit in device memory (`set_lr`, PolyLR-ready).
-Convolutions and BatchNorm of DeepLab stay library kernels (out of the hand-written scope).
+  * dual BN: the tail's BatchNorm layers (stages after `se`, ASPP, decoder) run on the hand-written dual-BN kernels and
+    the two stage-`se` tail passes of the final forward are ONE batched pass with two statistic groups (`dual_bn=True`).
+Convolutions of DeepLab and the head's BatchNorm stay library kernels (out of the hand-written scope).
+
+Declared deviations from the reference schedule: with the head cache (a) the shared layers' running statistics
+get the k-fold update up front, where the reference interleaves clean pass #2, the ascents' tail updates and clean pass
+#3 -- an exponential average depends on that order, the statistics agree to 2e-2 (tested); (b) ASPP's Dropout draws ONE
+mask for the decoder anchor and `out0` where the reference's two clean passes draw two; (c) the flat SGD arena applies
+weight decay to every parameter of the group, torch.optim.SGD skips parameters whose .grad is None (none exists in this
+model: every parameter receives a gradient each iteration).  `head_cache=False` replays the reference schedule literally.
 """
 from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
 
+from . import dual_bn as dual_bn_mod
 from . import ops, segmentation
 from ._lib import AfanError
+from .dual_bn import DualBatchNorm2d
+
+_BN = (nn.BatchNorm2d, DualBatchNorm2d)
 
 
 class _Arena:
@@ -94,8 +107,15 @@ class SegAfanTrainer:
                  eps: float = 2.0, gamma_se: float = 0.5, gamma_sd: float = 0.5, randinit: bool = False,
                  clip: bool = False, mix_sd: bool = False, noise_sd: float = 0.0, mix_layer: str = "00",
                  lr: float = 0.01, momentum: float = 0.9, weight_decay: float = 1e-4,
-                 criterion: Optional[nn.Module] = None, head_cache: bool = True, rng: str = "philox", seed: int = 0):
-        """Flag names / units follow Segmentation/args.py:19-40 (eps, gamma_* in 1/255)."""
+                 criterion: Optional[nn.Module] = None, head_cache: bool = True, rng: str = "philox", seed: int = 0,
+                 dual_bn: bool = True):
+        """Flag names / units follow Segmentation/args.py:19-40 (eps, gamma_* in 1/255).
+
+        dual_bn: the BatchNorm layers of the TAIL (backbone stages after `pertub_idx_se`, ASPP, decoder:
+        Segmentation/network/backbone/resnet.py:127,144, _deeplab.py:47-80) become DualBatchNorm2d (the hand-written
+        sm_100a kernels), and the two stage-`se` tail passes of the final forward (main_aug_final.py:222-223) run as ONE
+        batched pass with two statistic groups -- the same per-pass statistics, shared affine, running average updated in
+        pass order."""
         if pertub_idx_se not in (1, 2, 3, 4) or pertub_idx_sd not in ("aspp", "concat"):
             raise AfanError("pertub_idx_se must be 1..4 and pertub_idx_sd 'aspp' or 'concat'")
         if len(mix_layer) != 2 or any(ch not in "01" for ch in mix_layer):
@@ -103,6 +123,7 @@ class SegAfanTrainer:
         self.model, self.se, self.sd = model, pertub_idx_se, pertub_idx_sd
         self.steps, self.eps = int(steps), eps / 255.0
         self.gamma_se, self.gamma_sd = gamma_se / 255.0, gamma_sd / 255.0
+        self.gamma_sd_raw = float(gamma_sd)                 # :206-207 scale the uniform noise by opts.gamma_sd itself
         self.randinit, self.clip, self.mix_sd, self.noise_sd = randinit, clip, mix_sd, float(noise_sd)
         self.f0, self.f1 = int(mix_layer[0]), int(mix_layer[1])
         self.momentum, self.weight_decay = momentum, weight_decay
@@ -111,17 +132,22 @@ class SegAfanTrainer:
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise AfanError("SegAfanTrainer needs the model on a CUDA device: there is no CPU path")
+        self.dual_bn = bool(dual_bn)
+        if self.dual_bn:
+            for k in range(pertub_idx_se + 1, 5):
+                dual_bn_mod.convert_batchnorm(getattr(model.backbone, f"layer{k}"))
+            dual_bn_mod.convert_batchnorm(model.classifier)
         # the reference's two SGD groups (main_aug_final.py:79-82)
         self.arenas = [_Arena(model.backbone.parameters(), 0.1 * lr, self.device),
                        _Arena(model.classifier.parameters(), lr, self.device)]
         self._lr = float(lr)
         bb = model.backbone
         shared = [bb.bn1] + [m for k in range(1, self.se + 1) for m in getattr(bb, f"layer{k}").modules()
-                             if isinstance(m, nn.BatchNorm2d)]
-        rest = [m for k in range(self.se + 1, 5) for m in getattr(bb, f"layer{k}").modules() if isinstance(m, nn.BatchNorm2d)]
-        aspp = [m for m in model.classifier.aspp.modules() if isinstance(m, nn.BatchNorm2d)]
+                             if isinstance(m, _BN)]
+        rest = [m for k in range(self.se + 1, 5) for m in getattr(bb, f"layer{k}").modules() if isinstance(m, _BN)]
+        aspp = [m for m in model.classifier.aspp.modules() if isinstance(m, _BN)]
         if self.sd == "concat":           # '<concat>_head' (#2) and the clean pass (#3) both run the low-level projection
-            aspp += [m for m in model.classifier.project.modules() if isinstance(m, nn.BatchNorm2d)]
+            aspp += [m for m in model.classifier.project.modules() if isinstance(m, _BN)]
         # (statistic arena, how often the reference forwards these layers on the CLEAN images per iteration)
         self._replays = [(_StatArena(shared, self.device), 3), (_StatArena(rest, self.device), 2),
                          (_StatArena(aspp, self.device), 2)] if head_cache else []
@@ -184,7 +210,7 @@ class SegAfanTrainer:
         if self.noise_sd != 0:
             u = noise["noise_sd"].to(self.device) if (noise is not None and "noise_sd" in noise) else \
                 torch.rand(adv_sd.shape, device=self.device)
-            adv_sd = adv_sd + (2.0 * u - 1.0) * self.gamma_sd * 255.0 * self.noise_sd                       # :206-207 (opts.gamma_sd, not /255)
+            adv_sd = adv_sd + (2.0 * u - 1.0) * self.gamma_sd_raw * self.noise_sd                           # :206-207 (opts.gamma_sd, not /255)
         dec_dict["adv"] = adv_sd
         pts = segmentation.sat_sample_points(feat_se, adv_se, 3, mix=[self.f0, self.f1])                     # :210-214
 
@@ -197,8 +223,16 @@ class SegAfanTrainer:
             del feats
         else:
             out0 = model({"x": images, "adv": None, "out_idx": 0, "flag": "clean"})                          # :221
-        out1 = model({"x": images, "adv": pts[1], "out_idx": se, "flag": "tail", "low_level_feat": low})     # :222
-        out2 = model({"x": images, "adv": pts[2], "out_idx": se, "flag": "tail", "low_level_feat": low})     # :223
+        if self.dual_bn:
+            # :222-223 as ONE pass over [point 1; point 2] with two BatchNorm statistic groups ("dual BN")
+            nb = images.shape[0]
+            with dual_bn_mod.statistic_groups(2):
+                out12 = model({"x": images, "adv": torch.cat([pts[1], pts[2]], 0), "out_idx": se, "flag": "tail",
+                               "low_level_feat": torch.cat([low, low], 0)})
+            out1, out2 = out12[:nb], out12[nb:]
+        else:
+            out1 = model({"x": images, "adv": pts[1], "out_idx": se, "flag": "tail", "low_level_feat": low})     # :222
+            out2 = model({"x": images, "adv": pts[2], "out_idx": se, "flag": "tail", "low_level_feat": low})     # :223
         out3 = model({"x": images, "adv": dec_dict, "out_idx": sd + "_tail", "flag": "clean"})               # :224
         l0, l1, l2, l3 = crit(out0, labels), crit(out1, labels), crit(out2, labels), crit(out3, labels)
         loss = 0.7 * l0 + 0.1 * l1 + 0.1 * l2 + 0.1 * l3                                                     # :233

@@ -25,7 +25,7 @@ def _strict_fp32():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def _run(name, head_cache):
+def _run(name, head_cache, dual_bn=True):
     c = ref.CASES[name]
     dev = torch.device("cuda:0")
     model = PKG.deeplab.deeplabv3plus_resnet50(num_classes=ref.NUM_CLASSES, output_stride=16)
@@ -37,7 +37,9 @@ def _run(name, head_cache):
     tr = PKG.trainer_seg.SegAfanTrainer(model, pertub_idx_se=c["se"], pertub_idx_sd=c["sd"], steps=c["steps"], eps=c["eps"],
                                         gamma_se=c["gamma_se"], gamma_sd=c["gamma_sd"], randinit=c["randinit"], clip=c["clip"],
                                         mix_sd=c["mix_sd"], noise_sd=c["noise_sd"], mix_layer=c["mix_layer"], lr=ref.LR,
-                                        weight_decay=ref.WD, head_cache=head_cache)
+                                        weight_decay=ref.WD, head_cache=head_cache, dual_bn=dual_bn)
+    if dual_bn:       # tail BatchNorm on the hand-written kernels, the two stage-`se` tails batched with 2 statistic groups
+        assert sum(isinstance(m, PKG.dual_bn.DualBatchNorm2d) for m in model.modules()) >= 8
     images, labels = ref.make_batches(seed=21)
     losses = []
     for it in range(ref.ITERS):
@@ -133,3 +135,18 @@ def test_seg_training_iterations_vs_reference_golden(name, head_cache):
     for k in ref.FULL:
         if not k.endswith(STATS):
             np.testing.assert_allclose(sd[k].numpy(), G[f"{name}/final/{k}"], rtol=2e-2, atol=2e-3, err_msg=k)
+
+
+def test_dual_bn_tail_equals_the_library_batchnorm_tail():
+    """dual_bn=True (hand-written BatchNorm kernels in the tail + the two stage-`se` tails as one 2-group pass) against
+    dual_bn=False (nn.BatchNorm2d / cuDNN, two separate passes) on the same inputs: same losses, same running statistics
+    and step counts -- the batched pass computes exactly the per-pass statistics of Segmentation/main_aug_final.py:222-223."""
+    la, sa = _run("A", True, dual_bn=True)
+    lb, sb = _run("A", True, dual_bn=False)
+    np.testing.assert_allclose(la, lb, rtol=1e-3)
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert float(sa[k]) == float(sb[k]), k
+        elif k.endswith(STATS):
+            tight = torch.isclose(sa[k], sb[k], rtol=1e-3, atol=3e-3)
+            assert tight.float().mean() >= 0.995, (k, float(tight.float().mean()))
