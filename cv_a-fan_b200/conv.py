@@ -41,6 +41,43 @@ def _call_math(c: int, x) -> str:
     return _MATH.get(MODE)
 
 
+# ---- weight gradients on a second stream --------------------------------------------------------------------------
+# The input-gradient chain of a backward pass (dgrad conv -> BatchNorm backward -> dgrad conv ...) is sequential and made of
+# launch-latency-bound kernels, while the weight gradients feed nothing but the gradient arena.  A trainer that owns that
+# arena brackets loss.backward() with wgrad_overlap_begin / wgrad_overlap_join: every weight-gradient launch then goes to a
+# side stream (forked from the backward stream at the point its dy exists) and fills otherwise idle SMs; the join orders
+# the arena before the all-reduce / SGD.  Works under CUDA-graph capture (fork / join become graph edges).
+WGRAD_OVERLAP = os.environ.get("AFAN_WGRAD_OVERLAP", "1") != "0"
+_overlap = {"stream": None, "keep": [], "active": False}
+
+
+def wgrad_overlap_begin(device):
+    if not WGRAD_OVERLAP:
+        return
+    if _overlap["stream"] is None or _overlap["stream"].device != device:
+        _overlap["stream"] = torch.cuda.Stream(device=device)
+    _overlap["active"] = True
+
+
+def wgrad_overlap_join():
+    if _overlap["active"]:
+        torch.cuda.current_stream().wait_stream(_overlap["stream"])
+        _overlap["keep"].clear()              # x / dy stayed alive until the side stream's work was ordered before ours
+        _overlap["active"] = False
+
+
+def _arena_wgrad(fn, x, dy, mod):
+    """Weight gradient added straight into mod.weight.grad (a slice of the trainer's gradient arena)."""
+    if not _overlap["active"]:
+        fn(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)
+        return
+    side = _overlap["stream"]
+    side.wait_stream(torch.cuda.current_stream())                 # dy (and x) are complete on the backward stream
+    with torch.cuda.stream(side):
+        fn(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)
+    _overlap["keep"].append((x, dy))
+
+
 class _Conv3x3Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, mod):
@@ -59,7 +96,7 @@ class _Conv3x3Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             mod = ctx.mod
             if mod.grad_direct and mod.weight.grad is not None:
-                ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)   # no temporary, no add launch
+                _arena_wgrad(ops.conv3x3_wgrad, x, dy, mod)                                        # no temporary, no add launch
             else:
                 dw = ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace())
         return dx, dw, None
@@ -89,7 +126,7 @@ class _Conv3x3TapFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             mod = ctx.mod
             if mod.grad_direct and mod.weight.grad is not None:
-                ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)
+                _arena_wgrad(ops.conv3x3_wgrad, x, dy, mod)
             else:
                 dw = ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace())
         return dx, dw, None
@@ -116,7 +153,7 @@ class _Conv3x3S2Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             mod = ctx.mod
             if mod.grad_direct and mod.weight.grad is not None:
-                ops.conv3x3s2_wgrad(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)
+                _arena_wgrad(ops.conv3x3s2_wgrad, x, dy, mod)
             else:
                 dw = ops.conv3x3s2_wgrad(x, dy, mod.wgrad_workspace())
         return dx, dw, None

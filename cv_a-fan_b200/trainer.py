@@ -209,7 +209,11 @@ class AfanTrainer:
 
     def _optimize(self, loss):
         self.flat_grad.zero_()                                                       # :199
-        loss.backward()                                                              # :200
+        conv.wgrad_overlap_begin(self.device)      # weight gradients on a side stream, beside the dgrad / BN chain
+        try:
+            loss.backward()                                                          # :200
+        finally:
+            conv.wgrad_overlap_join()
         scale = sync.allreduce_grad_arena_(self.flat_grad, self.pg)                  # one NCCL message / iteration
         ops.sgd_momentum_(self.flat_param, self.flat_grad, self.flat_buf, self.lr_dev, momentum=self.momentum,
                           weight_decay=self.weight_decay, grad_scale=scale)                   # :201

@@ -274,3 +274,31 @@ def test_f1_variants_match_reference_goldens_bitwise():
                         eps=2 / 255, gamma=1 / 255, randinit=False)
     out = d["rpn_feature_map_dict"]["rpn_feature"]
     assert out.is_leaf and out.requires_grad and torch.equal(out.detach(), feat)
+
+
+def test_philox_start_is_distributionally_the_references_uniform_start():
+    """bench.py's headline uses the on-device Philox start, the bitwise evidence is for injected noise.
+    The Philox start must be the SAME distribution as the reference's `x + (2*torch.rand(shape) - 1) * eps`
+    (Classification/attack_algo.py:42-44): delta/eps uniform on [-1, 1) -- mean, variance, range, a KS distance against both
+    the exact CDF and a torch.rand sample of the same size, independence across offsets / seeds."""
+    n, eps = 1 << 22, 2.0 / 255
+    x = torch.zeros(n, device=dev())
+    u = (PKG.ops.pgd_init(x, eps, seed=3, offset=0).double().cpu().numpy() / eps + 1.0) / 2.0      # back to [0, 1)
+    assert 0.0 <= u.min() and u.max() < 1.0 + 1e-6
+    assert abs(u.mean() - 0.5) < 4 / np.sqrt(12 * n) and abs(u.var() - 1 / 12) < 1e-4
+    us = np.sort(u)
+    ks_exact = np.abs(us - (np.arange(n) + 0.5) / n).max()
+    ref = np.sort(torch.rand(n, generator=torch.Generator().manual_seed(3)).double().numpy())     # the reference's generator
+    ks_ref = np.abs(ref - (np.arange(n) + 0.5) / n).max()
+    crit = 1.95 / np.sqrt(n)                               # KS critical value at alpha = 0.001
+    assert ks_exact < crit and ks_ref < crit, (ks_exact, ks_ref, crit)
+    assert np.abs(us - ref).max() < 2 * crit               # two-sample distance to the torch.rand sample
+    # other seed / offset -> another, uncorrelated stream
+    v = (PKG.ops.pgd_init(x, eps, seed=4, offset=0).double().cpu().numpy() / eps + 1.0) / 2.0
+    w = (PKG.ops.pgd_init(x, eps, seed=3, offset=n // 4).double().cpu().numpy() / eps + 1.0) / 2.0
+    for other in (v, w):
+        assert abs(np.corrcoef(u, other)[0, 1]) < 5 / np.sqrt(n)
+    # consecutive draws are uncorrelated (lag-1) and every float4 lane behaves alike
+    assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 5 / np.sqrt(n)
+    for lane in range(4):
+        assert abs(u[lane::4].mean() - 0.5) < 5 / np.sqrt(12 * n / 4)
