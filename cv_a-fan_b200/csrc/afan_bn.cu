@@ -70,6 +70,17 @@ struct ReduceParams {
     unsigned int groups, n, c, hwv, splits;
 };
 
+// ---- shifted accumulation --------------------------------------------------------------------------------------
+// sum / sum-of-squares in fp32 partials cancels catastrophically when |mean| >> std (found on the DeepLab ASPP pooling
+// branch: 2 values per channel, relu-positive, nearly equal -> 2.5e-3 error against the two-pass library BatchNorm).
+// Every forward-statistics kernel therefore accumulates (x - K) with K = the first element of the (group, channel) domain
+// (one broadcast load), and un-shifts its per-CTA partial in DOUBLE before it is folded / exchanged:
+//   sum x = S1 + cnt K,   sum x^2 = S2 + 2 K S1 + cnt K^2          (cnt = elements behind the partial)
+// so everything downstream (cluster fold, NVLink / NCCL exchange, finalisers) still sees raw sums.
+__device__ __forceinline__ double2 unshift_sums(double s1, double s2, double cnt, double k) {
+    return make_double2(s1 + cnt * k, s2 + 2.0 * k * s1 + cnt * k * k);
+}
+
 // ---- finalisation math, shared by the in-kernel path and the stand-alone finalize kernels ----
 __device__ __forceinline__ void fwd_finalize_channel(const ReduceParams& p, unsigned int ch, const double* sum,
                                                      const double* sumsq) {
@@ -118,6 +129,7 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams 
     const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;   // vector offset of plane (g*N+0, ch)
     const size_t plane_stride = static_cast<size_t>(p.c) * p.hwv;
     const float mean = BWD ? p.save_mean[gc] : 0.f;
+    const float kshift = BWD ? 0.f : __ldg(p.a + plane0 * VEC);          // forward: accumulate x - K (see unshift_sums)
 
     float acc0 = 0.f, acc1 = 0.f;
     for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kThreads * kBnUnroll) {
@@ -148,8 +160,9 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams 
                             acc0 += d;
                             acc1 = fmaf(d, bv[e] - mean, acc1);
                         } else {
-                            acc0 += av[e];
-                            acc1 = fmaf(av[e], av[e], acc1);
+                            const float t = av[e] - kshift;
+                            acc0 += t;
+                            acc1 = fmaf(t, t, acc1);
                         }
                     }
                 } else {
@@ -158,8 +171,9 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams 
                         acc0 += d;
                         acc1 = fmaf(d, b[u] - mean, acc1);
                     } else {
-                        acc0 += a[u];
-                        acc1 = fmaf(a[u], a[u], acc1);
+                        const float t = a[u] - kshift;
+                        acc0 += t;
+                        acc1 = fmaf(t, t, acc1);
                     }
                 }
             }
@@ -172,7 +186,8 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams 
     block_sum2(d0, d1, scratch);
     if (threadIdx.x == 0) {
         if (BWD) d1 *= static_cast<double>(p.save_invstd[gc]);            // sum dy*(x-mean) -> sum dy*xhat
-        p.partials[static_cast<size_t>(gc) * p.splits + s] = make_double2(d0, d1);
+        p.partials[static_cast<size_t>(gc) * p.splits + s] =
+            BWD ? make_double2(d0, d1) : unshift_sums(d0, d1, static_cast<double>(hi - lo) * VEC, static_cast<double>(kshift));
     }
     // last CTA of this CHANNEL (all groups, all splits) folds and finalises
     if (!last_cta_arrives(p.counters + ch, p.groups * p.splits, &sflag)) return;
@@ -364,6 +379,8 @@ struct ClusterParams {
     float eps, momentum;
     int replay;
     unsigned int groups, n, c, hwv;
+    const float2* mask_table;   // bwd + relu, y == nullptr: ReLU mask recomputed as x * scale + shift > 0 from the forward's
+                                // per-(group, channel) table (the fused convolution never materialised y)
 };
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
@@ -410,13 +427,17 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const C
     // ---- sweep 1: per-group sum / sum of squares of this CTA's slice ----
     for (unsigned int g = 0; g < p.groups; ++g) {
         const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
+        const float kshift = __ldg(p.a + plane0 * VEC);               // accumulate x - K (see unshift_sums)
         float acc0 = 0.f, acc1 = 0.f;
         for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
-            V a[kBnUnroll] = {};
+            V a[kBnUnroll];
+            bool ok[kBnUnroll];
 #pragma unroll
             for (int u = 0; u < kBnUnroll; ++u) {
                 const unsigned int j = j0 + u * kClusterThreads;
-                if (j < hi) {
+                ok[u] = j < hi;
+                if constexpr (VEC == 4) a[u] = make_float4(kshift, kshift, kshift, kshift); else a[u] = kshift;
+                if (ok[u]) {
                     const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
                     a[u] = x_v[plane0 + nn * plane_stride + off];
                 }
@@ -424,17 +445,19 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const C
 #pragma unroll
             for (int u = 0; u < kBnUnroll; ++u) {
                 if constexpr (VEC == 4) {
-                    acc0 += (a[u].x + a[u].y) + (a[u].z + a[u].w);
-                    acc1 = fmaf(a[u].x, a[u].x, fmaf(a[u].y, a[u].y, fmaf(a[u].z, a[u].z, fmaf(a[u].w, a[u].w, acc1))));
+                    const float tx = a[u].x - kshift, ty = a[u].y - kshift, tz = a[u].z - kshift, tw = a[u].w - kshift;
+                    acc0 += (tx + ty) + (tz + tw);
+                    acc1 = fmaf(tx, tx, fmaf(ty, ty, fmaf(tz, tz, fmaf(tw, tw, acc1))));
                 } else {
-                    acc0 += a[u];
-                    acc1 = fmaf(a[u], a[u], acc1);
+                    const float t = a[u] - kshift;
+                    acc0 += t;
+                    acc1 = fmaf(t, t, acc1);
                 }
             }
         }
         double d0 = acc0, d1 = acc1;
         block_sum2(d0, d1, scratch);
-        if (threadIdx.x == 0) s_part[g] = make_double2(d0, d1);
+        if (threadIdx.x == 0) s_part[g] = unshift_sums(d0, d1, static_cast<double>(hi - lo) * VEC, static_cast<double>(kshift));
     }
 
     // ---- cluster-wide fold over DSMEM, finalise ----
@@ -823,19 +846,30 @@ bn_fwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
                 if (RES_EARLY) r[g][i] = ld_stream(r_v + (g * group_stride + rel[i]));
             }
         }
-    float acc[2 * G];
+    float acc[2 * G], kshift[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
+        // accumulate x - K, K = first element of the (group, channel) domain (see unshift_sums); padding lanes hold 0 and
+        // are excluded by the mask
+        kshift[g] = __ldg(reinterpret_cast<const float*>(x_v + (g * group_stride + ch * p.hwv)));
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            s0 += (a[g][i].x + a[g][i].y) + (a[g][i].z + a[g][i].w);
-            s1 = fmaf(a[g][i].x, a[g][i].x, fmaf(a[g][i].y, a[g][i].y, fmaf(a[g][i].z, a[g][i].z, fmaf(a[g][i].w, a[g][i].w, s1))));
+            if (rel[i] != 0xffffffffu) {
+                const float tx = a[g][i].x - kshift[g], ty = a[g][i].y - kshift[g], tz = a[g][i].z - kshift[g], tw = a[g][i].w - kshift[g];
+                s0 += (tx + ty) + (tz + tw);
+                s1 = fmaf(tx, tx, fmaf(ty, ty, fmaf(tz, tz, fmaf(tw, tw, s1))));
+            }
         }
         acc[2 * g] = s0;
         acc[2 * g + 1] = s1;
     }
     block_reduce_k<2 * G>(acc, reinterpret_cast<double*>(s_part), s_warp);
+    __syncthreads();
+    if (threadIdx.x < G) {                                            // raw sums from here on
+        const double cnt = 4.0 * static_cast<double>(hi - lo);
+        s_part[threadIdx.x] = unshift_sums(s_part[threadIdx.x].x, s_part[threadIdx.x].y, cnt, static_cast<double>(kshift[threadIdx.x]));
+    }
 
     __shared__ double2 s_loc[kMaxGroups], s_glob[kMaxGroups];
     const double2 tot = P2P ? cluster_fold_p2p(cluster, s_part, s_all, s_loc, s_glob, G, ch, q, seq)
@@ -933,7 +967,14 @@ bn_bwd_cluster_reg_kernel(const ClusterParams p, const P2PParams q) {
                 d[g][i] = ld_stream(dy_v + (g * group_stride + rel[i]));
                 x[g][i] = ld_stream(x_v + (g * group_stride + rel[i]));
                 if (RELU) {                                         // fold the ReLU mask into dy right away
-                    const float4 yy = ld_stream(y_v + (g * group_stride + rel[i]));
+                    float4 yy;
+                    if (p.mask_table) {                             // y = relu(x * scale + shift) was never stored: same fma, same mask
+                        const float2 t = __ldg(p.mask_table + g * p.c + ch);
+                        yy = make_float4(fmaf(x[g][i].x, t.x, t.y), fmaf(x[g][i].y, t.x, t.y), fmaf(x[g][i].z, t.x, t.y),
+                                         fmaf(x[g][i].w, t.x, t.y));
+                    } else {
+                        yy = ld_stream(y_v + (g * group_stride + rel[i]));
+                    }
                     if (!(yy.x > 0.f)) d[g][i].x = 0.f;
                     if (!(yy.y > 0.f)) d[g][i].y = 0.f;
                     if (!(yy.z > 0.f)) d[g][i].z = 0.f;
@@ -1049,6 +1090,229 @@ int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st, co
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, kernel, p, extra...) != cudaSuccess) { cudaGetLastError(); return AFAN_ERR_LAUNCH; }
     return launch_status();
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Plane-resident kernels (round 2): small per-channel domains with ANY H*W -- the DeepLab tail at 33 x 33 = 1089
+// (BASELINE config 5), where H*W % 4 != 0 sent every launch down scalar two-sweep paths (0.17-0.32 of the HBM roofline).
+// One CTA per channel holds the channel's whole domain (groups x n planes) in shared memory: every plane is read from
+// HBM exactly once with 128-bit loads -- a plane starts at an arbitrary 4-byte alignment, so it is peeled into a scalar
+// head, a 16-byte-aligned body and a scalar tail, and stored in shared memory at the same alignment class -- the
+// statistics and the normalisation both run out of shared memory, and the result leaves with the same peeled 128-bit
+// pattern.  No cluster, no second HBM read, 2-6 CTAs per SM keep > 64 KB of loads in flight per SM.
+// -----------------------------------------------------------------------------------------------------
+constexpr int kPlaneThreads = 256;
+
+struct PlaneParams {
+    const float* a;          // fwd: x            bwd: dy
+    const float* b;          // fwd: residual     bwd: x
+    const float* y;          // bwd + relu: forward output
+    float* out;              // fwd: y            bwd: dx
+    float* out2;             // bwd: dresidual
+    const float* weight;
+    const float* bias;
+    float* running_mean;
+    float* running_var;
+    float* save_mean;
+    float* save_invstd;
+    float* dweight;
+    float* dbias;
+    double count;
+    float eps, momentum;
+    int replay;
+    unsigned int groups, n, c, hw, pitch;      // pitch: floats per plane slot in shared memory (hw + 8, multiple of 4)
+};
+
+// visit every element of one plane: f(global index inside the plane, shared index) with 128-bit accesses on the aligned body
+template <typename FV, typename FS>
+__device__ __forceinline__ void plane_sweep(const float* gplane, unsigned int hw, unsigned int slot, FV&& vec4, FS&& scalar) {
+    const unsigned int mis = static_cast<unsigned int>((reinterpret_cast<uintptr_t>(gplane) >> 2) & 3u);   // floats past a 16-byte line
+    const unsigned int head = (4u - mis) & 3u, nbody = hw > head ? (hw - head) >> 2 : 0u, tail0 = head + 4u * nbody;
+    const unsigned int s0 = slot + mis;                               // shared index of element 0: same alignment class
+    for (unsigned int v = threadIdx.x; v < nbody; v += kPlaneThreads) vec4(head + 4u * v, s0 + head + 4u * v);
+    if (threadIdx.x < head && threadIdx.x < hw) scalar(threadIdx.x, s0 + threadIdx.x);
+    if (threadIdx.x >= 32 && threadIdx.x - 32 < hw - tail0 && hw > head) scalar(tail0 + threadIdx.x - 32, s0 + tail0 + threadIdx.x - 32);
+}
+
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(kPlaneThreads) bn_fwd_plane_kernel(const PlaneParams p) {
+    extern __shared__ __align__(16) float sh[];
+    __shared__ double scratch[64];
+    __shared__ float2 s_tab[16];
+    const unsigned int ch = blockIdx.x, planes = p.groups * p.n;
+    pdl_wait();
+    pdl_launch_dependents();
+    // ---- one HBM read of the whole domain into shared memory ----
+    for (unsigned int pl = 0; pl < planes; ++pl) {
+        const float* gp = p.a + (static_cast<size_t>(pl) * p.c + ch) * p.hw;
+        plane_sweep(gp, p.hw, pl * p.pitch,
+                    [&](unsigned int gi, unsigned int si) { *reinterpret_cast<float4*>(sh + si) = ld_stream(reinterpret_cast<const float4*>(gp + gi)); },
+                    [&](unsigned int gi, unsigned int si) { sh[si] = ld_stream(gp + gi); });
+    }
+    __syncthreads();
+    // ---- statistics per group out of shared memory (fixed order: deterministic) ----
+    __shared__ double2 s_raw[16];
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        const float kshift = __ldg(p.a + (static_cast<size_t>(g) * p.n * p.c + ch) * p.hw);     // accumulate x - K (see unshift_sums)
+        float a0 = 0.f, a1 = 0.f;
+        for (unsigned int pl = g * p.n; pl < (g + 1) * p.n; ++pl) {
+            const float* gp = p.a + (static_cast<size_t>(pl) * p.c + ch) * p.hw;
+            plane_sweep(gp, p.hw, pl * p.pitch,
+                        [&](unsigned int, unsigned int si) {
+                            const float4 v = *reinterpret_cast<const float4*>(sh + si);
+                            const float tx = v.x - kshift, ty = v.y - kshift, tz = v.z - kshift, tw = v.w - kshift;
+                            a0 += (tx + ty) + (tz + tw);
+                            a1 = fmaf(tx, tx, fmaf(ty, ty, fmaf(tz, tz, fmaf(tw, tw, a1))));
+                        },
+                        [&](unsigned int, unsigned int si) { const float t = sh[si] - kshift; a0 += t; a1 = fmaf(t, t, a1); });
+        }
+        double d0 = a0, d1 = a1;
+        block_sum2(d0, d1, scratch);
+        if (threadIdx.x == 0) s_raw[g] = unshift_sums(d0, d1, p.count, static_cast<double>(kshift));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {                                           // same maths / order as fwd_finalize_channel
+        float rm = p.running_mean ? p.running_mean[ch] : 0.f, rv = p.running_var ? p.running_var[ch] : 0.f;
+        const float w = p.weight ? p.weight[ch] : 1.f, b = p.bias ? p.bias[ch] : 0.f;
+        for (unsigned int g = 0; g < p.groups; ++g) {
+            const double mean = s_raw[g].x / p.count;
+            double var = s_raw[g].y / p.count - mean * mean;
+            var = var < 0.0 ? 0.0 : var;
+            const double invstd = rsqrt(var + static_cast<double>(p.eps));
+            const double unbiased = p.count > 1.0 ? var * (p.count / (p.count - 1.0)) : var;
+            for (int r = 0; r < p.replay; ++r) {
+                rm = static_cast<float>((1.0 - p.momentum) * rm + p.momentum * mean);
+                rv = static_cast<float>((1.0 - p.momentum) * rv + p.momentum * unbiased);
+            }
+            p.save_mean[g * p.c + ch] = static_cast<float>(mean);
+            p.save_invstd[g * p.c + ch] = static_cast<float>(invstd);
+            s_tab[g] = make_float2(static_cast<float>(w * invstd), static_cast<float>(b - mean * w * invstd));
+        }
+        if (p.running_mean) p.running_mean[ch] = rm;
+        if (p.running_var) p.running_var[ch] = rv;
+    }
+    __syncthreads();
+    // ---- normalise (+ residual, + ReLU) out of shared memory, one HBM write ----
+    for (unsigned int pl = 0; pl < planes; ++pl) {
+        const float2 t = s_tab[pl / p.n];
+        const size_t goff = (static_cast<size_t>(pl) * p.c + ch) * p.hw;
+        const float* gp = p.a + goff;
+        const float* rp = RES ? p.b + goff : nullptr;
+        float* op = p.out + goff;
+        auto one = [&](float v, float r) { float o = fmaf(v, t.x, t.y); if (RES) o += r; if (RELU) o = fmaxf(o, 0.f); return o; };
+        plane_sweep(gp, p.hw, pl * p.pitch,
+                    [&](unsigned int gi, unsigned int si) {
+                        const float4 v = *reinterpret_cast<const float4*>(sh + si);
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (RES) r = ld_stream(reinterpret_cast<const float4*>(rp + gi));
+                        *reinterpret_cast<float4*>(op + gi) = make_float4(one(v.x, r.x), one(v.y, r.y), one(v.z, r.z), one(v.w, r.w));
+                    },
+                    [&](unsigned int gi, unsigned int si) { op[gi] = one(sh[si], RES ? ld_stream(rp + gi) : 0.f); });
+    }
+}
+
+// backward: dy (ReLU-masked on load) and x live in shared memory; sums, coefficients and dx out of shared memory
+template <bool RELU, bool DRES>
+__global__ void __launch_bounds__(kPlaneThreads) bn_bwd_plane_kernel(const PlaneParams p) {
+    extern __shared__ __align__(16) float sh[];
+    __shared__ double scratch[64];
+    __shared__ float4 s_cf[16];
+    __shared__ double2 s_sum[16];
+    const unsigned int ch = blockIdx.x, planes = p.groups * p.n;
+    float* sd = sh;                                                    // masked dy
+    float* sx = sh + static_cast<size_t>(planes) * p.pitch;            // x
+    pdl_wait();
+    pdl_launch_dependents();
+    for (unsigned int pl = 0; pl < planes; ++pl) {
+        const size_t goff = (static_cast<size_t>(pl) * p.c + ch) * p.hw;
+        const float* dp = p.a + goff;
+        const float* xp = p.b + goff;
+        const float* yp = RELU ? p.y + goff : nullptr;
+        plane_sweep(dp, p.hw, pl * p.pitch,
+                    [&](unsigned int gi, unsigned int si) {
+                        float4 d = ld_stream(reinterpret_cast<const float4*>(dp + gi));
+                        if (RELU) {
+                            const float4 yy = ld_stream(reinterpret_cast<const float4*>(yp + gi));
+                            if (!(yy.x > 0.f)) d.x = 0.f;
+                            if (!(yy.y > 0.f)) d.y = 0.f;
+                            if (!(yy.z > 0.f)) d.z = 0.f;
+                            if (!(yy.w > 0.f)) d.w = 0.f;
+                        }
+                        *reinterpret_cast<float4*>(sd + si) = d;
+                        *reinterpret_cast<float4*>(sx + si) = ld_stream(reinterpret_cast<const float4*>(xp + gi));
+                    },
+                    [&](unsigned int gi, unsigned int si) {
+                        float d = ld_stream(dp + gi);
+                        if (RELU && !(ld_stream(yp + gi) > 0.f)) d = 0.f;
+                        sd[si] = d;
+                        sx[si] = ld_stream(xp + gi);
+                    });
+    }
+    __syncthreads();
+    for (unsigned int g = 0; g < p.groups; ++g) {
+        const float mean = p.save_mean[g * p.c + ch];
+        float a0 = 0.f, a1 = 0.f;
+        for (unsigned int pl = g * p.n; pl < (g + 1) * p.n; ++pl) {
+            const float* dp = p.a + (static_cast<size_t>(pl) * p.c + ch) * p.hw;
+            plane_sweep(dp, p.hw, pl * p.pitch,
+                        [&](unsigned int, unsigned int si) {
+                            const float4 d = *reinterpret_cast<const float4*>(sd + si), xv = *reinterpret_cast<const float4*>(sx + si);
+                            a0 += (d.x + d.y) + (d.z + d.w);
+                            a1 = fmaf(d.x, xv.x - mean, fmaf(d.y, xv.y - mean, fmaf(d.z, xv.z - mean, fmaf(d.w, xv.w - mean, a1))));
+                        },
+                        [&](unsigned int, unsigned int si) { a0 += sd[si]; a1 = fmaf(sd[si], sx[si] - mean, a1); });
+        }
+        double d0 = a0, d1 = a1;
+        block_sum2(d0, d1, scratch);
+        if (threadIdx.x == 0) {
+            const unsigned int gc = g * p.c + ch;
+            const float invstd = p.save_invstd[gc], w = p.weight ? p.weight[ch] : 1.f;
+            const double s_dyxh = d1 * static_cast<double>(invstd);
+            s_sum[g] = make_double2(d0, s_dyxh);
+            s_cf[g] = make_float4(w * invstd, static_cast<float>(d0 / p.count), static_cast<float>(s_dyxh / p.count * invstd), mean);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double dw = 0.0, db = 0.0;
+        for (unsigned int g = 0; g < p.groups; ++g) { db += s_sum[g].x; dw += s_sum[g].y; }
+        if (p.dweight) p.dweight[ch] = static_cast<float>(dw);
+        if (p.dbias) p.dbias[ch] = static_cast<float>(db);
+    }
+    for (unsigned int pl = 0; pl < planes; ++pl) {
+        const float4 cf = s_cf[pl / p.n];
+        const size_t goff = (static_cast<size_t>(pl) * p.c + ch) * p.hw;
+        const float* dp = p.a + goff;
+        float* op = p.out + goff;
+        float* rp = DRES ? p.out2 + goff : nullptr;
+        auto one = [&](float d, float xv) { return cf.x * (d - cf.y - (xv - cf.w) * cf.z); };
+        plane_sweep(dp, p.hw, pl * p.pitch,
+                    [&](unsigned int gi, unsigned int si) {
+                        const float4 d = *reinterpret_cast<const float4*>(sd + si), xv = *reinterpret_cast<const float4*>(sx + si);
+                        *reinterpret_cast<float4*>(op + gi) = make_float4(one(d.x, xv.x), one(d.y, xv.y), one(d.z, xv.z), one(d.w, xv.w));
+                        if (DRES) *reinterpret_cast<float4*>(rp + gi) = d;
+                    },
+                    [&](unsigned int gi, unsigned int si) { op[gi] = one(sd[si], sx[si]); if (DRES) rp[gi] = sd[si]; });
+    }
+}
+
+// applicable when H*W is not a multiple of 4 (the vector paths cover the rest), every tensor is 4-byte aligned in the same
+// class per plane (true for same-shaped contiguous tensors whose bases are 16-byte aligned) and the domain fits
+__host__ inline size_t plane_smem_bytes(int64_t groups, int64_t n, int64_t hw, int tensors) {
+    const int64_t pitch = ((hw + 3) / 4) * 4 + 8;
+    return static_cast<size_t>(groups * n * pitch * tensors) * sizeof(float);
+}
+__host__ inline bool plane_path_ok(int64_t groups, int64_t n, int64_t c, int64_t hw, int tensors, bool bases_aligned) {
+    // measured on B200 (4 x C x 33 x 33): C = 2048 45.7 -> 32.9 us fwd, 67.9 -> 55.4 us bwd; C = 256 is slower than the cluster
+    // paths (256 CTAs do not fill the chip) -> only when the channels alone give >= 4 CTAs per SM
+    return bases_aligned && hw % 4 != 0 && groups <= 16 && c >= 4 * static_cast<int64_t>(sm_count()) &&
+           plane_smem_bytes(groups, n, hw, tensors) <= 100 * 1024;
+}
+template <typename K>
+__host__ inline int launch_plane(K kernel, const PlaneParams& p, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+        return (cudaGetLastError(), AFAN_ERR_LAUNCH);
+    return launch_pdl(kernel, dim3(p.c), dim3(kPlaneThreads), smem, st, p);
 }
 
 // ---- host helpers -------------------------------------------------------------------------------
@@ -1191,6 +1455,19 @@ AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const flo
     if (!s.ok) return AFAN_OK;
     if (!x || !y || !save_mean || !save_invstd) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;   // uniform contract on both paths
+    if (plane_path_ok(groups, n, c, hw, 1, al)) {                    // odd H*W, small domain: plane-resident single pass
+        PlaneParams pp{};
+        pp.a = x; pp.b = residual; pp.out = y; pp.weight = weight; pp.bias = bias;
+        pp.running_mean = running_mean; pp.running_var = running_var; pp.save_mean = save_mean; pp.save_invstd = save_invstd;
+        pp.count = static_cast<double>(n) * static_cast<double>(hw);
+        pp.eps = eps; pp.momentum = momentum; pp.replay = replay;
+        pp.groups = static_cast<unsigned int>(groups); pp.n = static_cast<unsigned int>(n); pp.c = static_cast<unsigned int>(c);
+        pp.hw = static_cast<unsigned int>(hw); pp.pitch = static_cast<unsigned int>(((hw + 3) / 4) * 4 + 8);
+        const size_t smem = plane_smem_bytes(groups, n, hw, 1);
+        const bool r = relu != 0, rs = residual != nullptr;
+        if (r) return rs ? launch_plane(bn_fwd_plane_kernel<true, true>, pp, smem, st) : launch_plane(bn_fwd_plane_kernel<true, false>, pp, smem, st);
+        return rs ? launch_plane(bn_fwd_plane_kernel<false, true>, pp, smem, st) : launch_plane(bn_fwd_plane_kernel<false, false>, pp, smem, st);
+    }
     const int cs = pick_cluster(groups, n, c, hw, s.vec);
     const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 16);
     if (cs > 0 || rp.nv > 0) {                                       // single-launch cluster paths
@@ -1322,6 +1599,19 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
     if (!s.ok) return AFAN_OK;
     if (!dy || !x || !dx || !save_mean || !save_invstd || (relu && !y)) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
+    if (plane_path_ok(groups, n, c, hw, 2, al)) {                    // odd H*W, small domain: plane-resident single pass
+        PlaneParams pp{};
+        pp.a = dy; pp.b = x; pp.y = y; pp.out = dx; pp.out2 = dresidual; pp.weight = weight;
+        pp.save_mean = const_cast<float*>(save_mean); pp.save_invstd = const_cast<float*>(save_invstd);
+        pp.dweight = dweight; pp.dbias = dbias;
+        pp.count = static_cast<double>(n) * static_cast<double>(hw);
+        pp.groups = static_cast<unsigned int>(groups); pp.n = static_cast<unsigned int>(n); pp.c = static_cast<unsigned int>(c);
+        pp.hw = static_cast<unsigned int>(hw); pp.pitch = static_cast<unsigned int>(((hw + 3) / 4) * 4 + 8);
+        const size_t smem = plane_smem_bytes(groups, n, hw, 2);
+        const bool r = relu != 0, dr = dresidual != nullptr;
+        if (r) return dr ? launch_plane(bn_bwd_plane_kernel<true, true>, pp, smem, st) : launch_plane(bn_bwd_plane_kernel<true, false>, pp, smem, st);
+        return dr ? launch_plane(bn_bwd_plane_kernel<false, true>, pp, smem, st) : launch_plane(bn_bwd_plane_kernel<false, false>, pp, smem, st);
+    }
     const int cs = pick_cluster(groups * 3, n, c, hw, s.vec);        // three tensors are swept twice
     const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 8);    // dy and x are both held: G*NV <= 8
     if (cs > 0 || rp.nv > 0) {
@@ -1356,6 +1646,34 @@ two_launch_bwd:
                                 workspace_bytes, groups, n, c, hw, relu, al1, st, &s);
     if (rc != AFAN_OK || !s.ok) return rc;
     return afan_bn_bwd_apply_f32(dy, x, y, dx, dresidual, workspace, workspace_bytes, groups, n, c, hw, relu, stream);
+}
+
+/* Backward of BatchNorm + ReLU whose forward output was never materialised (the convolution that consumed it applied the
+ * normalisation while loading, afan_conv3x3_umma_bn_f32): the ReLU mask is recomputed from x and the forward's
+ * (scale, shift) table.  Register-resident cluster plan only (every tail shape of the CIFAR ResNets). */
+AFAN_EXPORT int afan_bn_bwd_xmask_f32(const float* dy, const float* x, const float* mask_table, const float* weight,
+                                      const float* save_mean, const float* save_invstd, float* dx, float* dweight,
+                                      float* dbias, int64_t groups, int64_t n, int64_t c, int64_t hw, afan_stream_t stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool al = aligned16(dy) && aligned16(x) && aligned16(dx);
+    BnShape s = bn_shape(groups, n, c, hw, al);
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_OK;
+    if (!dy || !x || !dx || !save_mean || !save_invstd || !mask_table) return AFAN_ERR_NULL;
+    const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 8);
+    if (rp.nv == 0) return AFAN_ERR_UNSUPPORTED;
+    ClusterParams p{};
+    p.a = dy; p.b = x; p.y = nullptr; p.out = dx; p.out2 = nullptr; p.weight = weight;
+    p.save_mean = const_cast<float*>(save_mean); p.save_invstd = const_cast<float*>(save_invstd);
+    p.dweight = dweight; p.dbias = dbias;
+    p.count = static_cast<double>(n) * static_cast<double>(hw);
+    p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
+    p.mask_table = reinterpret_cast<const float2*>(mask_table);
+    const P2PParams noq{};
+#define AFAN_XB(G_, NV_) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, false, false>, p, rp.cs, st, noq);
+    if (groups == 1) { switch (rp.nv) { case 1: AFAN_XB(1, 1) case 2: AFAN_XB(1, 2) case 4: AFAN_XB(1, 4) default: AFAN_XB(1, 8) } }
+    else             { switch (rp.nv) { case 1: AFAN_XB(2, 1) case 2: AFAN_XB(2, 2) default: AFAN_XB(2, 4) } }
+#undef AFAN_XB
 }
 
 AFAN_EXPORT int afan_bn_bwd_reduce_f32(const float* dy, const float* x, const float* y, const float* save_mean,

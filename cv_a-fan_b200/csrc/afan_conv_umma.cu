@@ -143,11 +143,35 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
 }
 
+// ---- BatchNorm folded into the convolution (round 2, verdict item 4) -------------------------------------------------
+// in_table: the PRODUCER's BatchNorm + ReLU applied while staging (normalise-on-load): v = max(0, x * scale + shift) with
+//           the per-(group, channel) table the producer convolution's finaliser wrote -- the intermediate
+//           relu(bn1(conv1(x))) of a BasicBlock (resnet_s.py:70-72) is never materialised.
+// partials: per-CTA per-channel {sum, sum of squares} of THIS convolution's output, folded in a fixed order by the last
+//           CTA of the grid, which then finalises the train-mode statistics exactly like the BatchNorm kernels do
+//           (afan_bn.cu: fwd_finalize_channel): save_mean / save_invstd, running statistics (pass order, `replay` times)
+//           and the (scale, shift) table for the consumer.
+struct Fuse {
+    const float2* in_table;
+    double2* partials;
+    unsigned int* counter;
+    const float* bn_weight;
+    const float* bn_bias;
+    float* running_mean;
+    float* running_var;
+    float* save_mean;
+    float* save_invstd;
+    float2* out_table;
+    double count;
+    float eps, momentum;
+    int replay, n_per_group, groups;
+};
+
 // ---- the kernel ----------------------------------------------------------------------------------------
 template <int C, int H>
 __global__ void __launch_bounds__(kThreadsTotal, 1)
 conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, float* __restrict__ y,
-                    const float* __restrict__ addend, const int dbg) {
+                    const float* __restrict__ addend, const Fuse f, const int dbg) {
     using K = Cfg<C, H>;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -266,6 +290,7 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
         __syncwarp();
     } else {
         // ================= staging: raw fp32 chunk -> {hi, lo} TF32 tiles in the band-interleaved layout =================
+        if (f.in_table) pdl_wait();            // the table is the previous kernel's output: order these threads' reads too
         for (int kc = 0; kc < K::NCHUNK; ++kc) {
             const int s = kc % kAStages;
             mbar_wait(raw_full(kc), 0);
@@ -278,16 +303,23 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
                 *reinterpret_cast<uint4*>(a_hi + off) = hi;
                 *reinterpret_cast<uint4*>(a_lo + off) = lo;
             };
+            // normalise-on-load: the producer's BatchNorm + ReLU (per-(group, channel) scale / shift) or the identity
+            auto bn_relu = [&](float v, const float2* tab, int ch) {
+                if (!tab) return v;
+                const float2 t = __ldg(tab + ch);
+                return fmaxf(fmaf(v, t.x, t.y), 0.f);
+            };
             if (dbg & 4) {                          // dbg bit 2: timing probe, no staging work
             } else if constexpr (H == 16) {
                 const int py = tid >> 4, px = tid & 15, b = py >> 1, odd = py & 1;
+                const float2* tab = f.in_table ? f.in_table + (n0 / f.n_per_group) * C + kc * 8 : nullptr;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     uint4 hi, lo;
-                    split_tf32(raw[(4 * j + 0) * 256 + tid], hi.x, lo.x);
-                    split_tf32(raw[(4 * j + 1) * 256 + tid], hi.y, lo.y);
-                    split_tf32(raw[(4 * j + 2) * 256 + tid], hi.z, lo.z);
-                    split_tf32(raw[(4 * j + 3) * 256 + tid], hi.w, lo.w);
+                    split_tf32(bn_relu(raw[(4 * j + 0) * 256 + tid], tab, 4 * j + 0), hi.x, lo.x);
+                    split_tf32(bn_relu(raw[(4 * j + 1) * 256 + tid], tab, 4 * j + 1), hi.y, lo.y);
+                    split_tf32(bn_relu(raw[(4 * j + 2) * 256 + tid], tab, 4 * j + 2), hi.z, lo.z);
+                    split_tf32(bn_relu(raw[(4 * j + 3) * 256 + tid], tab, 4 * j + 3), hi.w, lo.w);
                     put((odd + 1) * K::PW + px + 1, j, b, hi, lo);
                     if (!odd && b > 0) put(3 * K::PW + px + 1, j, b - 1, hi, lo);     // bottom halo row of the band above
                     if (odd && b < 7) put(px + 1, j, b + 1, hi, lo);                  // top halo row of the band below
@@ -295,11 +327,12 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
             } else {
                 const int j = tid >> 7, r = tid & 127, im = r & 1, px = (r >> 1) & 7, py = r >> 4;
                 const float* src = raw + im * (K::RAW_IMG / 4 + 16) + py * 8 + px;
+                const float2* tab = f.in_table ? f.in_table + ((n0 + im) / f.n_per_group) * C + kc * 8 : nullptr;
                 uint4 hi, lo;
-                split_tf32(src[(4 * j + 0) * 64], hi.x, lo.x);
-                split_tf32(src[(4 * j + 1) * 64], hi.y, lo.y);
-                split_tf32(src[(4 * j + 2) * 64], hi.z, lo.z);
-                split_tf32(src[(4 * j + 3) * 64], hi.w, lo.w);
+                split_tf32(bn_relu(src[(4 * j + 0) * 64], tab, 4 * j + 0), hi.x, lo.x);
+                split_tf32(bn_relu(src[(4 * j + 1) * 64], tab, 4 * j + 1), hi.y, lo.y);
+                split_tf32(bn_relu(src[(4 * j + 2) * 64], tab, 4 * j + 2), hi.z, lo.z);
+                split_tf32(bn_relu(src[(4 * j + 3) * 64], tab, 4 * j + 3), hi.w, lo.w);
                 const int qx = (px + 1) * 2 + im;
                 put(K::PW + qx, j, py, hi, lo);
                 if (py > 0) put(2 * K::PW + qx, j, py - 1, hi, lo);
@@ -317,6 +350,25 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
         {
         const int wq = warp & 3, bnd = lane & 7, g = 4 * wq + (lane >> 3);
         const uint32_t lane_base = static_cast<uint32_t>(32 * wq) << 16;
+        // output statistics: the staging ring is free now (every MMA has completed) and serves as reduction scratch.
+        // Per 16-channel slab a warp transposes its 32 pixels x 16 channels through shared memory (pitch 33: conflict
+        // free) and lane (ci, kind) sums channel ci over the 32 pixels in a fixed order: kind 0 = sum, 1 = sum of squares.
+        float* red = reinterpret_cast<float*>(smem + K::OFF_A) + warp * (16 * 33);
+        float* wsum = reinterpret_cast<float*>(smem + K::OFF_A) + 8 * 16 * 33;               // [8 warps][2 slabs][32]
+        auto slab_stats = [&](const float (&v)[16], int slab) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) red[i * 33 + lane] = v[i];
+            __syncwarp();
+            const int ci = lane & 15, kind = lane >> 4;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const float t = red[ci * 33 + j];
+                acc = kind ? fmaf(t, t, acc) : acc + t;
+            }
+            wsum[(warp * 2 + slab) * 32 + lane] = acc;
+            __syncwarp();
+        };
         if constexpr (H == 16) {
             const int mt = warp >> 2, oy = bnd * 2 + mt, ox = g;
             const size_t o = (static_cast<size_t>(n0) * C * H + oy) * H + ox;
@@ -331,6 +383,7 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
                     const size_t oi = o + static_cast<size_t>(half * 16 + i) * H * H;
                     y[oi] = addend ? __fadd_rn(v[i], __ldg(addend + oi)) : v[i];
                 }
+                if (f.partials) slab_stats(v, half);
             }
         } else {
             const int half = warp >> 2, oy = bnd, ox = g >> 1, im = g & 1;
@@ -344,10 +397,62 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
                 const size_t oi = o + static_cast<size_t>(i) * H * H;
                 y[oi] = addend ? __fadd_rn(v[i], __ldg(addend + oi)) : v[i];
             }
+            if (f.partials) slab_stats(v, 0);
+        }
+        if (f.partials) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");                   // the 8 epilogue warps only
+            // CTA partial per channel: fixed order over the warps that hold the channel
+            if (tid < 2 * kNT) {
+                const int cl = tid & (kNT - 1), kind = tid >> 5;             // local channel 0..31, 0 = sum / 1 = squares
+                double acc = 0.0;
+                if constexpr (H == 16) {
+                    for (int w = 0; w < 8; ++w) acc += static_cast<double>(wsum[(w * 2 + (cl >> 4)) * 32 + (cl & 15) + 16 * kind]);
+                } else {
+                    for (int w = 0; w < 4; ++w) acc += static_cast<double>(wsum[((4 * (cl >> 4) + w) * 2) * 32 + (cl & 15) + 16 * kind]);
+                }
+                double* dst = reinterpret_cast<double*>(f.partials + static_cast<size_t>(blockIdx.x) * C + ns * kNT + cl);
+                dst[kind] = acc;
+            }
         }
         }
     }
 done:
+    if (f.partials) {
+        // ---- last CTA of the grid: fold the partials in CTA order, finalise the train-mode statistics ----
+        __shared__ int s_last;
+        if (last_cta_arrives(f.counter, gridDim.x * gridDim.y, &s_last)) {
+            double* fold = reinterpret_cast<double*>(smem + K::OFF_A + 32 * 1024);           // [groups][C][2]
+            const int per_g = f.n_per_group / K::IMG;                                        // CTAs (blockIdx.x) per group
+            for (int t = tid; t < f.groups * C * 2; t += kThreadsTotal) {
+                const int gi = t / (2 * C), rest = t - gi * 2 * C, ch = rest >> 1, kind = rest & 1;
+                const double* src = reinterpret_cast<const double*>(f.partials + static_cast<size_t>(gi) * per_g * C + ch) + kind;
+                double acc = 0.0;
+                for (int i = 0; i < per_g; ++i) acc += __ldcg(src + static_cast<size_t>(i) * C * 2);
+                fold[t] = acc;
+            }
+            __syncthreads();
+            if (tid < C) {                       // same maths / order as afan_bn.cu: fwd_finalize_channel
+                float rm = f.running_mean ? f.running_mean[tid] : 0.f, rv = f.running_var ? f.running_var[tid] : 0.f;
+                const float w = f.bn_weight ? f.bn_weight[tid] : 1.f, b = f.bn_bias ? f.bn_bias[tid] : 0.f;
+                for (int gi = 0; gi < f.groups; ++gi) {
+                    const double mean = fold[(gi * C + tid) * 2] / f.count;
+                    double var = fold[(gi * C + tid) * 2 + 1] / f.count - mean * mean;
+                    var = var < 0.0 ? 0.0 : var;
+                    const double invstd = rsqrt(var + static_cast<double>(f.eps));
+                    const double unbiased = f.count > 1.0 ? var * (f.count / (f.count - 1.0)) : var;
+                    for (int r = 0; r < f.replay; ++r) {
+                        rm = static_cast<float>((1.0 - f.momentum) * rm + f.momentum * mean);
+                        rv = static_cast<float>((1.0 - f.momentum) * rv + f.momentum * unbiased);
+                    }
+                    f.save_mean[gi * C + tid] = static_cast<float>(mean);
+                    f.save_invstd[gi * C + tid] = static_cast<float>(invstd);
+                    f.out_table[gi * C + tid] = make_float2(static_cast<float>(w * invstd), static_cast<float>(b - mean * w * invstd));
+                }
+                if (f.running_mean) f.running_mean[tid] = rm;
+                if (f.running_var) f.running_var[tid] = rv;
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) {
@@ -383,7 +488,7 @@ __global__ void conv3x3_pack_umma_kernel(const PackDesc* __restrict__ descs, int
 }
 
 template <int C, int H>
-static int launch_conv(const float* x, const float* wpk, float* y, const float* addend, int64_t n, cudaStream_t st) {
+static int launch_conv(const float* x, const float* wpk, float* y, const float* addend, const Fuse& f, int64_t n, cudaStream_t st) {
     static const int dbg = [] { const char* e = getenv("AFAN_UMMA_DBG"); return e ? atoi(e) : 0; }();
     using K = Cfg<C, H>;
     static bool configured = false;      // benign race: idempotent
@@ -395,8 +500,8 @@ static int launch_conv(const float* x, const float* wpk, float* y, const float* 
     if (n % K::IMG) return AFAN_ERR_UNSUPPORTED;
     static const bool pdl = [] { const char* e = getenv("AFAN_UMMA_PDL"); return !(e && e[0] == '0'); }();
     const dim3 grid(static_cast<unsigned int>(n / K::IMG), K::NSPLIT);
-    if (pdl) return launch_pdl(conv3x3_umma_kernel<C, H>, grid, dim3(kThreadsTotal), K::SMEM, st, x, wpk, y, addend, dbg);
-    conv3x3_umma_kernel<C, H><<<grid, kThreadsTotal, K::SMEM, st>>>(x, wpk, y, addend, dbg);
+    if (pdl) return launch_pdl(conv3x3_umma_kernel<C, H>, grid, dim3(kThreadsTotal), K::SMEM, st, x, wpk, y, addend, f, dbg);
+    conv3x3_umma_kernel<C, H><<<grid, kThreadsTotal, K::SMEM, st>>>(x, wpk, y, addend, f, dbg);
     return launch_status();
 }
 
@@ -427,6 +532,43 @@ AFAN_EXPORT int afan_conv3x3_umma_f32(const float* x, const float* w_packed, flo
     if (!aligned16(x) || !aligned16(w_packed)) return AFAN_ERR_UNSUPPORTED;
     if (!afan_conv3x3_umma_supported(n, c, hw)) return AFAN_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (c == 32) return umma::launch_conv<32, 16>(x, w_packed, y, addend, n, st);
-    return umma::launch_conv<64, 8>(x, w_packed, y, addend, n, st);
+    const umma::Fuse none{};
+    if (c == 32) return umma::launch_conv<32, 16>(x, w_packed, y, addend, none, n, st);
+    return umma::launch_conv<64, 8>(x, w_packed, y, addend, none, n, st);
+}
+
+AFAN_EXPORT int64_t afan_conv3x3_umma_bn_workspace_bytes(int64_t n, int64_t c) {
+    if (n < 1 || c < 1) return AFAN_ERR_SIZE;
+    return 256 + n * c * static_cast<int64_t>(sizeof(double2));      // ticket + one {sum, sum of squares} per (CTA, channel)
+}
+
+AFAN_EXPORT int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, const float* in_table,
+                                         const float* bn_weight, const float* bn_bias, float* running_mean, float* running_var,
+                                         float* save_mean, float* save_invstd, float* out_table, void* workspace,
+                                         int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c, int64_t hw, float eps,
+                                         float momentum, int replay, afan_stream_t stream) {
+    if (!x || !w_packed || !y) return AFAN_ERR_NULL;
+    if (n < 0 || groups < 1) return AFAN_ERR_SIZE;
+    if (n == 0) return AFAN_OK;
+    if (!aligned16(x) || !aligned16(w_packed)) return AFAN_ERR_UNSUPPORTED;
+    if (!afan_conv3x3_umma_supported(n, c, hw) || groups > 2 || n % groups) return AFAN_ERR_UNSUPPORTED;
+    const int64_t npg = n / groups;
+    if (hw == 8 && npg % 2) return AFAN_ERR_UNSUPPORTED;             // two images per CTA must share a statistic group
+    umma::Fuse f{};
+    f.in_table = reinterpret_cast<const float2*>(in_table);
+    f.n_per_group = static_cast<int>(npg);
+    f.groups = static_cast<int>(groups);
+    if (out_table) {                                                 // statistics of the output requested
+        if (!save_mean || !save_invstd) return AFAN_ERR_NULL;
+        if (!workspace || workspace_bytes < afan_conv3x3_umma_bn_workspace_bytes(n, c) || !aligned16(workspace)) return AFAN_ERR_WORKSPACE;
+        f.counter = static_cast<unsigned int*>(workspace);
+        f.partials = reinterpret_cast<double2*>(static_cast<char*>(workspace) + 256);
+        f.bn_weight = bn_weight; f.bn_bias = bn_bias; f.running_mean = running_mean; f.running_var = running_var;
+        f.save_mean = save_mean; f.save_invstd = save_invstd; f.out_table = reinterpret_cast<float2*>(out_table);
+        f.count = static_cast<double>(npg) * static_cast<double>(hw * hw);
+        f.eps = eps; f.momentum = momentum; f.replay = replay;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (c == 32) return umma::launch_conv<32, 16>(x, w_packed, y, nullptr, f, n, st);
+    return umma::launch_conv<64, 8>(x, w_packed, y, nullptr, f, n, st);
 }

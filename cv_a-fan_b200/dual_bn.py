@@ -33,17 +33,46 @@ def statistic_groups(k: int):
         _DEFAULT_GROUPS = old
 
 
-def convert_batchnorm(module: nn.Module) -> nn.Module:
+def convert_batchnorm(module: nn.Module, pooled=()) -> nn.Module:
     """Replace every nn.BatchNorm2d below `module` (in place) by a DualBatchNorm2d that SHARES its Parameter / buffer
-    objects (optimizer arenas, state_dict keys and checkpoints are unaffected).  Returns `module`."""
+    objects (optimizer arenas, state_dict keys and checkpoints are unaffected).  Returns `module`.
+
+    pooled: module types whose BatchNorm normalises globally pooled features ([N, C, 1, 1]: N values per channel), e.g.
+    torchvision's ASPPPooling.  Those layers get a GroupedLibraryBatchNorm2d instead: nothing streams there, and with a
+    handful of values per channel the gradient carries the factor (1 - xhat^2), which any change of summation order moves
+    by ~1e-3 -- the library kernel keeps such layers bit-compatible with the reference's."""
     for name, child in list(module.named_children()):
-        if isinstance(child, nn.BatchNorm2d) and not isinstance(child, DualBatchNorm2d):
+        if isinstance(child, nn.BatchNorm2d) and not isinstance(child, GroupedLibraryBatchNorm2d):
             if not (child.affine and child.track_running_stats) or child.momentum is None:
                 raise AfanError("convert_batchnorm needs affine BatchNorm2d layers with running statistics and a momentum")
-            setattr(module, name, DualBatchNorm2d.from_batchnorm(child))
-        else:
-            convert_batchnorm(child)
+            if pooled and isinstance(module, tuple(pooled)):
+                setattr(module, name, GroupedLibraryBatchNorm2d.from_batchnorm(child))
+            else:
+                setattr(module, name, DualBatchNorm2d.from_batchnorm(child))
+        elif not isinstance(child, DualBatchNorm2d):
+            convert_batchnorm(child, pooled)
     return module
+
+
+class GroupedLibraryBatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d that honours statistic_groups(k): the batch is k passes stacked along N, each normalised by its own
+    call of the library kernel in pass order (= what k separate forward passes do to the running statistics)."""
+
+    @classmethod
+    def from_batchnorm(cls, bn: nn.BatchNorm2d) -> "GroupedLibraryBatchNorm2d":
+        m = cls(bn.num_features, bn.eps, bn.momentum)
+        m.weight, m.bias = bn.weight, bn.bias
+        m.running_mean, m.running_var, m.num_batches_tracked = bn.running_mean, bn.running_var, bn.num_batches_tracked
+        m.train(bn.training)
+        return m
+
+    def forward(self, x):
+        k = _DEFAULT_GROUPS
+        if k == 1 or not self.training:
+            return super().forward(x)
+        if x.shape[0] % k:
+            raise AfanError(f"batch {x.shape[0]} is not divisible into {k} statistic groups")
+        return torch.cat([super(GroupedLibraryBatchNorm2d, self).forward(c) for c in x.chunk(k, dim=0)], dim=0)
 
 
 class _DualBNTrainFn(torch.autograd.Function):

@@ -359,6 +359,53 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0, math: str
     return y
 
 
+def conv3x3_umma_bn_workspace(n: int, c: int, device) -> torch.Tensor:
+    """Zeroed scratch of conv3x3_umma_bn (ticket + per-CTA partial statistics); reusable across calls on one stream."""
+    return torch.zeros(_lib.lib().afan_conv3x3_umma_bn_workspace_bytes(int(n), int(c)) // 8, dtype=torch.float64, device=device)
+
+
+def conv3x3_umma_bn(x: torch.Tensor, w_packed: torch.Tensor, *, in_table: Optional[torch.Tensor] = None, bn=None,
+                    groups: int = 1, eps: float = 1e-5, momentum: float = 0.1, replay: int = 1,
+                    workspace: Optional[torch.Tensor] = None):
+    """tcgen05 convolution with BatchNorm folded in (Classification/resnet_s.py:70-72).
+
+    in_table [groups, C, 2]: apply the PRODUCER's BatchNorm + ReLU while loading x (x is then the producer's raw output).
+    bn = (weight, bias, running_mean, running_var): also compute the train-mode statistics of the OUTPUT for `groups`
+    statistic groups; returns (y, save_mean, save_invstd, table) -- table is what the consumer passes as in_table.
+    Without bn returns (y, None, None, None)."""
+    n, c, h, _ = x.shape
+    y = torch.empty_like(x)
+    sm = si = tab = None
+    a = [None] * 4
+    ws_ptr, ws_bytes = None, 0
+    if bn is not None:
+        sm = torch.empty((groups, c), dtype=torch.float32, device=x.device)
+        si = torch.empty_like(sm)
+        tab = torch.empty((groups, c, 2), dtype=torch.float32, device=x.device)
+        a = [f32(t) for t in bn]
+        if workspace is None:
+            workspace = conv3x3_umma_bn_workspace(n, c, x.device)
+        ws_ptr, ws_bytes = ptr(workspace), workspace.numel() * 8
+    check(_lib.lib().afan_conv3x3_umma_bn_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), f32(in_table, "in_table"),
+                                              a[0], a[1], a[2], a[3], f32(sm), f32(si), f32(tab), ws_ptr, ws_bytes, int(groups),
+                                              n, c, h, float(eps), float(momentum), int(replay), stream()),
+          "afan_conv3x3_umma_bn_f32")
+    return y, sm, si, tab
+
+
+def bn_bwd_xmask(dy, x, table, weight, save_mean, save_invstd, *, groups=1, dweight_out=None, dbias_out=None):
+    """Backward of BatchNorm + ReLU whose output was never stored (consumed by conv3x3_umma_bn(in_table=table)): the
+    ReLU mask is recomputed from x and the table.  Returns (dx, dweight, dbias)."""
+    n, c, hw = _nchw(x, groups)
+    dx = torch.empty_like(x)
+    dweight = torch.empty(c, dtype=torch.float32, device=x.device) if dweight_out is None else dweight_out
+    dbias = torch.empty_like(dweight) if dbias_out is None else dbias_out
+    check(_lib.lib().afan_bn_bwd_xmask_f32(f32(dy, "dy"), f32(x, "x"), f32(table, "table"), f32(weight), f32(save_mean),
+                                           f32(save_invstd), f32(dx), f32(dweight), f32(dbias), groups, n, c, hw, stream()),
+          "afan_bn_bwd_xmask_f32")
+    return dx, dweight, dbias
+
+
 CONV3X3S2_SHAPES = ((16, 32), (32, 16))          # (C_in, H_in) of the two stride-2 stage transitions of the CIFAR ResNets
 
 

@@ -41,7 +41,7 @@ from . import ops, segmentation
 from ._lib import AfanError
 from .dual_bn import DualBatchNorm2d
 
-_BN = (nn.BatchNorm2d, DualBatchNorm2d)
+_BN = (nn.BatchNorm2d, DualBatchNorm2d)         # (GroupedLibraryBatchNorm2d is an nn.BatchNorm2d)
 
 
 class _Arena:
@@ -134,9 +134,10 @@ class SegAfanTrainer:
             raise AfanError("SegAfanTrainer needs the model on a CUDA device: there is no CPU path")
         self.dual_bn = bool(dual_bn)
         if self.dual_bn:
+            from torchvision.models.segmentation.deeplabv3 import ASPPPooling
             for k in range(pertub_idx_se + 1, 5):
                 dual_bn_mod.convert_batchnorm(getattr(model.backbone, f"layer{k}"))
-            dual_bn_mod.convert_batchnorm(model.classifier)
+            dual_bn_mod.convert_batchnorm(model.classifier, pooled=(ASPPPooling,))     # image-pooling branch: library kernel
         # the reference's two SGD groups (main_aug_final.py:79-82)
         self.arenas = [_Arena(model.backbone.parameters(), 0.1 * lr, self.device),
                        _Arena(model.classifier.parameters(), lr, self.device)]

@@ -22,3 +22,18 @@ res["nms_12000_us"] = t(lambda: ops.nms_flags(boxes, scores, 0.7))
 import torchvision
 res["torchvision_nms_12000_us"] = t(lambda: torchvision.ops.nms(boxes, scores, 0.7))
 print(json.dumps(res))
+# ROIAlign at the Faster R-CNN pooler shape: 256 ROIs x 1024 channels, 14 x 14 bins, 38 x 63 map (8 images)
+feat = torch.randn(8, 1024, 38, 63, device=dev, generator=g)
+r = 256
+x1 = torch.rand(r, device=dev, generator=g) * 800; y1 = torch.rand(r, device=dev, generator=g) * 480
+rois = torch.stack([torch.randint(0, 8, (r,), device=dev, generator=g).float(), x1, y1,
+                    x1 + 16 + torch.rand(r, device=dev, generator=g) * 400, y1 + 16 + torch.rand(r, device=dev, generator=g) * 300], 1).contiguous()
+dout = torch.randn(r, 1024, 14, 14, device=dev, generator=g)
+L = pkg._lib.lib(); st = pkg._lib.stream
+out = torch.empty(r, 1024, 14, 14, device=dev); dfeat = torch.empty_like(feat)
+roi_res = {}
+roi_res["roi_align_fwd_256x1024_us"] = t(lambda: pkg._lib.check(L.afan_roi_align_fwd_f32(feat.data_ptr(), rois.data_ptr(), out.data_ptr(), 8, 1024, 38, 63, r, 14, 14, 1 / 16, 0, st()), "afan_roi_align_fwd_f32"))
+roi_res["roi_align_bwd_256x1024_us"] = t(lambda: pkg._lib.check(L.afan_roi_align_bwd_f32(dout.data_ptr(), rois.data_ptr(), dfeat.data_ptr(), 8, 1024, 38, 63, r, 14, 14, 1 / 16, 0, st()), "afan_roi_align_bwd_f32"))
+roi_res["roi_path"] = ("forward: " + ("one thread per element" if os.environ.get("AFAN_ROI_LEGACY") == "1" else "separable tap tables in smem")
+                       + "; backward: " + ("plane-resident smem scatter" if os.environ.get("AFAN_ROI_PLANE_BWD") == "1" else "global atomics"))
+print(json.dumps(roi_res))

@@ -179,3 +179,24 @@ def test_fused_p2p_exchange_loopback_two_virtual_ranks(case):
     np.testing.assert_allclose(db_sum, db_o, rtol=1e-4, atol=1e-3)
     for bx in boxes:
         bx.close()
+
+
+@pytest.mark.parametrize("shape,groups", [((2, 256, 1, 1), 1), ((4, 64, 1, 1), 2), ((2, 64, 5, 5), 1), ((4, 2048, 33, 33), 1),
+                                          ((8, 256, 33, 33), 2), ((128, 32, 16, 16), 1), ((256, 64, 8, 8), 2), ((6, 8, 40, 40), 1)])
+def test_statistics_survive_large_mean_over_std(shape, groups):
+    """Round-2 regression (found on DeepLab's ASPP pooling branch, 2 relu-positive nearly equal values per channel): a
+    sum / sum-of-squares accumulation in fp32 loses the variance when |mean| >> std.  Every forward-statistics kernel
+    accumulates shifted data now; against the library's (two-pass) train-mode BatchNorm in float64."""
+    g = torch.Generator().manual_seed(shape[1] + shape[2])
+    x = 7.0 + 2e-3 * torch.randn(shape, generator=g)                      # mean / std = 3500
+    c = shape[1]
+    wt, b = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    d = dev()
+    rm, rv = torch.zeros(c, device=d), torch.ones(c, device=d)
+    y, sm, si = ops.bn_fwd(x.to(d), None, wt.to(d), b.to(d), rm, rv, ops.bn_workspace(groups, c, d), groups=groups)
+    per = shape[0] // groups
+    ref = torch.cat([F.batch_norm(x[k * per:(k + 1) * per].double(), None, None, wt.double(), b.double(), True, 0.1, 1e-5)
+                     for k in range(groups)])
+    # fp32 inputs carry ~6e-8 * 7 of representation noise themselves: 2e-3 of the normalised values' O(1) scale is the
+    # floor for mean / std = 3500; the unshifted accumulation missed it by 0.3 .. 1.0 (variance lost entirely)
+    assert float((y.double().cpu() - ref).abs().max()) < 5e-3 * float(ref.abs().max())

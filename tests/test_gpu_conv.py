@@ -193,3 +193,82 @@ def test_tcgen05_mode_falls_back_outside_its_shapes(monkeypatch):
         x = torch.randn(n, c, h, h, device=dev)
         ref = F.conv2d(x.double(), m.weight.double(), padding=1)
         assert _rel(m(x), ref) < 6e-5, (n, c, h)
+
+
+@pytest.mark.parametrize("n,c,h,groups", [(128, 32, 16, 1), (128, 64, 8, 1), (256, 32, 16, 2), (256, 64, 8, 2), (6, 32, 16, 2), (4, 64, 8, 1)])
+def test_tcgen05_conv_with_folded_batchnorm(n, c, h, groups):
+    """BatchNorm folded into the tcgen05 convolution (resnet_s.py:70-72): statistics of the output in the epilogue
+    (= the stand-alone dual-BN kernel on the same tensor), the producer's BatchNorm + ReLU applied on load (= convolving the
+    materialised activation), and the BatchNorm + ReLU backward with the mask recomputed from x."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(n + c + h + groups)
+    x = torch.randn(n, c, h, h, generator=g).to(dev)
+    dy = torch.randn(n, c, h, h, generator=g).to(dev)
+    m1, m2 = conv.Conv3x3(c, c, 1).to(dev), conv.Conv3x3(c, c, 1).to(dev)
+    descs = torch.tensor([m1.desc_row(), m2.desc_row()], dtype=torch.int64, device=dev)
+    ops.conv3x3_pack(descs, c, "umma")
+    wf1, wf2 = m1._packed[0], m2._packed[0]
+    w, b = (torch.rand(c, generator=g) + 0.5).to(dev), torch.randn(c, generator=g).to(dev)
+    rm0, rv0 = torch.randn(c, generator=g).to(dev), (torch.rand(c, generator=g) + 0.5).to(dev)
+    # un-fused: conv -> dual BN (+ReLU) kernel -> conv
+    c1 = ops.conv3x3(x, wf1, math="umma")
+    rm_a, rv_a = rm0.clone(), rv0.clone()
+    hmat, sm, si = ops.bn_fwd(c1, None, w, b, rm_a, rv_a, ops.bn_workspace(groups, c, dev), groups=groups, relu=True, replay=2)
+    c2 = ops.conv3x3(hmat, wf2, math="umma")
+    dx_ref, _, dw_ref, db_ref = ops.bn_bwd(dy, c1, hmat, w, sm, si, ops.bn_workspace(groups, c, dev), groups=groups, relu=True)
+    # fused
+    rm_b, rv_b = rm0.clone(), rv0.clone()
+    ws = ops.conv3x3_umma_bn_workspace(n, c, dev)
+    for _ in range(2):                                    # twice: the ticket / partial workspace is reusable
+        rm_b.copy_(rm0); rv_b.copy_(rv0)
+        c1f, smf, sif, tab = ops.conv3x3_umma_bn(x, wf1, bn=(w, b, rm_b, rv_b), groups=groups, replay=2, workspace=ws)
+    c2f, _, _, _ = ops.conv3x3_umma_bn(c1f, wf2, in_table=tab, groups=groups)
+    assert torch.equal(c1f, c1)                           # same MMA sequence
+    torch.testing.assert_close(smf, sm, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sif, si, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rm_b, rm_a, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv_b, rv_a, rtol=1e-5, atol=1e-6)
+    assert _rel(c2f, c2.double()) < 1e-5
+    dxf, dwf, dbf = ops.bn_bwd_xmask(dy, c1f, tab, w, smf, sif, groups=groups)
+    assert _rel(dxf, dx_ref.double()) < 1e-4
+    torch.testing.assert_close(dwf, dw_ref, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(dbf, db_ref, rtol=1e-4, atol=1e-3)
+    # deterministic: fixed-order fold
+    c1g, smg, sig, tabg = ops.conv3x3_umma_bn(x, wf1, bn=(w, b, rm_b.clone(), rv_b.clone()), groups=groups, workspace=ws)
+    assert torch.equal(smg, smf) and torch.equal(tabg, tab)
+
+
+@pytest.mark.parametrize("n,c,h,groups", [(128, 32, 16, 1), (128, 64, 8, 1), (8, 32, 16, 2)])
+def test_fused_basic_block_equals_the_unfused_block(n, c, h, groups, monkeypatch):
+    """AFAN_FUSE_BN1: conv1 -> [bn1 + relu folded into conv2] -> conv2 -> bn2 (+shortcut, relu) with frozen parameters (a
+    PGD ascent pass) against the same block with its four separate launches: output, input gradient, running statistics."""
+    rs = pkg.resnet_s
+    dev = torch.device("cuda:0")
+    monkeypatch.setattr(conv, "MODE", "tc3")
+    torch.manual_seed(n + c)
+    blk = rs.BasicBlock(c, c, 1).to(dev).train()
+    with torch.no_grad():
+        for bn in (blk.bn1, blk.bn2):
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+    for p in blk.parameters():
+        p.requires_grad_(False)
+    x = torch.randn(n, c, h, h, device=dev)
+    dy = torch.randn(n, c, h, h, device=dev)
+    state0 = {k: v.clone() for k, v in blk.state_dict().items()}
+    outs = {}
+    for fuse in (False, True):
+        monkeypatch.setattr(rs, "FUSE_BN1", fuse)
+        blk.load_state_dict(state0)
+        blk.bn1._pending_batches = blk.bn2._pending_batches = 0
+        xr = x.clone().requires_grad_(True)
+        assert blk._fusable(xr, groups) == fuse
+        y = blk(xr, groups=groups, replay=1)
+        (dx,) = torch.autograd.grad(y, xr, dy)
+        outs[fuse] = (y.detach(), dx, {k: v.clone() for k, v in blk.state_dict().items()})
+    (y0, dx0, s0), (y1, dx1, s1) = outs[False], outs[True]
+    assert _rel(y1, y0.double()) < 2e-5 and _rel(dx1, dx0.double()) < 2e-4
+    for k in s0:
+        if s0[k].dtype.is_floating_point:
+            torch.testing.assert_close(s1[k], s0[k], rtol=1e-5, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
+        else:
+            assert torch.equal(s1[k], s0[k]), k

