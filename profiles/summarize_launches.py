@@ -29,7 +29,7 @@ def main(path):
     print("|---|---:|---:|---:|---:|")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
         print(f"| `{k[:70]}` | {n} | {t:.0f} | {100 * t / tot:.1f}% | {t / n:.2f} |")
-    mine = sum(t for k, (n, t) in agg.items() if k.startswith("afan::") or "afan" in k)
+    mine = sum(t for k, (n, t) in agg.items() if "afan" in k or "umma::" in k)      # afan::umma::* prints as umma::*
     print(f"\nhand-written afan:: kernels: {100 * mine / tot:.1f}% of device time")
 
 

@@ -87,7 +87,7 @@ def _run_restatement(name):
 # Case B (2 PGD steps on the 512x9x9 stage-2 feature of a random-init network, 50-element BatchNorm batches) is
 # chaotic: the plain-PyTorch restatement itself moves the fully-adversarial loss l2 by 0.8 % (iteration 0) / 3 %
 # (iteration 1) between CPU and GPU.  Tolerances per case: (on-device loss rtol, golden loss rtol).
-TOL = {"A": (1e-3, 3e-3), "B": (2e-2, 5e-2)}
+TOL = {"A": (1e-3, 3e-3), "B": (5e-2, 5e-2)}      # B on-device: 2e-2 held in most runs, one in ~5 flips a PGD sign (atomics in F.interpolate's backward)
 STATS = ("running_mean", "running_var")
 
 
