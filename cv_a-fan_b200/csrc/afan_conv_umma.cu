@@ -144,17 +144,17 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 }
 
 // ---- BatchNorm folded into the convolution (round 2, verdict item 4) -------------------------------------------------
-// in_table: the PRODUCER's BatchNorm + ReLU applied while staging (normalise-on-load): v = max(0, x * scale + shift) with
-//           the per-(group, channel) table the producer convolution's finaliser wrote -- the intermediate
-//           relu(bn1(conv1(x))) of a BasicBlock (resnet_s.py:70-72) is never materialised.
-// partials: per-CTA per-channel {sum, sum of squares} of THIS convolution's output, folded in a fixed order by the last
-//           CTA of the grid, which then finalises the train-mode statistics exactly like the BatchNorm kernels do
-//           (afan_bn.cu: fwd_finalize_channel): save_mean / save_invstd, running statistics (pass order, `replay` times)
-//           and the (scale, shift) table for the consumer.
+// out_partials: per-CTA per-channel {sum, sum of squares} of THIS convolution's output (plain stores; the kernel boundary
+//           orders them) -- the statistics of the BatchNorm that follows, reduced where the data already sits in registers.
+// in_partials: the PRODUCER convolution's partials.  Every CTA of this (consumer) kernel folds them in CTA order -- 4 threads
+//           per (group, channel, sum) x 32 partials each, combined in a fixed order: deterministic; it runs under the
+//           latency of the first operand loads -- finalises the train-mode statistics like afan_bn.cu: fwd_finalize_channel,
+//           and applies the producer's BatchNorm + ReLU while staging (normalise-on-load): relu(bn1(conv1(x))) of a
+//           BasicBlock (resnet_s.py:70-72) is never materialised.  CTA (0, 0) also writes save_mean / save_invstd / the
+//           (scale, shift) table for the backward pass and advances the running statistics (group order, `replay` times).
 struct Fuse {
-    const float2* in_table;
-    double2* partials;
-    unsigned int* counter;
+    const double2* in_partials;
+    double2* out_partials;
     const float* bn_weight;
     const float* bn_bias;
     float* running_mean;
@@ -243,11 +243,55 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
             *reinterpret_cast<uint4*>(smem + K::OFF_A + tile * K::A_TILE + off) = z;
         }
     }
+    __shared__ float2 s_table[2 * C];                 // [groups <= 2][C]: the producer BatchNorm's (scale, shift)
+    __shared__ double s_fold[2 * C * 2][4];           // [(group, channel, sum | squares)][quarter of the producer's CTAs]
+    if (f.in_partials) {
+        pdl_wait();                                    // the partials are the previous kernel's output
+        const int per_g = f.n_per_group / K::IMG, q4 = (per_g + 3) / 4;       // producer CTAs (blockIdx.x) per statistic group
+        for (int t = tid; t < f.groups * C * 2 * 4; t += kThreadsTotal) {
+            const int o = t >> 2, part = t & 3, gi = o / (2 * C), rest = o - gi * 2 * C, ch = rest >> 1, kind = rest & 1;
+            const double* src = reinterpret_cast<const double*>(f.in_partials + static_cast<size_t>(gi) * per_g * C + ch) + kind;
+            const int i1 = min(per_g, (part + 1) * q4);
+            double acc = 0.0;
+            for (int i = part * q4; i < i1; ++i) acc += __ldcg(src + static_cast<size_t>(i) * C * 2);
+            s_fold[o][part] = acc;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     pdl_launch_dependents();
+    if (f.in_partials && tid < kStageThreads) {
+        if (tid < C) {                                  // same maths / order as afan_bn.cu: fwd_finalize_channel
+            const bool writer = blockIdx.x == 0 && blockIdx.y == 0;
+            float rm = (writer && f.running_mean) ? f.running_mean[tid] : 0.f, rv = (writer && f.running_var) ? f.running_var[tid] : 0.f;
+            const float w = f.bn_weight ? f.bn_weight[tid] : 1.f, b = f.bn_bias ? f.bn_bias[tid] : 0.f;
+            for (int gi = 0; gi < f.groups; ++gi) {
+                const double* s1 = s_fold[(gi * C + tid) * 2], * s2 = s_fold[(gi * C + tid) * 2 + 1];
+                const double sum = ((s1[0] + s1[1]) + s1[2]) + s1[3], sq = ((s2[0] + s2[1]) + s2[2]) + s2[3];
+                const double mean = sum / f.count;
+                double var = sq / f.count - mean * mean;
+                var = var < 0.0 ? 0.0 : var;
+                const double invstd = rsqrt(var + static_cast<double>(f.eps));
+                const double unbiased = f.count > 1.0 ? var * (f.count / (f.count - 1.0)) : var;
+                const float2 t = make_float2(static_cast<float>(w * invstd), static_cast<float>(b - mean * w * invstd));
+                s_table[gi * C + tid] = t;
+                if (writer) {
+                    for (int r = 0; r < f.replay; ++r) {
+                        rm = static_cast<float>((1.0 - f.momentum) * rm + f.momentum * mean);
+                        rv = static_cast<float>((1.0 - f.momentum) * rv + f.momentum * unbiased);
+                    }
+                    f.save_mean[gi * C + tid] = static_cast<float>(mean);
+                    f.save_invstd[gi * C + tid] = static_cast<float>(invstd);
+                    f.out_table[gi * C + tid] = t;
+                }
+            }
+            if (writer && f.running_mean) f.running_mean[tid] = rm;
+            if (writer && f.running_var) f.running_var[tid] = rv;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");       // the 8 staging warps: table complete
+    }
 
     if (warp == 9) {
         // ================= loader: raw activation chunks + packed weight chunks, all by bulk copy =================
@@ -290,7 +334,6 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
         __syncwarp();
     } else {
         // ================= staging: raw fp32 chunk -> {hi, lo} TF32 tiles in the band-interleaved layout =================
-        if (f.in_table) pdl_wait();            // the table is the previous kernel's output: order these threads' reads too
         for (int kc = 0; kc < K::NCHUNK; ++kc) {
             const int s = kc % kAStages;
             mbar_wait(raw_full(kc), 0);
@@ -306,13 +349,13 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
             // normalise-on-load: the producer's BatchNorm + ReLU (per-(group, channel) scale / shift) or the identity
             auto bn_relu = [&](float v, const float2* tab, int ch) {
                 if (!tab) return v;
-                const float2 t = __ldg(tab + ch);
+                const float2 t = tab[ch];
                 return fmaxf(fmaf(v, t.x, t.y), 0.f);
             };
             if (dbg & 4) {                          // dbg bit 2: timing probe, no staging work
             } else if constexpr (H == 16) {
                 const int py = tid >> 4, px = tid & 15, b = py >> 1, odd = py & 1;
-                const float2* tab = f.in_table ? f.in_table + (n0 / f.n_per_group) * C + kc * 8 : nullptr;
+                const float2* tab = f.in_partials ? s_table + (n0 / f.n_per_group) * C + kc * 8 : nullptr;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     uint4 hi, lo;
@@ -327,7 +370,7 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
             } else {
                 const int j = tid >> 7, r = tid & 127, im = r & 1, px = (r >> 1) & 7, py = r >> 4;
                 const float* src = raw + im * (K::RAW_IMG / 4 + 16) + py * 8 + px;
-                const float2* tab = f.in_table ? f.in_table + ((n0 + im) / f.n_per_group) * C + kc * 8 : nullptr;
+                const float2* tab = f.in_partials ? s_table + ((n0 + im) / f.n_per_group) * C + kc * 8 : nullptr;
                 uint4 hi, lo;
                 split_tf32(bn_relu(src[(4 * j + 0) * 64], tab, 4 * j + 0), hi.x, lo.x);
                 split_tf32(bn_relu(src[(4 * j + 1) * 64], tab, 4 * j + 1), hi.y, lo.y);
@@ -383,7 +426,7 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
                     const size_t oi = o + static_cast<size_t>(half * 16 + i) * H * H;
                     y[oi] = addend ? __fadd_rn(v[i], __ldg(addend + oi)) : v[i];
                 }
-                if (f.partials) slab_stats(v, half);
+                if (f.out_partials) slab_stats(v, half);
             }
         } else {
             const int half = warp >> 2, oy = bnd, ox = g >> 1, im = g & 1;
@@ -397,9 +440,9 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
                 const size_t oi = o + static_cast<size_t>(i) * H * H;
                 y[oi] = addend ? __fadd_rn(v[i], __ldg(addend + oi)) : v[i];
             }
-            if (f.partials) slab_stats(v, 0);
+            if (f.out_partials) slab_stats(v, 0);
         }
-        if (f.partials) {
+        if (f.out_partials) {
             asm volatile("bar.sync 1, 256;" ::: "memory");                   // the 8 epilogue warps only
             // CTA partial per channel: fixed order over the warps that hold the channel
             if (tid < 2 * kNT) {
@@ -410,49 +453,13 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
                 } else {
                     for (int w = 0; w < 4; ++w) acc += static_cast<double>(wsum[((4 * (cl >> 4) + w) * 2) * 32 + (cl & 15) + 16 * kind]);
                 }
-                double* dst = reinterpret_cast<double*>(f.partials + static_cast<size_t>(blockIdx.x) * C + ns * kNT + cl);
+                double* dst = reinterpret_cast<double*>(f.out_partials + static_cast<size_t>(blockIdx.x) * C + ns * kNT + cl);
                 dst[kind] = acc;
             }
         }
         }
     }
 done:
-    if (f.partials) {
-        // ---- last CTA of the grid: fold the partials in CTA order, finalise the train-mode statistics ----
-        __shared__ int s_last;
-        if (last_cta_arrives(f.counter, gridDim.x * gridDim.y, &s_last)) {
-            double* fold = reinterpret_cast<double*>(smem + K::OFF_A + 32 * 1024);           // [groups][C][2]
-            const int per_g = f.n_per_group / K::IMG;                                        // CTAs (blockIdx.x) per group
-            for (int t = tid; t < f.groups * C * 2; t += kThreadsTotal) {
-                const int gi = t / (2 * C), rest = t - gi * 2 * C, ch = rest >> 1, kind = rest & 1;
-                const double* src = reinterpret_cast<const double*>(f.partials + static_cast<size_t>(gi) * per_g * C + ch) + kind;
-                double acc = 0.0;
-                for (int i = 0; i < per_g; ++i) acc += __ldcg(src + static_cast<size_t>(i) * C * 2);
-                fold[t] = acc;
-            }
-            __syncthreads();
-            if (tid < C) {                       // same maths / order as afan_bn.cu: fwd_finalize_channel
-                float rm = f.running_mean ? f.running_mean[tid] : 0.f, rv = f.running_var ? f.running_var[tid] : 0.f;
-                const float w = f.bn_weight ? f.bn_weight[tid] : 1.f, b = f.bn_bias ? f.bn_bias[tid] : 0.f;
-                for (int gi = 0; gi < f.groups; ++gi) {
-                    const double mean = fold[(gi * C + tid) * 2] / f.count;
-                    double var = fold[(gi * C + tid) * 2 + 1] / f.count - mean * mean;
-                    var = var < 0.0 ? 0.0 : var;
-                    const double invstd = rsqrt(var + static_cast<double>(f.eps));
-                    const double unbiased = f.count > 1.0 ? var * (f.count / (f.count - 1.0)) : var;
-                    for (int r = 0; r < f.replay; ++r) {
-                        rm = static_cast<float>((1.0 - f.momentum) * rm + f.momentum * mean);
-                        rv = static_cast<float>((1.0 - f.momentum) * rv + f.momentum * unbiased);
-                    }
-                    f.save_mean[gi * C + tid] = static_cast<float>(mean);
-                    f.save_invstd[gi * C + tid] = static_cast<float>(invstd);
-                    f.out_table[gi * C + tid] = make_float2(static_cast<float>(w * invstd), static_cast<float>(b - mean * w * invstd));
-                }
-                if (f.running_mean) f.running_mean[tid] = rm;
-                if (f.running_var) f.running_var[tid] = rv;
-            }
-        }
-    }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) {
@@ -539,14 +546,14 @@ AFAN_EXPORT int afan_conv3x3_umma_f32(const float* x, const float* w_packed, flo
 
 AFAN_EXPORT int64_t afan_conv3x3_umma_bn_workspace_bytes(int64_t n, int64_t c) {
     if (n < 1 || c < 1) return AFAN_ERR_SIZE;
-    return 256 + n * c * static_cast<int64_t>(sizeof(double2));      // ticket + one {sum, sum of squares} per (CTA, channel)
+    return n * c * static_cast<int64_t>(sizeof(double2));            // one {sum, sum of squares} per (CTA <= image, channel)
 }
 
-AFAN_EXPORT int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, const float* in_table,
+AFAN_EXPORT int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, const void* in_partials,
                                          const float* bn_weight, const float* bn_bias, float* running_mean, float* running_var,
-                                         float* save_mean, float* save_invstd, float* out_table, void* workspace,
-                                         int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c, int64_t hw, float eps,
-                                         float momentum, int replay, afan_stream_t stream) {
+                                         float* save_mean, float* save_invstd, float* table_out, void* out_partials,
+                                         int64_t groups, int64_t n, int64_t c, int64_t hw, float eps, float momentum, int replay,
+                                         afan_stream_t stream) {
     if (!x || !w_packed || !y) return AFAN_ERR_NULL;
     if (n < 0 || groups < 1) return AFAN_ERR_SIZE;
     if (n == 0) return AFAN_OK;
@@ -555,19 +562,19 @@ AFAN_EXPORT int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, 
     const int64_t npg = n / groups;
     if (hw == 8 && npg % 2) return AFAN_ERR_UNSUPPORTED;             // two images per CTA must share a statistic group
     umma::Fuse f{};
-    f.in_table = reinterpret_cast<const float2*>(in_table);
     f.n_per_group = static_cast<int>(npg);
     f.groups = static_cast<int>(groups);
-    if (out_table) {                                                 // statistics of the output requested
-        if (!save_mean || !save_invstd) return AFAN_ERR_NULL;
-        if (!workspace || workspace_bytes < afan_conv3x3_umma_bn_workspace_bytes(n, c) || !aligned16(workspace)) return AFAN_ERR_WORKSPACE;
-        f.counter = static_cast<unsigned int*>(workspace);
-        f.partials = reinterpret_cast<double2*>(static_cast<char*>(workspace) + 256);
+    f.out_partials = static_cast<double2*>(out_partials);
+    if (in_partials) {                                               // normalise-on-load with the producer's statistics
+        if (!save_mean || !save_invstd || !table_out) return AFAN_ERR_NULL;
+        if (!aligned16(in_partials)) return AFAN_ERR_UNSUPPORTED;
+        f.in_partials = static_cast<const double2*>(in_partials);
         f.bn_weight = bn_weight; f.bn_bias = bn_bias; f.running_mean = running_mean; f.running_var = running_var;
-        f.save_mean = save_mean; f.save_invstd = save_invstd; f.out_table = reinterpret_cast<float2*>(out_table);
+        f.save_mean = save_mean; f.save_invstd = save_invstd; f.out_table = reinterpret_cast<float2*>(table_out);
         f.count = static_cast<double>(npg) * static_cast<double>(hw * hw);
         f.eps = eps; f.momentum = momentum; f.replay = replay;
     }
+    if (out_partials && !aligned16(out_partials)) return AFAN_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (c == 32) return umma::launch_conv<32, 16>(x, w_packed, y, nullptr, f, n, st);
     return umma::launch_conv<64, 8>(x, w_packed, y, nullptr, f, n, st);

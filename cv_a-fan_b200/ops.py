@@ -360,34 +360,36 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, variant: int = 0, math: str
 
 
 def conv3x3_umma_bn_workspace(n: int, c: int, device) -> torch.Tensor:
-    """Zeroed scratch of conv3x3_umma_bn (ticket + per-CTA partial statistics); reusable across calls on one stream."""
-    return torch.zeros(_lib.lib().afan_conv3x3_umma_bn_workspace_bytes(int(n), int(c)) // 8, dtype=torch.float64, device=device)
+    """Per-CTA partial statistics of conv3x3_umma_bn(stats_out=...) (need not be zeroed; one per producer call in flight)."""
+    return torch.empty(_lib.lib().afan_conv3x3_umma_bn_workspace_bytes(int(n), int(c)) // 8, dtype=torch.float64, device=device)
 
 
-def conv3x3_umma_bn(x: torch.Tensor, w_packed: torch.Tensor, *, in_table: Optional[torch.Tensor] = None, bn=None,
-                    groups: int = 1, eps: float = 1e-5, momentum: float = 0.1, replay: int = 1,
-                    workspace: Optional[torch.Tensor] = None):
+def conv3x3_umma_bn(x: torch.Tensor, w_packed: torch.Tensor, *, stats_out: Optional[torch.Tensor] = None,
+                    stats_in: Optional[torch.Tensor] = None, bn=None, groups: int = 1, eps: float = 1e-5,
+                    momentum: float = 0.1, replay: int = 1):
     """tcgen05 convolution with BatchNorm folded in (Classification/resnet_s.py:70-72).
 
-    in_table [groups, C, 2]: apply the PRODUCER's BatchNorm + ReLU while loading x (x is then the producer's raw output).
-    bn = (weight, bias, running_mean, running_var): also compute the train-mode statistics of the OUTPUT for `groups`
-    statistic groups; returns (y, save_mean, save_invstd, table) -- table is what the consumer passes as in_table.
-    Without bn returns (y, None, None, None)."""
+    stats_out (producer): workspace that receives the per-CTA {sum, sum of squares} of the OUTPUT.
+    stats_in + bn = (weight, bias, running_mean, running_var) (consumer): x is the producer's raw output; its train-mode
+    BatchNorm (+ ReLU) over `groups` statistic groups is applied while loading.  Returns (y, save_mean, save_invstd, table)
+    -- the last three only for a consumer call (what bn_bwd_xmask needs)."""
     n, c, h, _ = x.shape
     y = torch.empty_like(x)
     sm = si = tab = None
     a = [None] * 4
-    ws_ptr, ws_bytes = None, 0
-    if bn is not None:
+    if stats_in is not None:
+        if bn is None:
+            raise AfanError("stats_in needs bn=(weight, bias, running_mean, running_var)")
         sm = torch.empty((groups, c), dtype=torch.float32, device=x.device)
         si = torch.empty_like(sm)
         tab = torch.empty((groups, c, 2), dtype=torch.float32, device=x.device)
         a = [f32(t) for t in bn]
-        if workspace is None:
-            workspace = conv3x3_umma_bn_workspace(n, c, x.device)
-        ws_ptr, ws_bytes = ptr(workspace), workspace.numel() * 8
-    check(_lib.lib().afan_conv3x3_umma_bn_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), f32(in_table, "in_table"),
-                                              a[0], a[1], a[2], a[3], f32(sm), f32(si), f32(tab), ws_ptr, ws_bytes, int(groups),
+    need = _lib.lib().afan_conv3x3_umma_bn_workspace_bytes(n, c) // 8
+    for ws in (stats_in, stats_out):
+        if ws is not None and (ws.dtype != torch.float64 or ws.numel() < need or not ws.is_cuda):
+            raise AfanError("statistics workspace must be a CUDA float64 tensor from conv3x3_umma_bn_workspace(n, c)")
+    check(_lib.lib().afan_conv3x3_umma_bn_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), ptr(stats_in),
+                                              a[0], a[1], a[2], a[3], f32(sm), f32(si), f32(tab), ptr(stats_out), int(groups),
                                               n, c, h, float(eps), float(momentum), int(replay), stream()),
           "afan_conv3x3_umma_bn_f32")
     return y, sm, si, tab

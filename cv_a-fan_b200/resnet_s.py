@@ -21,11 +21,13 @@ from . import ops
 from .conv import Conv3x3
 from .dual_bn import DualBatchNorm2d
 
-# AFAN_FUSE_BN1=1: in passes that need no weight gradients (the PGD ascent: attack_algo.py:52 `only_inputs=True`) an
+# AFAN_FUSE_BN1 (default on): in passes that need no weight gradients (the PGD ascent: attack_algo.py:52 `only_inputs=True`) an
 # identity BasicBlock runs conv1 -> [bn1 + relu folded into conv2's operand staging] -> conv2: conv1's tcgen05 kernel reduces
 # the BatchNorm statistics of its own output in its epilogue, conv2 normalises while it loads, and relu(bn1(conv1(x))) is
-# never written to memory -- one BatchNorm launch and 8 B/element of traffic less per block and pass.
-FUSE_BN1 = os.environ.get("AFAN_FUSE_BN1", "0") == "1"
+# never written to memory -- one BatchNorm launch and 8 B/element of traffic less per block and pass (80 launches per
+# step at config 2; same-box A/B 11.18 -> 10.89 ms).  Single process only: with a BatchNorm exchange configured the block
+# keeps its four launches.
+FUSE_BN1 = os.environ.get("AFAN_FUSE_BN1", "1") == "1"
 
 
 class _FusedConvBnReluConvFn(torch.autograd.Function):
@@ -42,9 +44,9 @@ class _FusedConvBnReluConvFn(torch.autograd.Function):
         ws = block._fuse_ws.get((n, c, x.device))
         if ws is None:
             ws = block._fuse_ws[(n, c, x.device)] = ops.conv3x3_umma_bn_workspace(n, c, x.device)
-        c1, sm, si, tab = ops.conv3x3_umma_bn(x, wf1, bn=(bn.weight, bn.bias, bn.running_mean, bn.running_var), groups=groups,
-                                              eps=bn.eps, momentum=bn.momentum, replay=replay, workspace=ws)
-        c2, _, _, _ = ops.conv3x3_umma_bn(c1, wf2, in_table=tab, groups=groups)
+        c1, _, _, _ = ops.conv3x3_umma_bn(x, wf1, stats_out=ws, groups=groups)
+        c2, sm, si, tab = ops.conv3x3_umma_bn(c1, wf2, stats_in=ws, bn=(bn.weight, bn.bias, bn.running_mean, bn.running_var),
+                                              groups=groups, eps=bn.eps, momentum=bn.momentum, replay=replay)
         ctx.save_for_backward(c1, tab, sm, si, bn.weight)
         ctx.wd1, ctx.wd2, ctx.groups = wd1, wd2, groups
         return c2, x.view_as(x)

@@ -276,21 +276,22 @@ int afan_conv3x3_pack_umma_f32(const void* descs_device, int64_t n_layers, int64
 int afan_conv3x3_umma_f32(const float* x, const float* w_packed, float* y, const float* addend, int64_t n, int64_t c,
                           int64_t hw, afan_stream_t stream);
 /* BatchNorm folded into the tcgen05 convolution (resnet_s.py:70-72 `relu(bn1(conv1(x)))` -> `conv2`, train mode):
- *   out_table != NULL: the kernel also reduces per-channel {sum, sum of squares} of its OUTPUT (per-CTA partials, folded
- *     in a fixed order by the last CTA), finalises the train-mode statistics of `groups` statistic groups along the batch
- *     exactly like afan_bn_fwd_f32 (save_mean / save_invstd [groups][c], running statistics updated in group order,
- *     `replay` times) and writes the per-(group, channel) {scale, shift} table [groups][c][2] of the BatchNorm that
- *     follows.  workspace >= afan_conv3x3_umma_bn_workspace_bytes(n, c), zeroed once.
- *   in_table != NULL: the PRODUCER's BatchNorm + ReLU is applied while the input is staged (v = max(0, x*scale + shift)
- *     with that table): the normalised activation is never written to memory.
+ *   out_partials != NULL (producer, conv1): the kernel also writes per-CTA per-channel {sum, sum of squares} of its
+ *     OUTPUT into out_partials (>= afan_conv3x3_umma_bn_workspace_bytes(n, c) bytes; need not be zeroed).
+ *   in_partials != NULL (consumer, conv2): x is the producer's raw output and in_partials its statistics.  Every CTA
+ *     folds them in a fixed order, finalises the train-mode statistics of `groups` statistic groups along the batch
+ *     exactly like afan_bn_fwd_f32 and applies BatchNorm + ReLU while the input is staged (v = max(0, x*scale + shift)):
+ *     the normalised activation is never written to memory.  One CTA also writes save_mean / save_invstd [groups][c],
+ *     the {scale, shift} table [groups][c][2] (for afan_bn_bwd_xmask_f32) and advances the running statistics in
+ *     group order, `replay` times.
  * afan_bn_bwd_xmask_f32 is the matching BatchNorm + ReLU backward: the ReLU mask is recomputed from x and the table
  * (there is no stored forward output).  Same shape support as afan_conv3x3_umma_f32; groups in {1, 2}. */
 int64_t afan_conv3x3_umma_bn_workspace_bytes(int64_t n, int64_t c);
-int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, const float* in_table,
+int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, const void* in_partials,
                              const float* bn_weight, const float* bn_bias, float* running_mean, float* running_var,
-                             float* save_mean, float* save_invstd, float* out_table, void* workspace,
-                             int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c, int64_t hw, float eps,
-                             float momentum, int replay, afan_stream_t stream);
+                             float* save_mean, float* save_invstd, float* table_out, void* out_partials,
+                             int64_t groups, int64_t n, int64_t c, int64_t hw, float eps, float momentum, int replay,
+                             afan_stream_t stream);
 int afan_bn_bwd_xmask_f32(const float* dy, const float* x, const float* mask_table, const float* weight,
                           const float* save_mean, const float* save_invstd, float* dx, float* dweight, float* dbias,
                           int64_t groups, int64_t n, int64_t c, int64_t hw, afan_stream_t stream);

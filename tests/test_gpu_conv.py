@@ -216,13 +216,13 @@ def test_tcgen05_conv_with_folded_batchnorm(n, c, h, groups):
     hmat, sm, si = ops.bn_fwd(c1, None, w, b, rm_a, rv_a, ops.bn_workspace(groups, c, dev), groups=groups, relu=True, replay=2)
     c2 = ops.conv3x3(hmat, wf2, math="umma")
     dx_ref, _, dw_ref, db_ref = ops.bn_bwd(dy, c1, hmat, w, sm, si, ops.bn_workspace(groups, c, dev), groups=groups, relu=True)
-    # fused
+    # fused: the producer writes per-CTA statistics, the consumer folds them and normalises while loading
     rm_b, rv_b = rm0.clone(), rv0.clone()
     ws = ops.conv3x3_umma_bn_workspace(n, c, dev)
-    for _ in range(2):                                    # twice: the ticket / partial workspace is reusable
+    for _ in range(2):                                    # twice: the workspace is reusable as is
         rm_b.copy_(rm0); rv_b.copy_(rv0)
-        c1f, smf, sif, tab = ops.conv3x3_umma_bn(x, wf1, bn=(w, b, rm_b, rv_b), groups=groups, replay=2, workspace=ws)
-    c2f, _, _, _ = ops.conv3x3_umma_bn(c1f, wf2, in_table=tab, groups=groups)
+        c1f, _, _, _ = ops.conv3x3_umma_bn(x, wf1, stats_out=ws, groups=groups)
+        c2f, smf, sif, tab = ops.conv3x3_umma_bn(c1f, wf2, stats_in=ws, bn=(w, b, rm_b, rv_b), groups=groups, replay=2)
     assert torch.equal(c1f, c1)                           # same MMA sequence
     torch.testing.assert_close(smf, sm, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(sif, si, rtol=1e-5, atol=1e-6)
@@ -234,8 +234,8 @@ def test_tcgen05_conv_with_folded_batchnorm(n, c, h, groups):
     torch.testing.assert_close(dwf, dw_ref, rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(dbf, db_ref, rtol=1e-4, atol=1e-3)
     # deterministic: fixed-order fold
-    c1g, smg, sig, tabg = ops.conv3x3_umma_bn(x, wf1, bn=(w, b, rm_b.clone(), rv_b.clone()), groups=groups, workspace=ws)
-    assert torch.equal(smg, smf) and torch.equal(tabg, tab)
+    c2g, smg, sig, tabg = ops.conv3x3_umma_bn(c1f, wf2, stats_in=ws, bn=(w, b, rm_b.clone(), rv_b.clone()), groups=groups)
+    assert torch.equal(smg, smf) and torch.equal(tabg, tab) and torch.equal(c2g, c2f)
 
 
 @pytest.mark.parametrize("n,c,h,groups", [(128, 32, 16, 1), (128, 64, 8, 1), (8, 32, 16, 2)])
