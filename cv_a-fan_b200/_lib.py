@@ -69,6 +69,8 @@ SIGNATURES = {
     "afan_conv3x3_umma_bn_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
                                         _f32, _f32, _int, _vp]),
     "afan_bn_bwd_xmask_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "afan_conv3x3_wgrad_umma_supported": (_int, [_i64, _i64, _i64]),
+    "afan_conv3x3_wgrad_umma_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
     "afan_conv3x3_wgrad_workspace_bytes": (_i64, [_i64]),
     "afan_conv3x3_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
 }
@@ -76,7 +78,7 @@ SIGNATURES = {
 AFAN_ERR_UNSUPPORTED = -5
 _lib = None
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); bumped by check() on success
-KERNELS_PER_CALL = {"afan_nms_f32": 2, "afan_conv3x3_wgrad_f32": 2, "afan_conv3x3s2_wgrad_f32": 2}
+KERNELS_PER_CALL = {"afan_nms_f32": 2, "afan_conv3x3_wgrad_f32": 2, "afan_conv3x3_wgrad_umma_f32": 2, "afan_conv3x3s2_wgrad_f32": 2}
 launch_count = 0
 
 

@@ -66,8 +66,26 @@ def wgrad_overlap_join():
         _overlap["active"] = False
 
 
+WGRAD_UMMA = os.environ.get("AFAN_WGRAD_UMMA", "1") == "1"      # tcgen05 weight gradient in "tc3" mode (tail shapes)
+
+
+def _wgrad_math(mod, x) -> str:
+    # measured on B200 (L2-cold, kernel + fold): 128x32x16x16 21.1 vs 22.5 us (FFMA), 256x32x16x16 29.2 vs 38.7 us,
+    # 256x64x8x8 50.8 vs 36.8 us -> the tcgen05 weight gradient is used for the C = 32 layers only
+    if MODE == "tc3" and WGRAD_UMMA and mod.stride == (1, 1) and mod.out_channels == 32 and \
+            ops.conv3x3_wgrad_umma_supported(x.shape[0], mod.out_channels, x.shape[2]):
+        return "umma"
+    return "fp32"
+
+
+def _wgrad_s1(x, dy, ws, accumulate_into=None, mod=None):
+    return ops.conv3x3_wgrad(x, dy, ws, accumulate_into=accumulate_into, math=_wgrad_math(mod, x))
+
+
 def _arena_wgrad(fn, x, dy, mod):
     """Weight gradient added straight into mod.weight.grad (a slice of the trainer's gradient arena)."""
+    if fn is ops.conv3x3_wgrad:
+        fn = lambda a, b, ws, accumulate_into=None: _wgrad_s1(a, b, ws, accumulate_into, mod)
     if not _overlap["active"]:
         fn(x, dy, mod.wgrad_workspace(), accumulate_into=mod.weight.grad)
         return
@@ -98,7 +116,7 @@ class _Conv3x3Fn(torch.autograd.Function):
             if mod.grad_direct and mod.weight.grad is not None:
                 _arena_wgrad(ops.conv3x3_wgrad, x, dy, mod)                                        # no temporary, no add launch
             else:
-                dw = ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace())
+                dw = _wgrad_s1(x, dy, mod.wgrad_workspace(), mod=mod)
         return dx, dw, None
 
 
@@ -128,7 +146,7 @@ class _Conv3x3TapFn(torch.autograd.Function):
             if mod.grad_direct and mod.weight.grad is not None:
                 _arena_wgrad(ops.conv3x3_wgrad, x, dy, mod)
             else:
-                dw = ops.conv3x3_wgrad(x, dy, mod.wgrad_workspace())
+                dw = _wgrad_s1(x, dy, mod.wgrad_workspace(), mod=mod)
         return dx, dw, None
 
 

@@ -446,13 +446,23 @@ def conv3x3_wgrad_workspace(c: int, device) -> torch.Tensor:
     return torch.empty(_lib.lib().afan_conv3x3_wgrad_workspace_bytes(int(c)) // 4, dtype=torch.float32, device=device)
 
 
-def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, ws: torch.Tensor, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+def conv3x3_wgrad_umma_supported(n: int, c: int, h: int) -> bool:
+    return bool(_lib.lib().afan_conv3x3_wgrad_umma_supported(int(n), int(c), int(h)))
+
+
+def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, ws: torch.Tensor, accumulate_into: Optional[torch.Tensor] = None,
+                  math: str = "fp32") -> torch.Tensor:
     """dW [C, C, 3, 3] of the convolution above (deterministic: per-CTA partials folded in a fixed order).
-    accumulate_into: add the result to this tensor (a parameter's .grad inside the gradient arena) instead."""
+    accumulate_into: add the result to this tensor (a parameter's .grad inside the gradient arena) instead.
+    math: "fp32" (FFMA kernel) or "umma" (tcgen05 3xTF32, (C, H) in {(32, 16), (64, 8)})."""
     n, c, h, _ = x.shape
     dw = torch.empty((c, c, 3, 3), dtype=torch.float32, device=x.device) if accumulate_into is None else accumulate_into
     if dw.numel() != c * c * 9:
         raise AfanError("accumulate_into must hold C*C*9 floats")
+    if math == "umma":
+        check(_lib.lib().afan_conv3x3_wgrad_umma_f32(f32(x, "x"), f32(dy, "dy"), f32(dw), ptr(ws), ws.numel() * 4, n, c, h,
+                                                     int(accumulate_into is not None), stream()), "afan_conv3x3_wgrad_umma_f32")
+        return dw
     check(_lib.lib().afan_conv3x3_wgrad_f32(f32(x, "x"), f32(dy, "dy"), f32(dw), ptr(ws), ws.numel() * 4, n, c, h,
                                             int(accumulate_into is not None), stream()), "afan_conv3x3_wgrad_f32")
     return dw

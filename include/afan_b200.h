@@ -295,6 +295,13 @@ int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, co
 int afan_bn_bwd_xmask_f32(const float* dy, const float* x, const float* mask_table, const float* weight,
                           const float* save_mean, const float* save_invstd, float* dx, float* dweight, float* dbias,
                           int64_t groups, int64_t n, int64_t c, int64_t hw, afan_stream_t stream);
+/* tcgen05 twin of afan_conv3x3_wgrad_f32 for (c, hw) in {(32, 16), (64, 8)}: the weight gradient as a GEMM whose
+ * reduction dimension is the pixels (kind::tf32, 3xTF32 split, TMEM accumulators; the three kx shifts are materialised
+ * while staging and form the M dimension, ky shifts are descriptor offsets), persistent CTAs, one partial dW per CTA and
+ * a fixed-order fold (deterministic).  Same workspace (afan_conv3x3_wgrad_workspace_bytes(c)) and accumulate semantics. */
+int afan_conv3x3_wgrad_umma_supported(int64_t n, int64_t c, int64_t hw);
+int afan_conv3x3_wgrad_umma_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
+                                int64_t n, int64_t c, int64_t hw, int accumulate, afan_stream_t stream);
 int64_t afan_conv3x3_wgrad_workspace_bytes(int64_t c);
 int afan_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, void* workspace, int64_t workspace_bytes,
                            int64_t n, int64_t c, int64_t hw, int accumulate, afan_stream_t stream);

@@ -57,3 +57,16 @@ for n, c, h in [(128, 32, 16), (128, 64, 8), (256, 32, 16), (256, 64, 8)]:
             out["max_abs_diff_vs_ffma"] = float((got - ref).abs().max())
     print(f"conv3x3 {n}x{c}x{h}x{h}: ffma {out['afan']:.2f} us, tcgen05 3xtf32 {out['tc3']:.2f} us, "
           f"max |diff| {out['max_abs_diff_vs_ffma']:.2e}", flush=True)
+
+# weight gradient: FFMA kernel (+ fold) vs tcgen05 kernel (+ fold)
+for n, c, h in [(128, 32, 16), (256, 32, 16), (256, 64, 8)]:
+    res = {}
+    R = max(2, min(24, (4 * 126 * 2 ** 20) // (8 * n * c * h * h)))
+    sets = [(torch.randn(n, c, h, h, device=dev), torch.randn(n, c, h, h, device=dev), ops.conv3x3_wgrad_workspace(c, dev),
+             torch.zeros(c, c, 3, 3, device=dev)) for _ in range(R)]
+    for math in ("fp32", "umma"):
+        res[math] = time_graph(lambda s: ops.conv3x3_wgrad(s[0], s[1], s[2], accumulate_into=s[3], math=math), sets)
+    a = ops.conv3x3_wgrad(sets[0][0], sets[0][1], sets[0][2], math="fp32")
+    b = ops.conv3x3_wgrad(sets[0][0], sets[0][1], sets[0][2], math="umma")
+    print(f"wgrad {n}x{c}x{h}x{h}: ffma {res['fp32']:.2f} us, tcgen05 3xtf32 {res['umma']:.2f} us, max |diff| {float((a - b).abs().max()):.2e} "
+          f"(max |dw| {float(a.abs().max()):.1f})", flush=True)
