@@ -35,7 +35,10 @@ def time_graph(run, sets, reps=10):
     return a.elapsed_time(b) * 1e3 / (reps * len(sets))
 
 
-for n, c, h in [(128, 32, 16), (128, 64, 8), (256, 32, 16), (256, 64, 8)]:
+SHAPES = [(128, 32, 16), (128, 64, 8), (256, 32, 16), (256, 64, 8)]
+if os.environ.get("AFAN_PROBE_SHAPE"):                      # e.g. "128,64,8": one shape only (ncu captures)
+    SHAPES = [tuple(int(v) for v in os.environ["AFAN_PROBE_SHAPE"].split(","))]
+for n, c, h in SHAPES:
     out = {}
     for mode, math in (("afan", "fp32"), ("tc3", "umma")):
         conv.MODE = mode
@@ -59,7 +62,7 @@ for n, c, h in [(128, 32, 16), (128, 64, 8), (256, 32, 16), (256, 64, 8)]:
           f"max |diff| {out['max_abs_diff_vs_ffma']:.2e}", flush=True)
 
 # weight gradient: FFMA kernel (+ fold) vs tcgen05 kernel (+ fold)
-for n, c, h in [(128, 32, 16), (256, 32, 16), (256, 64, 8)]:
+for n, c, h in ([] if os.environ.get("AFAN_PROBE_SHAPE") else [(128, 32, 16), (256, 32, 16), (256, 64, 8)]):
     res = {}
     R = max(2, min(24, (4 * 126 * 2 ** 20) // (8 * n * c * h * h)))
     sets = [(torch.randn(n, c, h, h, device=dev), torch.randn(n, c, h, h, device=dev), ops.conv3x3_wgrad_workspace(c, dev),
