@@ -737,7 +737,9 @@ def main():
             "e2e": {"value": global_batch * args.steps / sec_e2e, "unit": "img/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * sec_e2e / args.steps},
             "gpu_launches": per_iter * args.steps, "afan_kernels_per_step": per_iter}
-    detail.update({"cuda_graph": not args.no_graph, "sync_bn": (not args.no_sync_bn) and world > 1,
+    detail.update({"bn1_folded_into_conv2_in_ascent": bool(pkg.resnet_s.FUSE_BN1) and world == 1 and pkg.conv.MODE == "tc3",
+                   "wgrad_tcgen05_c32": bool(pkg.conv.WGRAD_UMMA) and pkg.conv.MODE == "tc3",
+                   "cuda_graph": not args.no_graph, "sync_bn": (not args.no_sync_bn) and world > 1,
                    "bn_exchange": trainer.bn_exchange_used, "final_loss": loss_dev})
     if world > 1:
         line["bn_exchange"] = trainer.bn_exchange_used
