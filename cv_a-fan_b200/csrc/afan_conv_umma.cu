@@ -25,9 +25,11 @@
 //   warp 9   loader:   cp.async.bulk (TMA bulk copy, UBLKCP) of the raw NCHW channel chunks (8 channels = one K step of
 //                      every tap; contiguous in NCHW) and of the packed weight chunk -> mbarrier complete_tx
 //   warps 0-7 staging: raw chunk -> {hi, lo} TF32 tiles in the layout above (generic stores + fence.proxy.async)
-//   warp 8   MMA:      one thread issues MT x 9 taps x 3 tcgen05.mma.kind::tf32 per chunk, accumulators in TMEM;
-//                      tcgen05.commit releases the staging / weight buffers and finally publishes the accumulator
-//   warps 0-7 epilogue: tcgen05.ld (TMEM -> registers), optional addend (identity-shortcut gradient), store NCHW.
+//   warp 8   MMA:      one elected thread issues MT x 9 taps x {A_hi x [B_hi ; B_lo] (N = 64), A_lo x B_hi (N = 32)} per chunk,
+//                      accumulators in TMEM; tcgen05.commit releases the staging / weight buffers and finally publishes
+//                      the accumulator
+//   warps 0-7 epilogue: tcgen05.ld (TMEM -> registers), sum of the two column halves, optional addend (identity-shortcut
+//                      gradient), optional per-channel output statistics (folded BatchNorm, see struct Fuse), store NCHW.
 // Accumulation order is fixed by the issue order: results are bitwise reproducible run to run.
 #include "afan_umma.cuh"
 

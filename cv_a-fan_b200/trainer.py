@@ -11,7 +11,9 @@ again) -> backward -> SGD.  Here:
   * dual-BN tail    the final adversarial and clean tail passes run as ONE pass over [adv; clean] with
                     per-half batch statistics (groups=2) -- same maths as the reference's two passes.
   * fused PGD       one kernel per step (ascent + projection), per-sample ||delta|| norms fused into
-                    the last step (no D2H), tail parameters frozen during the ascent (dgrad only).
+                    the last step (no D2H), tail parameters frozen during the ascent (dgrad only) -- which
+                    also lets every identity block run conv1 -> [bn1 + relu folded into conv2] -> conv2
+                    (resnet_s.FUSE_BN1: statistics in conv1's tcgen05 epilogue, normalise-on-load).
   * flat arena      parameters / gradients / momentum live in three flat buffers: ONE fused SGD kernel,
                     ONE NCCL all-reduce of the gradient arena per iteration (weak-scaling data parallel).
   * CUDA graph      the whole iteration (forward, ascent loop, backward, all-reduce, SGD) is captured
