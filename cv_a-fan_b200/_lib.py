@@ -69,6 +69,10 @@ SIGNATURES = {
     "afan_conv3x3_umma_bn_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64,
                                         _f32, _f32, _int, _vp]),
     "afan_bn_bwd_xmask_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "afan_conv3x3_umma_bn_p2p_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _f32,
+                                            _int, _int, _int, _vp, _i64, _vp, _vp]),
+    "afan_bn_bwd_xmask_p2p_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64,
+                                         _vp, _vp]),
     "afan_conv3x3_wgrad_umma_supported": (_int, [_i64, _i64, _i64]),
     "afan_conv3x3_wgrad_umma_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp]),
     "afan_conv3x3_wgrad_workspace_bytes": (_i64, [_i64]),

@@ -22,6 +22,7 @@
 #include <type_traits>
 
 #include "afan_common.cuh"
+#include "afan_p2p.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -669,42 +670,6 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
 // of every launch increments seq.  RING >= 2 suffices: a GPU can run ahead of a peer by at most one exchange
 // (it cannot pass exchange k+1 before the peer has published k+1, i.e. finished reading k).
 // -----------------------------------------------------------------------------------------------------
-constexpr int kP2PMaxWorld = 8;
-constexpr int kP2PRing = 4;
-// A lost peer must neither hang the GPU nor go unnoticed: after `timeout_cycles` (AFAN_P2P_TIMEOUT_S, default 60 s --
-// the bound on tolerated inter-rank skew, e.g. rank 0 writing a checkpoint) the waiting rank sets state[2] AND poisons
-// the folded statistics with NaN, so every later loss on that rank is NaN instead of silently wrong.
-constexpr double kP2PDefaultTimeoutS = 60.0;
-constexpr double kP2PCyclesPerSecond = 1.9e9;
-
-struct P2PParams {
-    void* peers[kP2PMaxWorld];        // peer-mapped mailbox base of every rank (peers[rank] = own mailbox)
-    unsigned long long* state;        // local: {seq, ticket, error}
-    int world, rank;
-    unsigned int cmax;
-    long long timeout_cycles;
-};
-
-// LL-style in-band flags (the idea of NCCL's low-latency protocol): every double travels as one 16-byte word
-// {lo32, tag, hi32, tag}; each 8-byte half carries its own tag, so the word is self-validating however the
-// fabric splits the store -- no fence, no separate flag, ONE one-way NVLink latency per exchange.
-// word index: ((((slot * world + src) * cmax + ch) * 2 + g) * 2 + k),  k = 0: first sum, 1: second sum.
-__host__ __device__ inline size_t p2p_word_off(unsigned int slot, unsigned int src, unsigned int ch, unsigned int g, unsigned int k,
-                                               int world, unsigned int cmax) {
-    return ((((static_cast<size_t>(slot) * world + src) * cmax + ch) * 2 + g) * 2 + k) * sizeof(uint4);
-}
-__host__ inline int64_t p2p_mailbox_bytes(int world, int64_t cmax) {
-    return static_cast<int64_t>(kP2PRing) * world * cmax * 4 * sizeof(uint4);
-}
-__device__ __forceinline__ void st_sys_u32x4(uint4* p, uint4 v) {
-    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_sys_u32x4(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-
 // Cluster fold + cross-GPU fold.  Returns the GLOBAL totals in threads g < groups of EVERY CTA; the rank-0
 // CTA additionally keeps the LOCAL totals in s_loc (the backward needs them for dweight / dbias).
 __device__ __forceinline__ double2 cluster_fold_p2p(cg::cluster_group& cluster, double2* s_part,
@@ -1676,6 +1641,35 @@ AFAN_EXPORT int afan_bn_bwd_xmask_f32(const float* dy, const float* x, const flo
 #undef AFAN_XB
 }
 
+/* afan_bn_bwd_xmask_f32 with the statistics of the GLOBAL batch (fused NVLink exchange, like afan_bn_bwd_p2p_f32). */
+AFAN_EXPORT int afan_bn_bwd_xmask_p2p_f32(const float* dy, const float* x, const float* mask_table, const float* weight,
+                                          const float* save_mean, const float* save_invstd, float* dx, float* dweight,
+                                          float* dbias, int64_t groups, int64_t n, int64_t c, int64_t hw, int world, int rank,
+                                          void* const* peer_mailboxes, int64_t cmax, void* state, afan_stream_t stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool al = aligned16(dy) && aligned16(x) && aligned16(dx);
+    BnShape s = bn_shape(groups, n, c, hw, al);
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_ERR_UNSUPPORTED;
+    if (!dy || !x || !dx || !save_mean || !save_invstd || !mask_table) return AFAN_ERR_NULL;
+    const RegPlan rp = pick_reg_plan(groups, n, c, hw, s.vec, 8);
+    if (rp.nv == 0) return AFAN_ERR_UNSUPPORTED;
+    P2PParams q{};
+    const int rc = fill_p2p(q, world, rank, peer_mailboxes, cmax, state, c);
+    if (rc != AFAN_OK) return rc;
+    ClusterParams p{};
+    p.a = dy; p.b = x; p.y = nullptr; p.out = dx; p.out2 = nullptr; p.weight = weight;
+    p.save_mean = const_cast<float*>(save_mean); p.save_invstd = const_cast<float*>(save_invstd);
+    p.dweight = dweight; p.dbias = dbias;
+    p.count = static_cast<double>(n) * static_cast<double>(hw) * world;
+    p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv;
+    p.mask_table = reinterpret_cast<const float2*>(mask_table);
+#define AFAN_XBP(G_, NV_) return launch_cluster(bn_bwd_cluster_reg_kernel<G_, NV_, true, false, true>, p, rp.cs, st, q);
+    if (groups == 1) { switch (rp.nv) { case 1: AFAN_XBP(1, 1) case 2: AFAN_XBP(1, 2) case 4: AFAN_XBP(1, 4) default: AFAN_XBP(1, 8) } }
+    else             { switch (rp.nv) { case 1: AFAN_XBP(2, 1) case 2: AFAN_XBP(2, 2) default: AFAN_XBP(2, 4) } }
+#undef AFAN_XBP
+}
+
 AFAN_EXPORT int afan_bn_bwd_reduce_f32(const float* dy, const float* x, const float* y, const float* save_mean,
                                        const float* save_invstd, double* sums, float* dweight, float* dbias,
                                        void* workspace, int64_t workspace_bytes, int64_t groups, int64_t n, int64_t c,
@@ -1705,25 +1699,6 @@ AFAN_EXPORT int afan_bn_bwd_finalize_f32(const double* sums, double count, const
 }
 
 // ---- fused multi-GPU entry points (statistics exchanged over NVLink peer memory inside the kernel) -------------
-static int fill_p2p(P2PParams& q, int world, int rank, void* const* peer_mailboxes, int64_t cmax, void* state, int64_t c) {
-    if (world < 2 || world > kP2PMaxWorld || rank < 0 || rank >= world || cmax < c) return AFAN_ERR_UNSUPPORTED;
-    if (!peer_mailboxes || !state) return AFAN_ERR_NULL;
-    for (int i = 0; i < world; ++i) {
-        if (!peer_mailboxes[i]) return AFAN_ERR_NULL;
-        q.peers[i] = peer_mailboxes[i];
-    }
-    q.state = static_cast<unsigned long long*>(state);
-    q.world = world; q.rank = rank; q.cmax = static_cast<unsigned int>(cmax);
-    static const long long timeout = [] {
-        const char* e = std::getenv("AFAN_P2P_TIMEOUT_S");
-        double sec = e ? std::atof(e) : kP2PDefaultTimeoutS;
-        if (!(sec > 0.0)) sec = kP2PDefaultTimeoutS;
-        return static_cast<long long>(sec * kP2PCyclesPerSecond);
-    }();
-    q.timeout_cycles = timeout;
-    return AFAN_OK;
-}
-
 AFAN_EXPORT int64_t afan_bn_mailbox_bytes(int world, int64_t cmax) {
     if (world < 1 || world > kP2PMaxWorld || cmax < 1) return AFAN_ERR_SIZE;
     return p2p_mailbox_bytes(world, cmax);

@@ -31,6 +31,7 @@
 //   warps 0-7 epilogue: tcgen05.ld (TMEM -> registers), sum of the two column halves, optional addend (identity-shortcut
 //                      gradient), optional per-channel output statistics (folded BatchNorm, see struct Fuse), store NCHW.
 // Accumulation order is fixed by the issue order: results are bitwise reproducible run to run.
+#include "afan_p2p.cuh"
 #include "afan_umma.cuh"
 
 namespace afan {
@@ -59,7 +60,7 @@ struct Cfg {
     static constexpr int PW = (H + 2) * IMG;               // positions per padded band row
     static constexpr int NQ = (R + 2) * PW;
     static constexpr int NCHUNK = C / 8;
-    static constexpr int WS = NCHUNK < 4 ? NCHUNK : (C == 32 ? 4 : 3);    // weight ring (C = 32: all four chunks resident)
+    static constexpr int WS = 3;                           // weight ring
     static constexpr uint32_t A_TILE = NQ * kSboA;         // one of {hi, lo}
     static constexpr uint32_t A_STAGE = 2 * A_TILE;
     static constexpr uint32_t RAW_IMG = 8 * H * H * 4;     // one image, one chunk of 8 channels
@@ -99,6 +100,8 @@ struct Fuse {
     double count;
     float eps, momentum;
     int replay, n_per_group, groups;
+    P2PParams q;            // q.world > 1: the folded sums are exchanged with the peer GPUs (same mailbox / sequence as the
+                            // BatchNorm kernels, afan_p2p.cuh) before the statistics are finalised: global-batch BatchNorm
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------------
@@ -179,8 +182,13 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
     }
     __shared__ float2 s_table[2 * C];                 // [groups <= 2][C]: the producer BatchNorm's (scale, shift)
     __shared__ double s_fold[2 * C * 2][4];           // [(group, channel, sum | squares)][quarter of the producer's CTAs]
+    __shared__ double s_recv[kP2PMaxWorld][2 * C * 2];   // multi-GPU: every rank's sums (rank order)
+    const bool p2p = f.in_partials && f.q.world > 1;
+    unsigned long long seq = 0ULL;
     if (f.in_partials) {
         pdl_wait();                                    // the partials are the previous kernel's output
+        if (p2p) seq = *reinterpret_cast<const volatile unsigned long long*>(f.q.state);   // after the wait: the previous
+                                                       // exchanging kernel's last CTA advanced it at ITS end
         const int per_g = f.n_per_group / K::IMG, q4 = (per_g + 3) / 4;       // producer CTAs (blockIdx.x) per statistic group
         for (int t = tid; t < f.groups * C * 2 * 4; t += kThreadsTotal) {
             const int o = t >> 2, part = t & 3, gi = o / (2 * C), rest = o - gi * 2 * C, ch = rest >> 1, kind = rest & 1;
@@ -196,6 +204,29 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     pdl_launch_dependents();
+    if (p2p && tid < kStageThreads) {
+        // ---- exchange with the peer GPUs (LL words with in-band tags, one one-way NVLink latency; see afan_p2p.cuh) ----
+        const int NO = f.groups * C * 2, items = f.q.world * NO;
+        const unsigned int slot = static_cast<unsigned int>(seq % kP2PRing), tag = p2p_tag(seq);
+        for (int t = tid; t < items; t += kStageThreads) {
+            const int peer = t / NO, o = t - peer * NO, gi = o / (2 * C), rest = o - gi * 2 * C, ch = rest >> 1, kind = rest & 1;
+            if (blockIdx.x == 0 && blockIdx.y == 0) {        // ONE CTA per rank publishes this rank's local sums to every mailbox
+                const double* s4 = s_fold[o];
+                p2p_publish(f.q, peer, slot, ch, gi, kind, tag, ((s4[0] + s4[1]) + s4[2]) + s4[3]);
+            }
+        }
+        for (int t = tid; t < items; t += kStageThreads) {   // every CTA collects all ranks' sums from its own GPU's mailbox
+            const int src = t / NO, o = t - src * NO, gi = o / (2 * C), rest = o - gi * 2 * C, ch = rest >> 1, kind = rest & 1;
+            s_recv[src][o] = p2p_collect(f.q, src, slot, ch, gi, kind, tag);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        for (int o = tid; o < NO; o += kStageThreads) {      // rank order on every GPU: bit-identical statistics everywhere
+            double tot = 0.0;
+            for (int r = 0; r < f.q.world; ++r) tot += s_recv[r][o];
+            s_fold[o][0] = tot; s_fold[o][1] = 0.0; s_fold[o][2] = 0.0; s_fold[o][3] = 0.0;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+    }
     if (f.in_partials && tid < kStageThreads) {
         if (tid < C) {                                  // same maths / order as afan_bn.cu: fwd_finalize_channel
             const bool writer = blockIdx.x == 0 && blockIdx.y == 0;
@@ -394,6 +425,11 @@ conv3x3_umma_kernel(const float* __restrict__ x, const float* __restrict__ wpk, 
         }
     }
 done:
+    if (p2p) {                                           // the last CTA advances the exchange sequence (all CTAs have read it)
+        __shared__ int s_last;
+        if (last_cta_arrives(reinterpret_cast<unsigned int*>(f.q.state + 1), gridDim.x * gridDim.y, &s_last) && tid == 0)
+            f.q.state[0] = f.q.state[0] + 1ULL;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) {
@@ -483,11 +519,11 @@ AFAN_EXPORT int64_t afan_conv3x3_umma_bn_workspace_bytes(int64_t n, int64_t c) {
     return n * c * static_cast<int64_t>(sizeof(double2));            // one {sum, sum of squares} per (CTA <= image, channel)
 }
 
-AFAN_EXPORT int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, const void* in_partials,
-                                         const float* bn_weight, const float* bn_bias, float* running_mean, float* running_var,
-                                         float* save_mean, float* save_invstd, float* table_out, void* out_partials,
-                                         int64_t groups, int64_t n, int64_t c, int64_t hw, float eps, float momentum, int replay,
-                                         afan_stream_t stream) {
+static int conv_bn_impl(const float* x, const float* w_packed, float* y, const void* in_partials,
+                        const float* bn_weight, const float* bn_bias, float* running_mean, float* running_var,
+                        float* save_mean, float* save_invstd, float* table_out, void* out_partials,
+                        int64_t groups, int64_t n, int64_t c, int64_t hw, float eps, float momentum, int replay,
+                        const P2PParams* q, afan_stream_t stream) {
     if (!x || !w_packed || !y) return AFAN_ERR_NULL;
     if (n < 0 || groups < 1) return AFAN_ERR_SIZE;
     if (n == 0) return AFAN_OK;
@@ -507,9 +543,36 @@ AFAN_EXPORT int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, 
         f.save_mean = save_mean; f.save_invstd = save_invstd; f.out_table = reinterpret_cast<float2*>(table_out);
         f.count = static_cast<double>(npg) * static_cast<double>(hw * hw);
         f.eps = eps; f.momentum = momentum; f.replay = replay;
+        if (q) {                                                     // statistics of the GLOBAL batch: n images on each of `world` GPUs
+            f.q = *q;
+            f.count *= q->world;
+        }
     }
     if (out_partials && !aligned16(out_partials)) return AFAN_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (c == 32) return umma::launch_conv<32, 16>(x, w_packed, y, nullptr, f, n, st);
     return umma::launch_conv<64, 8>(x, w_packed, y, nullptr, f, n, st);
+}
+
+AFAN_EXPORT int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, const void* in_partials,
+                                         const float* bn_weight, const float* bn_bias, float* running_mean, float* running_var,
+                                         float* save_mean, float* save_invstd, float* table_out, void* out_partials,
+                                         int64_t groups, int64_t n, int64_t c, int64_t hw, float eps, float momentum, int replay,
+                                         afan_stream_t stream) {
+    return conv_bn_impl(x, w_packed, y, in_partials, bn_weight, bn_bias, running_mean, running_var, save_mean, save_invstd, table_out,
+                        out_partials, groups, n, c, hw, eps, momentum, replay, nullptr, stream);
+}
+
+AFAN_EXPORT int afan_conv3x3_umma_bn_p2p_f32(const float* x, const float* w_packed, float* y, const void* in_partials,
+                                             const float* bn_weight, const float* bn_bias, float* running_mean, float* running_var,
+                                             float* save_mean, float* save_invstd, float* table_out, int64_t groups, int64_t n,
+                                             int64_t c, int64_t hw, float eps, float momentum, int replay, int world, int rank,
+                                             void* const* peer_mailboxes, int64_t cmax, void* state, afan_stream_t stream) {
+    if (!in_partials) return AFAN_ERR_NULL;
+    if (n > sm_count()) return AFAN_ERR_UNSUPPORTED;                 // every CTA spins on its peers: the grid must be co-resident
+    P2PParams q{};
+    const int rc = fill_p2p(q, world, rank, peer_mailboxes, cmax, state, c);
+    if (rc != AFAN_OK) return rc;
+    return conv_bn_impl(x, w_packed, y, in_partials, bn_weight, bn_bias, running_mean, running_var, save_mean, save_invstd, table_out,
+                        nullptr, groups, n, c, hw, eps, momentum, replay, &q, stream);
 }

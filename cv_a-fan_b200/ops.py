@@ -366,13 +366,14 @@ def conv3x3_umma_bn_workspace(n: int, c: int, device) -> torch.Tensor:
 
 def conv3x3_umma_bn(x: torch.Tensor, w_packed: torch.Tensor, *, stats_out: Optional[torch.Tensor] = None,
                     stats_in: Optional[torch.Tensor] = None, bn=None, groups: int = 1, eps: float = 1e-5,
-                    momentum: float = 0.1, replay: int = 1):
+                    momentum: float = 0.1, replay: int = 1, mailbox=None):
     """tcgen05 convolution with BatchNorm folded in (Classification/resnet_s.py:70-72).
 
     stats_out (producer): workspace that receives the per-CTA {sum, sum of squares} of the OUTPUT.
     stats_in + bn = (weight, bias, running_mean, running_var) (consumer): x is the producer's raw output; its train-mode
     BatchNorm (+ ReLU) over `groups` statistic groups is applied while loading.  Returns (y, save_mean, save_invstd, table)
-    -- the last three only for a consumer call (what bn_bwd_xmask needs)."""
+    -- the last three only for a consumer call (what bn_bwd_xmask needs).
+    mailbox (p2p.PeerMailbox, consumer only): statistics of the GLOBAL batch, exchanged with the peer GPUs inside the kernel."""
     n, c, h, _ = x.shape
     y = torch.empty_like(x)
     sm = si = tab = None
@@ -388,6 +389,14 @@ def conv3x3_umma_bn(x: torch.Tensor, w_packed: torch.Tensor, *, stats_out: Optio
     for ws in (stats_in, stats_out):
         if ws is not None and (ws.dtype != torch.float64 or ws.numel() < need or not ws.is_cuda):
             raise AfanError("statistics workspace must be a CUDA float64 tensor from conv3x3_umma_bn_workspace(n, c)")
+    if mailbox is not None and stats_in is not None:
+        if stats_out is not None:
+            raise AfanError("the multi-GPU consumer call does not also produce statistics")
+        check(_lib.lib().afan_conv3x3_umma_bn_p2p_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), ptr(stats_in), a[0], a[1], a[2],
+                                                      a[3], f32(sm), f32(si), f32(tab), int(groups), n, c, h, float(eps),
+                                                      float(momentum), int(replay), mailbox.world, mailbox.rank, mailbox.peer_ptrs,
+                                                      mailbox.cmax, ptr(mailbox.state), stream()), "afan_conv3x3_umma_bn_p2p_f32")
+        return y, sm, si, tab
     check(_lib.lib().afan_conv3x3_umma_bn_f32(f32(x, "x"), f32(w_packed, "w_packed"), f32(y), ptr(stats_in),
                                               a[0], a[1], a[2], a[3], f32(sm), f32(si), f32(tab), ptr(stats_out), int(groups),
                                               n, c, h, float(eps), float(momentum), int(replay), stream()),
@@ -395,13 +404,19 @@ def conv3x3_umma_bn(x: torch.Tensor, w_packed: torch.Tensor, *, stats_out: Optio
     return y, sm, si, tab
 
 
-def bn_bwd_xmask(dy, x, table, weight, save_mean, save_invstd, *, groups=1, dweight_out=None, dbias_out=None):
+def bn_bwd_xmask(dy, x, table, weight, save_mean, save_invstd, *, groups=1, dweight_out=None, dbias_out=None, mailbox=None):
     """Backward of BatchNorm + ReLU whose output was never stored (consumed by conv3x3_umma_bn(in_table=table)): the
     ReLU mask is recomputed from x and the table.  Returns (dx, dweight, dbias)."""
     n, c, hw = _nchw(x, groups)
     dx = torch.empty_like(x)
     dweight = torch.empty(c, dtype=torch.float32, device=x.device) if dweight_out is None else dweight_out
     dbias = torch.empty_like(dweight) if dbias_out is None else dbias_out
+    if mailbox is not None:
+        check(_lib.lib().afan_bn_bwd_xmask_p2p_f32(f32(dy, "dy"), f32(x, "x"), f32(table, "table"), f32(weight), f32(save_mean),
+                                                   f32(save_invstd), f32(dx), f32(dweight), f32(dbias), groups, n, c, hw,
+                                                   mailbox.world, mailbox.rank, mailbox.peer_ptrs, mailbox.cmax,
+                                                   ptr(mailbox.state), stream()), "afan_bn_bwd_xmask_p2p_f32")
+        return dx, dweight, dbias
     check(_lib.lib().afan_bn_bwd_xmask_f32(f32(dy, "dy"), f32(x, "x"), f32(table, "table"), f32(weight), f32(save_mean),
                                            f32(save_invstd), f32(dx), f32(dweight), f32(dbias), groups, n, c, hw, stream()),
           "afan_bn_bwd_xmask_f32")

@@ -25,8 +25,9 @@ from .dual_bn import DualBatchNorm2d
 # identity BasicBlock runs conv1 -> [bn1 + relu folded into conv2's operand staging] -> conv2: conv1's tcgen05 kernel reduces
 # the BatchNorm statistics of its own output in its epilogue, conv2 normalises while it loads, and relu(bn1(conv1(x))) is
 # never written to memory -- one BatchNorm launch and 8 B/element of traffic less per block and pass (80 launches per
-# step at config 2; same-box A/B 11.18 -> 10.89 ms).  Single process only: with a BatchNorm exchange configured the block
-# keeps its four launches.
+# step at config 2; same-box A/B 11.18 -> 10.89 ms).  Multi-GPU: with the fused NVLink exchange (bn_exchange="p2p") the
+# consumer convolution exchanges the folded sums with its peers in its prologue; with the NCCL split form the block keeps
+# its four launches.
 FUSE_BN1 = os.environ.get("AFAN_FUSE_BN1", "1") == "1"
 
 
@@ -46,16 +47,16 @@ class _FusedConvBnReluConvFn(torch.autograd.Function):
             ws = block._fuse_ws[(n, c, x.device)] = ops.conv3x3_umma_bn_workspace(n, c, x.device)
         c1, _, _, _ = ops.conv3x3_umma_bn(x, wf1, stats_out=ws, groups=groups)
         c2, sm, si, tab = ops.conv3x3_umma_bn(c1, wf2, stats_in=ws, bn=(bn.weight, bn.bias, bn.running_mean, bn.running_var),
-                                              groups=groups, eps=bn.eps, momentum=bn.momentum, replay=replay)
+                                              groups=groups, eps=bn.eps, momentum=bn.momentum, replay=replay, mailbox=bn.mailbox)
         ctx.save_for_backward(c1, tab, sm, si, bn.weight)
-        ctx.wd1, ctx.wd2, ctx.groups = wd1, wd2, groups
+        ctx.wd1, ctx.wd2, ctx.groups, ctx.mailbox = wd1, wd2, groups, bn.mailbox
         return c2, x.view_as(x)
 
     @staticmethod
     def backward(ctx, d_c2, dtap):
         c1, tab, sm, si, w = ctx.saved_tensors
         d_h = ops.conv3x3(d_c2.contiguous(), ctx.wd2, math="umma")
-        d_c1, _, _ = ops.bn_bwd_xmask(d_h, c1, tab, w, sm, si, groups=ctx.groups)
+        d_c1, _, _ = ops.bn_bwd_xmask(d_h, c1, tab, w, sm, si, groups=ctx.groups, mailbox=ctx.mailbox)
         dx = ops.conv3x3(d_c1, ctx.wd1, math="umma", addend=dtap.contiguous() if dtap is not None else None)
         return dx, None, None, None
 
@@ -101,7 +102,10 @@ class BasicBlock(nn.Module):
             return False
         if h == 8 and (n // groups) % 2:
             return False
-        if self.bn1.process_group is not None or self.bn1.mailbox is not None:      # single process only (for now)
+        if self.bn1.mailbox is not None:          # multi-GPU: the exchange runs inside the consumer convolution; every CTA
+            if n > torch.cuda.get_device_properties(x.device).multi_processor_count:      # spins on its peers -> co-resident grid
+                return False
+        elif self.bn1.process_group is not None:  # NCCL split form of the statistics exchange: keep the four launches
             return False
         return not any(p.requires_grad for m in (self.conv1, self.bn1, self.conv2) for p in m.parameters())
 

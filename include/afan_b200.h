@@ -295,6 +295,20 @@ int afan_conv3x3_umma_bn_f32(const float* x, const float* w_packed, float* y, co
 int afan_bn_bwd_xmask_f32(const float* dy, const float* x, const float* mask_table, const float* weight,
                           const float* save_mean, const float* save_invstd, float* dx, float* dweight, float* dbias,
                           int64_t groups, int64_t n, int64_t c, int64_t hw, afan_stream_t stream);
+/* Multi-GPU forms (one process per GPU, mailboxes / state as for afan_bn_fwd_p2p_f32): the consumer convolution folds its
+ * LOCAL producer statistics, ONE of its CTAs publishes them to every peer's mailbox and every CTA collects all ranks' sums
+ * (rank order: bit-identical statistics on all GPUs) while the operand loads are in flight -- global-batch BatchNorm without
+ * a BatchNorm launch.  n <= SM count (the grid must be co-resident).  Every rank must issue the same sequence of
+ * exchanging calls (these and the afan_bn_*_p2p_f32 ones share the mailbox sequence). */
+int afan_conv3x3_umma_bn_p2p_f32(const float* x, const float* w_packed, float* y, const void* in_partials,
+                                 const float* bn_weight, const float* bn_bias, float* running_mean, float* running_var,
+                                 float* save_mean, float* save_invstd, float* table_out, int64_t groups, int64_t n,
+                                 int64_t c, int64_t hw, float eps, float momentum, int replay, int world, int rank,
+                                 void* const* peer_mailboxes, int64_t cmax, void* state, afan_stream_t stream);
+int afan_bn_bwd_xmask_p2p_f32(const float* dy, const float* x, const float* mask_table, const float* weight,
+                              const float* save_mean, const float* save_invstd, float* dx, float* dweight, float* dbias,
+                              int64_t groups, int64_t n, int64_t c, int64_t hw, int world, int rank,
+                              void* const* peer_mailboxes, int64_t cmax, void* state, afan_stream_t stream);
 /* tcgen05 twin of afan_conv3x3_wgrad_f32 for (c, hw) in {(32, 16), (64, 8)}: the weight gradient as a GEMM whose
  * reduction dimension is the pixels (kind::tf32, 3xTF32 split, TMEM accumulators; the three kx shifts are materialised
  * while staging and form the M dimension, ky shifts are descriptor offsets), persistent CTAs, one partial dW per CTA and

@@ -280,3 +280,65 @@ def test_fused_basic_block_equals_the_unfused_block(n, c, h, groups, monkeypatch
             torch.testing.assert_close(s1[k], s0[k], rtol=1e-5, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
         else:
             assert torch.equal(s1[k], s0[k]), k
+
+
+@pytest.mark.parametrize("n_loc,c,h,groups", [(16, 32, 16, 1), (16, 64, 8, 1), (8, 32, 16, 2)])
+def test_folded_batchnorm_exchange_loopback_two_virtual_ranks(n_loc, c, h, groups):
+    """Multi-GPU form of the folded BatchNorm, exercised on ONE GPU like test_fused_p2p_exchange_loopback…: two virtual
+    ranks on two streams with mailboxes in local memory.  Each rank's consumer convolution folds its local producer
+    statistics, exchanges them inside its prologue and normalises with the statistics of the GLOBAL batch; the oracle is
+    the single-process un-fused sequence (conv -> dual-BN kernel -> conv, and its backward) over the global batch."""
+    dev = torch.device("cuda:0")
+    world = 2
+    g = torch.Generator(device="cpu").manual_seed(n_loc + c)
+    n_glob = n_loc * world                                   # per statistic group
+    x = torch.randn(groups * n_glob, c, h, h, generator=g).to(dev)
+    dh = torch.randn(groups * n_glob, c, h, h, generator=g).to(dev)
+    shard = lambda t, r: torch.cat([t[gi * n_glob + r * n_loc: gi * n_glob + (r + 1) * n_loc] for gi in range(groups)]).contiguous()
+    m1, m2 = conv.Conv3x3(c, c, 1).to(dev), conv.Conv3x3(c, c, 1).to(dev)
+    ops.conv3x3_pack(torch.tensor([m1.desc_row(), m2.desc_row()], dtype=torch.int64, device=dev), c, "umma")
+    wf1, wf2 = m1._packed[0], m2._packed[0]
+    w, b = (torch.rand(c, generator=g) + 0.5).to(dev), torch.randn(c, generator=g).to(dev)
+    # oracle: global batch, one process
+    c1g = ops.conv3x3(x, wf1, math="umma")
+    rm_g, rv_g = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    hg, smg, sig = ops.bn_fwd(c1g, None, w, b, rm_g, rv_g, ops.bn_workspace(groups, c, dev), groups=groups, relu=True)
+    c2g = ops.conv3x3(hg, wf2, math="umma")
+    dc1g, _, dwg, dbg = ops.bn_bwd(dh, c1g, hg, w, smg, sig, ops.bn_workspace(groups, c, dev), groups=groups, relu=True)
+    # two virtual ranks; every exchanging kernel is launched for both ranks before anything host-synchronous happens
+    boxes = pkg.p2p.PeerMailbox.loopback(world, dev, cmax=c)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    xs, dhs = [shard(x, r) for r in range(world)], [shard(dh, r) for r in range(world)]
+    wss = [ops.conv3x3_umma_bn_workspace(groups * n_loc, c, dev) for _ in range(world)]
+    rms, rvs = [torch.zeros(c, device=dev) for _ in range(world)], [torch.ones(c, device=dev) for _ in range(world)]
+    torch.cuda.synchronize()
+    c1, fw, bw = [None] * world, [None] * world, [None] * world
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            c1[r] = ops.conv3x3_umma_bn(xs[r], wf1, stats_out=wss[r], groups=groups)[0]
+    torch.cuda.synchronize()
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            fw[r] = ops.conv3x3_umma_bn(c1[r], wf2, stats_in=wss[r], bn=(w, b, rms[r], rvs[r]), groups=groups, mailbox=boxes[r])
+    torch.cuda.synchronize()
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            bw[r] = ops.bn_bwd_xmask(dhs[r], c1[r], fw[r][3], w, fw[r][1], fw[r][2], groups=groups, mailbox=boxes[r])
+    torch.cuda.synchronize()
+    for bx in boxes:
+        bx.check()
+    assert int(boxes[0].state[0]) == 2 and int(boxes[1].state[0]) == 2                 # two exchanges counted on each rank
+    assert torch.equal(fw[0][1], fw[1][1]) and torch.equal(fw[0][2], fw[1][2]) and torch.equal(fw[0][3], fw[1][3])   # bit-identical statistics
+    dw_sum, db_sum = 0, 0
+    for r in range(world):
+        c2, sm, si, tab = fw[r]
+        torch.testing.assert_close(sm, smg, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(si, sig, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(rvs[r], rv_g, rtol=1e-5, atol=1e-6)
+        assert _rel(c2, shard(c2g, r).double()) < 1e-5
+        assert _rel(bw[r][0], shard(dc1g, r).double()) < 1e-4
+        dw_sum, db_sum = dw_sum + bw[r][1], db_sum + bw[r][2]
+    torch.testing.assert_close(dw_sum, dwg, rtol=1e-4, atol=1e-3)                      # local dweight / dbias sum to the global ones
+    torch.testing.assert_close(db_sum, dbg, rtol=1e-4, atol=1e-3)
+    for bx in boxes:
+        bx.close()
