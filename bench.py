@@ -484,8 +484,9 @@ def multi_gpu_parity(pkg, dev, pg, rank, world, exchange, graph, sync_bn):
     targets = [torch.randint(0, 10, (B,), generator=g) for _ in range(iters)]
     noises = [torch.rand(B, 16, 32, 32, generator=g) for _ in range(iters)]
     torch.manual_seed(3)
-    model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
+    model = pkg.resnet_s.ResNet(num_blocks=(1, 2, 2)).to(dev)       # second block of stages 2 / 3: the folded-BatchNorm path
     init = {k: v.clone() for k, v in model.state_dict().items()}
+    folded0 = pkg.resnet_s.fused_forward_calls
     tr = pkg.trainer.AfanTrainer(model, process_group=pg, sync_bn=sync_bn, use_cuda_graph=graph, bn_exchange=exchange, **kw)
     sl = slice(rank * per_rank, (rank + 1) * per_rank)
     losses = []
@@ -502,9 +503,10 @@ def multi_gpu_parity(pkg, dev, pg, rank, world, exchange, graph, sync_bn):
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     identical = bool((lo == hi).all())
     tr.close()
-    res = {"ranks_bit_identical": identical, "exchange": tr.bn_exchange_used, "graph": graph, "per_rank_batch": per_rank}
+    res = {"ranks_bit_identical": identical, "exchange": tr.bn_exchange_used, "graph": graph, "per_rank_batch": per_rank,
+           "folded_block_calls": pkg.resnet_s.fused_forward_calls - folded0}
     if sync_bn:                       # per-replica statistics (--no-sync-bn) have no single-process equivalent
-        ref_model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
+        ref_model = pkg.resnet_s.ResNet(num_blocks=(1, 2, 2)).to(dev)
         ref_model.load_state_dict(init)
         ref = pkg.trainer.AfanTrainer(ref_model, use_cuda_graph=False, **kw)
         ref_losses = [float(ref.step(images[i].to(dev), targets[i].to(dev), noises[i].to(dev))["loss"]) for i in range(iters)]

@@ -29,6 +29,7 @@ from .dual_bn import DualBatchNorm2d
 # consumer convolution exchanges the folded sums with its peers in its prologue; with the NCCL split form the block keeps
 # its four launches.
 FUSE_BN1 = os.environ.get("AFAN_FUSE_BN1", "1") == "1"
+fused_forward_calls = 0       # host-side count of folded block forwards (eager calls + graph captures): evidence for the parity checks
 
 
 class _FusedConvBnReluConvFn(torch.autograd.Function):
@@ -116,6 +117,8 @@ class BasicBlock(nn.Module):
 
     def forward(self, x, groups: int = 1, replay: int = 1):
         if self._fusable(x, groups):
+            global fused_forward_calls
+            fused_forward_calls += 1
             c2, sc = _FusedConvBnReluConvFn.apply(x, self, groups, replay)
             self.bn1._pending_batches += groups * replay
             return self.bn2(c2, residual=sc, relu=True, groups=groups, replay=replay)

@@ -37,7 +37,7 @@ def main():
     noises = [torch.rand(B, 16, 32, 32, generator=g) for _ in range(iters)]
 
     torch.manual_seed(3)
-    model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
+    model = pkg.resnet_s.ResNet(num_blocks=(1, 2, 2)).to(dev)       # second block of stages 2 / 3: the folded-BatchNorm path
     init = {k: v.clone() for k, v in model.state_dict().items()}
     tr = pkg.trainer.AfanTrainer(model, process_group=dist.group.WORLD, sync_bn=sync_bn, use_cuda_graph=use_graph,
                                  bn_exchange=exchange, **kw)
@@ -54,7 +54,8 @@ def main():
     sharded = {k: v.detach().clone() for k, v in model.state_dict().items()}
 
     # the oracle: ONE process, global batch, same initial weights
-    ref_model = pkg.resnet_s.ResNet(num_blocks=(1, 1, 1)).to(dev)
+    folded = pkg.resnet_s.fused_forward_calls
+    ref_model = pkg.resnet_s.ResNet(num_blocks=(1, 2, 2)).to(dev)
     ref_model.load_state_dict(init)
     ref = pkg.trainer.AfanTrainer(ref_model, use_cuda_graph=False, **kw)
     ref_losses = [float(ref.step(images[i].to(dev), targets[i].to(dev), noises[i].to(dev))["loss"]) for i in range(iters)]
@@ -70,10 +71,12 @@ def main():
             continue
         err = float((sharded[k] - v).abs().max())
         # fused NVLink exchange: every rank folds the SAME float64 sums in rank order -> statistics bit-identical across ranks
-        # (checked exactly below) and equal to the single-process ones up to the fp32 rounding of the per-rank partials; the
-        # weights additionally see the NCCL sum order of `world` partial weight gradients.  Measured after 3 iterations:
-        # 2.4e-7 (2 B200s), 4.3e-5 (8 B200s); the NCCL split form (two-launch reduce kernels, other summation order): 2.6e-4
-        tol = (1e-4 + 1e-4 * float(v.abs().max())) if exchange == "p2p" else (1e-3 + 1e-3 * float(v.abs().max()))
+        # (checked exactly below).  Against the single-process step they agree to the fp32 rounding of the per-thread partial
+        # sums only: the statistics kernels accumulate (x - shift) with a shift taken from the LOCAL data (afan_bn.cu:
+        # unshift_sums), the weights see the NCCL sum order of `world` partial gradients, and this deliberately tiny, large-eps
+        # case turns one flipped sign() in the ascent into ~2.6e-4 on a running mean after 3 iterations (measured, both
+        # exchange forms; bench.py's in-line check at 32 images per rank measures 1e-7).
+        tol = 1e-3 + 1e-3 * float(v.abs().max())
         if err > worst[1]:
             worst = (k, err)
         ok &= err <= tol
@@ -86,7 +89,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"MULTI_GPU_CHECK world={world} graph={use_graph} exchange={exchange} losses={losses} ref={ref_losses} worst={worst} "
+        print(f"MULTI_GPU_CHECK world={world} graph={use_graph} exchange={exchange} folded_block_calls={folded} losses={losses} ref={ref_losses} worst={worst} "
               f"{'OK' if int(flag) else 'FAIL'}")
     tr.close()
     ref.close()
