@@ -34,7 +34,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import detection
+from . import detection, ops
 from .resnet_s import NormalizeByChannelMeanStd
 
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
@@ -93,11 +93,12 @@ def per_image_losses(logits, targets, pred_deltas, gt_deltas, batch_indices, bat
     seg = F.one_hot(batch_indices, batch_size).to(logits.dtype).t()              # [B, S]
     ce = F.cross_entropy(logits, targets, reduction="none")
     cross_entropies = (seg @ ce) / seg.sum(dim=1)
-    fg = (targets != 0).to(logits.dtype)
-    l1 = smooth_l1(pred_deltas - gt_deltas, beta).sum(dim=1) * fg
-    # background rows may hold inf / NaN regression targets (log of a zero-area ratio); they are excluded, not multiplied
-    l1 = torch.where(fg > 0, l1, torch.zeros_like(l1))
-    smooth_l1_losses = (seg @ l1) / (4.0 * (seg @ fg) + 1e-8)
+    fg = targets != 0
+    # background rows may hold inf / NaN regression targets (log of a zero-area ratio): their difference is replaced by 0
+    # BEFORE the loss, so neither the value nor the gradient sees them (the reference gathers the foreground rows)
+    diff = torch.where(fg.unsqueeze(1), pred_deltas - gt_deltas, torch.zeros_like(pred_deltas))
+    fg = fg.to(logits.dtype)
+    smooth_l1_losses = (seg @ smooth_l1(diff, beta).sum(dim=1)) / (4.0 * (seg @ fg) + 1e-8)
     return cross_entropies, smooth_l1_losses
 
 
@@ -300,7 +301,7 @@ class RegionProposalNetwork(nn.Module):
         kept = []
         for i in range(b):                                   # B launches; the sweep itself is on the device
             ranked = boxes[i].index_select(0, order[i])
-            keep, _ = detection.ops.nms_flags(ranked.contiguous(), score[i].contiguous(), 0.7)
+            keep, _ = ops.nms_flags(ranked.contiguous(), score[i].contiguous(), 0.7)
             kept.append((ranked, keep))
         counts = torch.stack([k.sum() for _, k in kept]).clamp(max=self._post_nms_top_n).tolist()    # ONE synchronisation
         out = boxes.new_zeros(b, max(counts), 4)
