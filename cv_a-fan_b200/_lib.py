@@ -35,6 +35,8 @@ SIGNATURES = {
     "afan_sat_mix_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _i64, _vp]),
     "afan_nms_workspace_bytes": (_i64, [_i64]),
     "afan_nms_f32": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "afan_nms_batched_workspace_bytes": (_i64, [_i64, _i64]),
+    "afan_nms_batched_f32": (_int, [_vp, _f32, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "afan_roi_align_fwd_f32": (_int, [_vp, _vp, _vp] + [_i64] * 7 + [_f32, _int, _vp]),
     "afan_roi_align_bwd_f32": (_int, [_vp, _vp, _vp] + [_i64] * 7 + [_f32, _int, _vp]),
     "afan_bn_workspace_bytes": (_i64, [_i64, _i64]),
@@ -55,6 +57,7 @@ SIGNATURES = {
     "afan_p2p_open_handle": (_int, [_vp, ctypes.POINTER(_vp)]),
     "afan_p2p_close_handle": (_int, [_vp]),
     "afan_bn_affine_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
+    "afan_bn_affine_bwd_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "afan_sgd_momentum_f32": (_int, [_vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp]),
     "afan_conv3x3_pack_f32": (_int, [_vp, _i64, _i64, _vp]),
     "afan_conv3x3_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
@@ -82,7 +85,7 @@ SIGNATURES = {
 AFAN_ERR_UNSUPPORTED = -5
 _lib = None
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); bumped by check() on success
-KERNELS_PER_CALL = {"afan_nms_f32": 2, "afan_conv3x3_wgrad_f32": 2, "afan_conv3x3_wgrad_umma_f32": 2, "afan_conv3x3s2_wgrad_f32": 2}
+KERNELS_PER_CALL = {"afan_nms_f32": 2, "afan_nms_batched_f32": 2, "afan_conv3x3_wgrad_f32": 2, "afan_conv3x3_wgrad_umma_f32": 2, "afan_conv3x3s2_wgrad_f32": 2}
 launch_count = 0
 
 

@@ -346,6 +346,54 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParam
 }
 
 
+// Backward of the frozen-statistics affine (afan_bn_affine_f32): dx = scale[c] * dy_eff, dresidual = dy_eff, with
+// dy_eff = dy where the forward output was positive (ReLU) -- one pass: reads dy (+ y), writes dx (+ dresidual).
+template <int VEC, bool RELU, bool DRES>
+__global__ void __launch_bounds__(kThreads) bn_affine_bwd_kernel(const ApplyParams p) {
+    using V = typename std::conditional<VEC == 4, float4, float>::type;
+    const V* dy_v = reinterpret_cast<const V*>(p.x);
+    const V* y_v = reinterpret_cast<const V*>(p.y);
+    V* dx_v = reinterpret_cast<V*>(p.out);
+    V* dr_v = reinterpret_cast<V*>(p.out2);
+    const float2* table = static_cast<const float2*>(p.table);
+    const unsigned int span = gridDim.x * kThreads * kBnUnroll;
+    for (unsigned int i0 = blockIdx.x * kThreads * kBnUnroll + threadIdx.x; i0 < p.total_v; i0 += span) {
+        V dy[kBnUnroll] = {}, y[kBnUnroll] = {};
+        float sc[kBnUnroll] = {};
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const unsigned int i = i0 + u * kThreads;
+            if (i < p.total_v) {
+                dy[u] = ld_stream(dy_v + i);
+                if (RELU) y[u] = __ldg(y_v + i);               // y stays live: it is the next layer's saved input
+                const unsigned int plane = i / p.hwv;
+                sc[u] = __ldg(table + (plane % p.c)).x;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const unsigned int i = i0 + u * kThreads;
+            if (i < p.total_v) {
+                V dx, dr;
+                auto one = [&](float d, float yv, float& o, float& r) {
+                    const float de = (RELU && !(yv > 0.f)) ? 0.f : d;
+                    r = de;
+                    o = sc[u] * de;
+                };
+                if constexpr (VEC == 4) {
+                    one(dy[u].x, y[u].x, dx.x, dr.x); one(dy[u].y, y[u].y, dx.y, dr.y);
+                    one(dy[u].z, y[u].z, dx.z, dr.z); one(dy[u].w, y[u].w, dx.w, dr.w);
+                } else {
+                    one(dy[u], y[u], dx, dr);
+                }
+                dx_v[i] = dx;
+                if (DRES) dr_v[i] = dr;
+            }
+        }
+    }
+}
+
+
 // =====================================================================================================
 // Cluster path (the one every BASELINE config takes): ONE launch per BatchNorm direction.
 //
@@ -1352,6 +1400,17 @@ int launch_bwd_apply(const ApplyParams& p, bool vec, bool relu, bool dres, cudaS
     return launch_status();
 }
 
+int launch_affine_bwd(const ApplyParams& p, bool vec, bool relu, bool dres, cudaStream_t st) {
+    const int grid = apply_grid(p.total_v);
+#define AFAN_AB(V, R, S) bn_affine_bwd_kernel<V, R, S><<<grid, kThreads, 0, st>>>(p)
+    if (vec) { if (relu) { if (dres) AFAN_AB(4, true, true); else AFAN_AB(4, true, false); }
+               else      { if (dres) AFAN_AB(4, false, true); else AFAN_AB(4, false, false); } }
+    else     { if (relu) { if (dres) AFAN_AB(1, true, true); else AFAN_AB(1, true, false); }
+               else      { if (dres) AFAN_AB(1, false, true); else AFAN_AB(1, false, false); } }
+#undef AFAN_AB
+    return launch_status();
+}
+
 __host__ inline bool ws_ok(void* ws, int64_t bytes, int64_t groups, int64_t c) {
     return ws && aligned16(ws) && bytes >= bn_layout(groups, c).total;
 }
@@ -1507,6 +1566,18 @@ AFAN_EXPORT int afan_bn_affine_f32(const float* x, const float* residual, const 
     p.x = x; p.b = residual; p.out = y; p.table = scale_shift;
     p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
     return launch_fwd_apply(p, s.vec, relu != 0, residual != nullptr, static_cast<cudaStream_t>(stream));
+}
+
+AFAN_EXPORT int afan_bn_affine_bwd_f32(const float* dy, const float* y, const float* scale_shift, float* dx, float* dresidual,
+                                       int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream) {
+    BnShape s = bn_shape(1, n, c, hw, aligned16(dy) && aligned16(dx) && (!relu || aligned16(y)) && (!dresidual || aligned16(dresidual)));
+    if (s.err != AFAN_OK) return s.err;
+    if (!s.ok) return AFAN_OK;
+    if (!dy || !dx || !scale_shift || (relu && !y)) return AFAN_ERR_NULL;
+    ApplyParams p{};
+    p.x = dy; p.y = y; p.out = dx; p.out2 = dresidual; p.table = scale_shift;
+    p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
+    return launch_affine_bwd(p, s.vec, relu != 0, dresidual != nullptr, static_cast<cudaStream_t>(stream));
 }
 
 // ---- backward -----------------------------------------------------------------------------------

@@ -106,7 +106,9 @@ class _DualBNTrainFn(torch.autograd.Function):
 
 
 class _AffineEvalFn(torch.autograd.Function):
-    """model.eval(): y = relu?(x*scale + shift (+res)) from running statistics (main_perturb.py:232-246)."""
+    """Frozen statistics: y = relu?(x*scale + shift (+res)) from running statistics -- model.eval() of the Classification
+    flavour (main_perturb.py:232-246) and the always-frozen BatchNorm of the Detection flavour (Detection/model.py:27-35,
+    47-48), where it is differentiated: dx = scale * dy_eff, dres = dy_eff (one fused pass each way)."""
 
     @staticmethod
     def forward(ctx, x, residual, scale_shift, relu):
@@ -114,13 +116,35 @@ class _AffineEvalFn(torch.autograd.Function):
         res = residual.contiguous() if residual is not None else None
         y = ops.bn_affine(x, res, scale_shift, relu=relu)
         ctx.save_for_backward(y if relu else None, scale_shift)
+        ctx.relu = bool(relu)
         ctx.has_res = residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        raise AfanError("eval-mode DualBatchNorm2d is inference-only; the reference runs PGD and training "
-                        "passes in train() mode (Classification/main_perturb.py:160)")
+        y, scale_shift = ctx.saved_tensors
+        dx, dres = ops.bn_affine_bwd(dy.contiguous(), y, scale_shift, relu=ctx.relu,
+                                     want_dresidual=ctx.has_res and ctx.needs_input_grad[1])
+        return dx, dres, None, None
+
+
+def frozen_table(bn: nn.Module) -> torch.Tensor:
+    """(scale, shift) [C, 2] of a BatchNorm whose statistics AND affine are frozen; cached on the module, rebuilt when any
+    of the four tensors is written (load_state_dict) or moved."""
+    src = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple(t._version for t in src) + tuple(t.data_ptr() for t in src)
+    cached = getattr(bn, "_afan_frozen_table", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            table = torch.stack((scale, bn.bias - bn.running_mean * scale), dim=1).float().contiguous()
+        bn._afan_frozen_table = cached = (key, table)
+    return cached[1]
+
+
+def frozen_bn_act(x, bn: nn.Module, residual=None, relu: bool = False):
+    """relu?(frozen_bn(x) (+ residual)) in ONE launch (forward) / ONE launch (backward)."""
+    return _AffineEvalFn.apply(x, residual, frozen_table(bn), relu)
 
 
 class DualBatchNorm2d(nn.Module):

@@ -27,7 +27,11 @@ forward (three in the RPN, three in the ROI head).  `Sampler("reference")` makes
 run seeded like the reference selects the same anchors / proposals; `Sampler("device")` draws on the GPU.
 
 BatchNorm is frozen: every BatchNorm2d of the backbone and of layer4 stays in eval mode with requires_grad False
-(model.py:27-35,47-48), conv1 / bn1 / layer1 are frozen as well (backbone/resnet101.py:29-31).
+(model.py:27-35,47-48), conv1 / bn1 / layer1 are frozen as well (backbone/resnet101.py:29-31).  Declared deviation: the
+reference's 'rpn_tail' branch (model.py:98-113) is the one branch that does not re-freeze BatchNorm after the caller's
+`model.train()`, so layer4 normalises with batch statistics there; that branch is unreachable from the training iteration
+(train_aug_final.py:88 raises KeyError for pertub_idx_sd='rpn'), and here BatchNorm is frozen in every branch
+(tests/test_oracle_vs_reference.py compares it with the reference's BatchNorm frozen by hand).
 """
 import numpy as np
 import torch
@@ -35,6 +39,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import detection, ops
+from .dual_bn import frozen_bn_act
 from .resnet_s import NormalizeByChannelMeanStd
 
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
@@ -155,7 +160,14 @@ class Bottleneck(nn.Module):
         if downsample:
             self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
 
+    fused_bn = False            # set by FasterRCNN(fuse_frozen_bn=True): frozen BatchNorm + residual + ReLU as one launch
+
     def forward(self, x):
+        if self.fused_bn and x.is_cuda:
+            y = frozen_bn_act(self.conv1(x), self.bn1, relu=True)
+            y = frozen_bn_act(self.conv2(y), self.bn2, relu=True)
+            idn = x if self.downsample is None else frozen_bn_act(self.downsample[0](x), self.downsample[1])
+            return frozen_bn_act(self.conv3(y), self.bn3, residual=idn, relu=True)
         y = F.relu(self.bn1(self.conv1(x)))
         y = F.relu(self.bn2(self.conv2(y)))
         y = self.bn3(self.conv3(y))
@@ -188,7 +200,11 @@ class SplitResNet(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
+    fused_bn = False
+
     def stem(self, x):
+        if self.fused_bn and x.is_cuda:
+            return self.layer1(self.maxpool(frozen_bn_act(self.conv1(self.normal(x)), self.bn1, relu=True)))
         return self.layer1(self.maxpool(F.relu(self.bn1(self.conv1(self.normal(x))))))
 
     def head(self, x, out_idx: int):
@@ -294,22 +310,12 @@ class RegionProposalNetwork(nn.Module):
         """region_proposal_network.py:227-271: decode, clip, rank by objectness, NMS at 0.7, keep the best
         post_nms_top_n, zero-pad to the longest list of the batch.  Ranking uses the foreground logit: the reference
         ranks by a softmax ACROSS ANCHORS of that logit (:247), a monotone map, so the order is the same."""
-        b = objectnesses.shape[0]
         boxes = clip_boxes(apply_deltas(anchors.unsqueeze(0), transformers.detach()), image_width, image_height)
-        score, order = torch.sort(objectnesses.detach()[:, :, 1], dim=1, descending=True, stable=True)
-        order, score = order[:, :self._pre_nms_top_n], score[:, :self._pre_nms_top_n]
-        kept = []
-        for i in range(b):                                   # B launches; the sweep itself is on the device
-            ranked = boxes[i].index_select(0, order[i])
-            keep, _ = ops.nms_flags(ranked.contiguous(), score[i].contiguous(), 0.7)
-            kept.append((ranked, keep))
-        counts = torch.stack([k.sum() for _, k in kept]).clamp(max=self._post_nms_top_n).tolist()    # ONE synchronisation
-        out = boxes.new_zeros(b, max(counts), 4)
-        for i, (ranked, keep) in enumerate(kept):
-            idx = torch.nonzero_static(keep, size=int(keep.shape[0]), fill_value=0).squeeze(1)[:counts[i]] if counts[i] else None
-            if idx is not None:
-                out[i, :counts[i]] = ranked.index_select(0, idx)
-        return out
+        order = torch.sort(objectnesses.detach()[:, :, 1], dim=1, descending=True, stable=True)[1][:, :self._pre_nms_top_n]
+        ranked = torch.gather(boxes, 1, order.unsqueeze(2).expand(-1, -1, 4)).contiguous()
+        # one launch pair for the batch: a CTA per image sweeps on the device and stops at post_nms_top_n kept boxes
+        kept, counts, _ = ops.nms_batched(ranked, 0.7, self._post_nms_top_n)
+        return kept[:, :int(counts.max())].contiguous()                              # ONE synchronisation (the padded length)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -335,7 +341,10 @@ class DetectionHead(nn.Module):
         return F.max_pool2d(detection.roi_align(features, rois, (14, 14), 1 / 16, 0), 2, 2)
 
     def embed(self, pooled):
-        return F.adaptive_max_pool2d(self.hidden(pooled), 1)                          # [S, 2048, 1, 1]
+        # adaptive_max_pool2d(., 1) of model.py:276 as a plain reduction (the pooling kernel and its atomic backward cost
+        # 18 ms per iteration at config 4); on tied maxima -- zeros after the block's ReLU -- the gradient is shared instead
+        # of given to the first, and the ReLU backward right below it zeroes both
+        return self.hidden(pooled).amax(dim=(2, 3), keepdim=True)                      # [S, 2048, 1, 1]
 
     def assign(self, proposal_bboxes, gt_classes_batch, gt_bboxes_batch):
         """model.py:246-268: label every proposal, select 128 per image (<= 32 foreground), build the targets."""
@@ -352,7 +361,7 @@ class DetectionHead(nn.Module):
         return boxes, bi, labels[bi, pi], gt_deltas
 
     def classify(self, roi_feature_map):
-        hidden = roi_feature_map.reshape(roi_feature_map.shape[0], -1)
+        hidden = roi_feature_map.reshape(roi_feature_map.shape[0], self._proposal_class.in_features)
         return self._proposal_class(hidden), self._proposal_transformer(hidden)
 
     def losses(self, proposal_classes, proposal_transformers, gt_classes, gt_deltas, batch_size, batch_indices):
@@ -410,7 +419,11 @@ class FasterRCNN(nn.Module):
 
     def __init__(self, num_classes: int, anchor_ratios=((1, 2), (1, 1), (2, 1)), anchor_sizes=(128, 256, 512),
                  rpn_pre_nms_top_n: int = 12000, rpn_post_nms_top_n: int = 2000, anchor_smooth_l1_loss_beta: float = 1.0,
-                 proposal_smooth_l1_loss_beta: float = 1.0, layers=(3, 4, 23, 3), base_width: int = 64, sampler: str = "reference"):
+                 proposal_smooth_l1_loss_beta: float = 1.0, layers=(3, 4, 23, 3), base_width: int = 64, sampler: str = "reference",
+                 fuse_frozen_bn: bool = True):
+        """fuse_frozen_bn: every frozen BatchNorm (+ residual add + ReLU) of the backbone and of layer4 runs as ONE
+        hand-written launch per direction (csrc/afan_bn.cu: afan_bn_affine_f32 / _bwd_f32) from a cached (scale, shift)
+        table, instead of the library's eval BatchNorm + add + ReLU kernels; False keeps the library sequence."""
         super().__init__()
         self.sampler = Sampler(sampler)
         self.features = SplitResNet(layers, base_width)
@@ -423,6 +436,9 @@ class FasterRCNN(nn.Module):
         for m in (self.features.conv1, self.features.layer1):
             for p in m.parameters():
                 p.requires_grad = False
+        for m in self.modules():
+            if isinstance(m, (Bottleneck, SplitResNet)):
+                m.fused_bn = bool(fuse_frozen_bn)
 
     def train(self, mode: bool = True):
         super().train(mode)

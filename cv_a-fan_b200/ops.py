@@ -263,6 +263,16 @@ def bn_affine(x, residual, scale_shift, *, relu=False):
     return y
 
 
+def bn_affine_bwd(dy, y, scale_shift, *, relu=False, want_dresidual=False):
+    """Backward of bn_affine for frozen statistics: (dx = scale[c] * dy_eff, dresidual = dy_eff or None)."""
+    n, c, hw = _nchw(dy, 1)
+    dx = torch.empty_like(dy)
+    dres = torch.empty_like(dy) if want_dresidual else None
+    check(_lib.lib().afan_bn_affine_bwd_f32(f32(dy), f32(y) if relu else None, f32(scale_shift), f32(dx), f32(dres), n, c, hw,
+                                            int(bool(relu)), stream()), "afan_bn_affine_bwd_f32")
+    return dx, dres
+
+
 # ------------------------------------------------------------------------------------------------
 # fused SGD (a7 tail)
 # ------------------------------------------------------------------------------------------------
@@ -295,6 +305,26 @@ def nms_flags(boxes: torch.Tensor, scores: torch.Tensor, threshold: float):
                                   _lib.dev_ptr(keep, torch.uint8, "keep"), _lib.dev_ptr(count, torch.int32, "count"),
                                   ptr(ws), ws.numel() * 8, n, stream()), "afan_nms_f32")
     return keep, count
+
+
+def nms_batched(boxes_sorted: torch.Tensor, threshold: float, max_keep: int, want_flags: bool = False):
+    """Greedy NMS of `images` ranked box lists in one launch pair.  boxes_sorted [B, N, 4] (descending score per image).
+    Returns (kept boxes [B, max_keep, 4] in rank order, zero-padded; counts int32 [B]; keep flags uint8 [B, N] by rank or
+    None).  No host sync."""
+    if boxes_sorted.dim() != 3 or boxes_sorted.shape[2] != 4:
+        raise AfanError("nms_batched needs boxes [B, N, 4]")
+    b, n = boxes_sorted.shape[:2]
+    dev = boxes_sorted.device
+    kept = torch.empty(b, max_keep, 4, dtype=torch.float32, device=dev)
+    counts = torch.empty(b, dtype=torch.int32, device=dev)
+    flags = torch.empty(b, n, dtype=torch.uint8, device=dev) if want_flags else None
+    nbytes = _lib.lib().afan_nms_batched_workspace_bytes(b, n)
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
+    check(_lib.lib().afan_nms_batched_f32(f32(boxes_sorted, "boxes"), float(threshold), int(max_keep), f32(kept),
+                                          _lib.dev_ptr(flags, torch.uint8, "keep") if want_flags else None,
+                                          _lib.dev_ptr(counts, torch.int32, "counts"), ptr(ws), ws.numel() * 8, b, n, stream()),
+          "afan_nms_batched_f32")
+    return kept, counts, flags
 
 
 # ------------------------------------------------------------------------------------------------

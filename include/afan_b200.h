@@ -205,6 +205,10 @@ int afan_p2p_close_handle(void* ptr);
  * (float [c][2]); used for model.eval() (main_perturb.py:232-246). */
 int afan_bn_affine_f32(const float* x, const float* residual, const float* scale_shift, float* y,
                        int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream);
+/* Its backward, for BatchNorm layers that stay FROZEN during training (Detection/model.py:27-35,47-48: eval mode,
+ * requires_grad False): dx = scale[c] * dy_eff, dresidual (nullable) = dy_eff, dy_eff = dy where y > 0 when relu. */
+int afan_bn_affine_bwd_f32(const float* dy, const float* y, const float* scale_shift, float* dx, float* dresidual,
+                           int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream);
 
 /* ---- f4: greedy NMS, fully on the device ---------------------------------------------------------------------
  * Replaces Detection/support/src/cuda/nms.cu:23-131 (+ its D2H mask copy and serial CPU sweep, :99-123).
@@ -215,6 +219,16 @@ int afan_bn_affine_f32(const float* x, const float* residual, const float* scale
 int64_t afan_nms_workspace_bytes(int64_t n);
 int afan_nms_f32(const float* boxes_sorted, const int64_t* order, float threshold, uint8_t* keep_flags,
                  int32_t* count_out, void* workspace, int64_t workspace_bytes, int64_t n, afan_stream_t stream);
+
+/* Batched form for the proposal layer (Detection/rpn/region_proposal_network.py:244-256: per-image NMS over the ranked
+ * boxes followed by `[:post_nms_top_n]` and zero padding): one launch pair for the whole batch, one CTA per image, the
+ * sweep stops once max_keep boxes of an image are kept.  boxes_sorted [images][n][4] ranked by descending score;
+ * kept_boxes [images][max_keep][4] (nullable, 16-byte aligned) = the surviving boxes in rank order, zero-padded;
+ * keep_flags [images][n] (nullable) indexed by RANK; counts [images] = min(survivors, max_keep). */
+int64_t afan_nms_batched_workspace_bytes(int64_t images, int64_t n);
+int afan_nms_batched_f32(const float* boxes_sorted, float threshold, int64_t max_keep, float* kept_boxes,
+                         uint8_t* keep_flags, int32_t* counts, void* workspace, int64_t workspace_bytes,
+                         int64_t images, int64_t n, afan_stream_t stream);
 
 /* ---- f4: ROIAlign ------------------------------------------------------------------------------------------------
  * Replaces Detection/support/src/cuda/ROIAlign_cuda.cu:64-122 (forward) and :177-254 (backward), bound by

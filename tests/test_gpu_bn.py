@@ -200,3 +200,40 @@ def test_statistics_survive_large_mean_over_std(shape, groups):
     # fp32 inputs carry ~6e-8 * 7 of representation noise themselves: 2e-3 of the normalised values' O(1) scale is the
     # floor for mean / std = 3500; the unshifted accumulation missed it by 0.3 .. 1.0 (variance lost entirely)
     assert float((y.double().cpu() - ref).abs().max()) < 5e-3 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 6, 10), (3, 5, 7, 9), (2, 64, 38, 63), (1, 256, 4, 4)])
+@pytest.mark.parametrize("relu,res", [(True, True), (True, False), (False, False), (False, True)])
+def test_frozen_affine_forward_backward_vs_torch(shape, relu, res):
+    """afan_bn_affine_f32 / afan_bn_affine_bwd_f32 (frozen BatchNorm + residual + ReLU in one launch per direction, the
+    Detection flavour's backbone) against eval-mode F.batch_norm + add + relu under autograd."""
+    import torch.nn.functional as F
+    d = dev()
+    g = torch.Generator().manual_seed(shape[1])
+    bn = torch.nn.BatchNorm2d(shape[1]).to(d).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(shape[1], generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(shape[1], generator=g))
+        bn.running_mean.copy_(torch.randn(shape[1], generator=g))
+        bn.running_var.copy_(torch.rand(shape[1], generator=g) + 0.5)
+    x = torch.randn(shape, generator=g).to(d).requires_grad_(True)
+    r = torch.randn(shape, generator=g).to(d).requires_grad_(True) if res else None
+    dy = torch.randn(shape, generator=g).to(d)
+    y = PKG.dual_bn.frozen_bn_act(x, bn, residual=r, relu=relu)
+    y.backward(dy)
+    got = (y.detach(), x.grad.clone(), r.grad.clone() if res else None)
+    x.grad = None
+    if res:
+        r.grad = None
+    w = bn(x) + (r if res else 0)
+    w = F.relu(w) if relu else w
+    w.backward(dy)
+    torch.testing.assert_close(got[0], w.detach(), rtol=1e-5, atol=1e-5)
+    same_mask = (got[0] > 0) == (w.detach() > 0) if relu else torch.ones_like(dy, dtype=torch.bool)
+    torch.testing.assert_close(got[1][same_mask], x.grad[same_mask], rtol=1e-5, atol=1e-6)
+    if res:
+        torch.testing.assert_close(got[2][same_mask], r.grad[same_mask], rtol=0, atol=0)
+    # the table follows the module: a write to any of the four tensors rebuilds it
+    with torch.no_grad():
+        bn.bias.add_(1.0)
+    torch.testing.assert_close(PKG.dual_bn.frozen_bn_act(x.detach(), bn), bn(x.detach()), rtol=1e-5, atol=1e-5)

@@ -30,18 +30,18 @@ def _strict_fp32():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def _model(dev, sampler="reference"):
+def _model(dev, sampler="reference", fuse=True):
     m = ref.MODEL
     model = PKG.faster_rcnn.FasterRCNN(m["num_classes"], anchor_ratios=m["anchor_ratios"], anchor_sizes=m["anchor_sizes"],
                                        rpn_pre_nms_top_n=m["pre_nms"], rpn_post_nms_top_n=m["post_nms"], layers=m["layers"],
-                                       base_width=m["base_width"], sampler=sampler)
+                                       base_width=m["base_width"], sampler=sampler, fuse_frozen_bn=fuse)
     return ref.procedural_init(model, 7).to(dev)
 
 
-def _run(name, head_cache):
+def _run(name, head_cache, fuse=True):
     c = ref.CASES[name]
     dev = torch.device("cuda:0")
-    model = _model(dev)
+    model = _model(dev, fuse=fuse)
     tr = PKG.trainer_det.DetAfanTrainer(model, pertub_idx_se=c["se"], gamma_se=c["gamma_se"], gamma_sd=c["gamma_sd"],
                                         randinit=c["randinit"], clip=c["clip"], mix_layer=c["mix_layer"], noise_sd=c["noise_sd"],
                                         only_roi_sd=c["only_roi_sd"], mix_sd=c["mix_sd"], sd_adv_loss_weight=c["w"], lr=ref.LR,
@@ -55,10 +55,10 @@ def _run(name, head_cache):
     return np.array(losses), {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
 
 
-@pytest.mark.parametrize("head_cache", [True, False])
+@pytest.mark.parametrize("head_cache,fuse", [(True, True), (False, True), (True, False)])
 @pytest.mark.parametrize("name", ["A", "B"])
-def test_detection_iteration_matches_executed_reference(name, head_cache):
-    losses, sd = _run(name, head_cache)
+def test_detection_iteration_matches_executed_reference(name, head_cache, fuse):
+    losses, sd = _run(name, head_cache, fuse)
     np.testing.assert_allclose(losses, G[f"{name}/losses"], rtol=2e-3, atol=1e-5)
     keys = [str(k) for k in G["keys"]]
     for k, gold in zip(keys, G[f"{name}/norms"]):

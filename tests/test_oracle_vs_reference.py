@@ -135,7 +135,17 @@ def _det_models(monkeypatch):
         keep[idx] = 1
         return keep, torch.tensor([idx.numel()], dtype=torch.int32)
 
+    def nms_batched(boxes_sorted, thr, max_keep, want_flags=False):
+        b, n = boxes_sorted.shape[:2]
+        kept, counts = torch.zeros(b, max_keep, 4), torch.zeros(b, dtype=torch.int32)
+        for i in range(b):
+            idx = nms_ref(boxes_sorted[i], -torch.arange(n, dtype=torch.float32), thr)[:max_keep]
+            kept[i, :idx.numel()] = boxes_sorted[i][idx]
+            counts[i] = idx.numel()
+        return kept, counts, None
+
     monkeypatch.setattr(pkg.ops, "nms_flags", nms_flags)
+    monkeypatch.setattr(pkg.ops, "nms_batched", nms_batched)
     monkeypatch.setattr(detection, "roi_align", roi_ref)
     with ref_shim_.cpu_cuda_identity():
         ref = D.build_reference_model(det_model, backbone_base, r101, Pooler)
