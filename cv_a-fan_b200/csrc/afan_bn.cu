@@ -116,6 +116,129 @@ __device__ __forceinline__ void bwd_finalize_group(const ReduceParams& p, unsign
 }
 
 // ---- pass 1 -------------------------------------------------------------------------------------
+// the last CTA of a channel (all groups, all splits) folds the partials in a fixed order and finalises
+template <bool BWD>
+__device__ __forceinline__ void reduce_finalize(const ReduceParams& p, unsigned int ch) {
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    constexpr int kMaxGroups = 16;                    // learnable-eta A-FAN batches 9 adversarial groups + clean
+    double t0[kMaxGroups], t1[kMaxGroups];
+    for (unsigned int gg = 0; gg < p.groups; ++gg) {
+        const volatile double* pp = reinterpret_cast<const volatile double*>(p.partials + (static_cast<size_t>(gg) * p.c + ch) * p.splits);
+        double x0 = 0.0, x1 = 0.0;
+        for (unsigned int k = lane; k < p.splits; k += 32) { x0 += pp[2 * k]; x1 += pp[2 * k + 1]; }
+        t0[gg] = warp_sum(x0);
+        t1[gg] = warp_sum(x1);
+    }
+    if (lane != 0) return;
+    if (p.sums_out)
+        for (unsigned int gg = 0; gg < p.groups; ++gg) {
+            p.sums_out[(static_cast<size_t>(gg) * p.c + ch) * 2] = t0[gg];
+            p.sums_out[(static_cast<size_t>(gg) * p.c + ch) * 2 + 1] = t1[gg];
+        }
+    if (BWD) {
+        double dw = 0.0, db = 0.0;
+        for (unsigned int gg = 0; gg < p.groups; ++gg) { db += t0[gg]; dw += t1[gg]; }
+        if (p.dweight) p.dweight[ch] = static_cast<float>(dw);
+        if (p.dbias) p.dbias[ch] = static_cast<float>(db);
+        if (p.do_finalize)
+            for (unsigned int gg = 0; gg < p.groups; ++gg) bwd_finalize_group(p, gg * p.c + ch, ch, t0[gg], t1[gg]);
+    } else if (p.do_finalize) {
+        fwd_finalize_channel(p, ch, t0, t1);
+    }
+}
+
+template <bool BWD, bool RELU>
+__device__ __forceinline__ void peel_add(float av, float bv, float yv, float mean, float kshift, float& acc0, float& acc1) {
+    if (BWD) {
+        const float d = (RELU && !(yv > 0.f)) ? 0.f : av;
+        acc0 += d;
+        acc1 = fmaf(d, bv - mean, acc1);
+    } else {
+        const float t = av - kshift;
+        acc0 += t;
+        acc1 = fmaf(t, t, acc1);
+    }
+}
+
+// Pass 1 for H*W % 4 != 0 (BASELINE config 5's 129 x 129 and 33 x 33 maps): the scalar form of bn_reduce_kernel spends ~40
+// instructions per element on index arithmetic and is issue-bound at 0.3 of the HBM roofline (ncu, 8x256x129x129).  Here a
+// CTA takes the same fraction [plo, phi) of EVERY plane of its (group, channel) domain; a plane segment starts at an
+// arbitrary 4-byte alignment, so it is peeled into a scalar head, a 16-byte-aligned body moved with 128-bit loads and a
+// scalar tail -- no division per element, four planes in flight per thread.  Same partials / finalisation as the kernel below.
+template <bool BWD, bool RELU>
+__global__ void __launch_bounds__(kThreads) bn_reduce_peel_kernel(const ReduceParams p) {
+    const unsigned int s = blockIdx.x, gc = blockIdx.y;
+    const unsigned int g = gc / p.c, ch = gc - g * p.c;
+    const unsigned int hw = p.hwv;                                          // scalar geometry: hwv == H*W
+    const unsigned int plo = static_cast<unsigned int>(static_cast<unsigned long long>(hw) * s / p.splits);
+    const unsigned int phi = static_cast<unsigned int>(static_cast<unsigned long long>(hw) * (s + 1) / p.splits);
+    const unsigned int len = phi - plo;
+    const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * hw;
+    const size_t plane_stride = static_cast<size_t>(p.c) * hw;
+    const float mean = BWD ? p.save_mean[gc] : 0.f;
+    const float kshift = BWD ? 0.f : __ldg(p.a + plane0);
+    float acc0 = 0.f, acc1 = 0.f;
+#define add(av, bv, yv) peel_add<BWD, RELU>((av), (bv), (yv), mean, kshift, acc0, acc1)
+    constexpr int PL = 4;                                                    // planes in flight
+    for (unsigned int n0 = 0; n0 < p.n; n0 += PL) {
+        size_t base[PL];
+        unsigned int head[PL], nbody[PL], most = 0u;
+#pragma unroll
+        for (int k = 0; k < PL; ++k) {
+            const bool on = n0 + k < p.n;
+            base[k] = plane0 + (on ? n0 + k : n0) * plane_stride + plo;
+            const unsigned int mis = static_cast<unsigned int>(base[k] & 3u);      // tensor bases are 16-byte aligned
+            head[k] = on ? min((4u - mis) & 3u, len) : 0u;
+            nbody[k] = on ? (len - head[k]) >> 2 : 0u;
+            most = max(most, nbody[k]);
+        }
+        for (unsigned int v = threadIdx.x; v < most; v += kThreads) {
+            float4 a[PL] = {}, b[PL] = {}, y[PL] = {};
+#pragma unroll
+            for (int k = 0; k < PL; ++k)
+                if (v < nbody[k]) {
+                    const size_t idx = base[k] + head[k] + 4u * v;
+                    a[k] = *reinterpret_cast<const float4*>(p.a + idx);
+                    if (BWD) b[k] = *reinterpret_cast<const float4*>(p.b + idx);
+                    if (BWD && RELU) y[k] = *reinterpret_cast<const float4*>(p.y + idx);
+                }
+#pragma unroll
+            for (int k = 0; k < PL; ++k)
+                if (v < nbody[k]) {
+                    add(a[k].x, b[k].x, y[k].x); add(a[k].y, b[k].y, y[k].y);
+                    add(a[k].z, b[k].z, y[k].z); add(a[k].w, b[k].w, y[k].w);
+                }
+        }
+        // scalar heads (<= 3 elements) and tails (<= 3): lanes 0..7 of warp k take plane k's ends
+        const unsigned int w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+#pragma unroll
+        for (int k = 0; k < PL; ++k)
+            if (w == static_cast<unsigned int>(k) && n0 + k < p.n) {
+                const unsigned int tail0 = head[k] + 4u * nbody[k];
+                unsigned int e = len;                                        // none
+                if (lane < head[k]) e = lane;
+                else if (lane >= 4u && lane - 4u < len - tail0) e = tail0 + lane - 4u;
+                if (e < len) {
+                    const size_t idx = base[k] + e;
+                    add(p.a[idx], BWD ? p.b[idx] : 0.f, (BWD && RELU) ? p.y[idx] : 0.f);
+                }
+            }
+    }
+    __shared__ double scratch[64];
+    __shared__ int sflag;
+    double d0 = acc0, d1 = acc1;
+    block_sum2(d0, d1, scratch);
+    if (threadIdx.x == 0) {
+        if (BWD) d1 *= static_cast<double>(p.save_invstd[gc]);
+        p.partials[static_cast<size_t>(gc) * p.splits + s] =
+            BWD ? make_double2(d0, d1) : unshift_sums(d0, d1, static_cast<double>(len) * p.n, static_cast<double>(kshift));
+    }
+    if (!last_cta_arrives(p.counters + ch, p.groups * p.splits, &sflag)) return;
+    reduce_finalize<BWD>(p, ch);
+#undef add
+}
+
 template <int VEC, bool BWD, bool RELU>
 __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams p) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
@@ -192,33 +315,7 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const ReduceParams 
     }
     // last CTA of this CHANNEL (all groups, all splits) folds and finalises
     if (!last_cta_arrives(p.counters + ch, p.groups * p.splits, &sflag)) return;
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    constexpr int kMaxGroups = 16;                    // learnable-eta A-FAN batches 9 adversarial groups + clean
-    double t0[kMaxGroups], t1[kMaxGroups];
-    for (unsigned int gg = 0; gg < p.groups; ++gg) {
-        const volatile double* pp = reinterpret_cast<const volatile double*>(p.partials + (static_cast<size_t>(gg) * p.c + ch) * p.splits);
-        double x0 = 0.0, x1 = 0.0;
-        for (unsigned int k = lane; k < p.splits; k += 32) { x0 += pp[2 * k]; x1 += pp[2 * k + 1]; }
-        t0[gg] = warp_sum(x0);
-        t1[gg] = warp_sum(x1);
-    }
-    if (lane != 0) return;
-    if (p.sums_out)
-        for (unsigned int gg = 0; gg < p.groups; ++gg) {
-            p.sums_out[(static_cast<size_t>(gg) * p.c + ch) * 2] = t0[gg];
-            p.sums_out[(static_cast<size_t>(gg) * p.c + ch) * 2 + 1] = t1[gg];
-        }
-    if (BWD) {
-        double dw = 0.0, db = 0.0;
-        for (unsigned int gg = 0; gg < p.groups; ++gg) { db += t0[gg]; dw += t1[gg]; }
-        if (p.dweight) p.dweight[ch] = static_cast<float>(dw);
-        if (p.dbias) p.dbias[ch] = static_cast<float>(db);
-        if (p.do_finalize)
-            for (unsigned int gg = 0; gg < p.groups; ++gg) bwd_finalize_group(p, gg * p.c + ch, ch, t0[gg], t1[gg]);
-    } else if (p.do_finalize) {
-        fwd_finalize_channel(p, ch, t0, t1);
-    }
+    reduce_finalize<BWD>(p, ch);
 }
 
 // stand-alone finalisers for the NCCL path (sums already all-reduced): one thread per channel
@@ -251,9 +348,31 @@ struct ApplyParams {
     const void* table;       // fwd: float2 [G*C]   bwd: float4 [G*C]
     unsigned int total_v;    // vectors in the tensor
     unsigned int hwv, c, n;  // n = samples per group
+    unsigned int hw_flat;    // != 0: H*W % 4 != 0 but the tensor is moved as 16-byte vectors of the FLAT index space; a
+                             // vector may then straddle two planes (one in H*W/4 does): its first `cut` lanes belong to
+                             // plane e0 / hw, the rest to the next plane
 };
 
-template <int VEC, bool RELU, bool RES>
+// table slot(s) of the vector at flat vector index i: (index of lanes [0, cut), index of lanes [cut, 4), cut)
+template <bool FLAT>
+__device__ __forceinline__ void apply_slots(const ApplyParams& p, unsigned int i, bool with_groups, unsigned int& s0,
+                                            unsigned int& s1, unsigned int& cut) {
+    auto slot = [&](unsigned int plane) {
+        const unsigned int smp = plane / p.c, ch = plane - smp * p.c;
+        return with_groups ? (smp / p.n) * p.c + ch : ch;
+    };
+    if constexpr (!FLAT) {
+        s0 = s1 = slot(i / p.hwv);
+        cut = 4u;
+    } else {
+        const unsigned int e0 = i * 4u, plane = e0 / p.hw_flat, left = p.hw_flat - (e0 - plane * p.hw_flat);
+        s0 = slot(plane);
+        cut = left < 4u ? left : 4u;
+        s1 = left < 4u ? slot(plane + 1u) : s0;
+    }
+}
+
+template <int VEC, bool RELU, bool RES, bool FLAT = false>
 __global__ void __launch_bounds__(kThreads) bn_fwd_apply_kernel(const ApplyParams p) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
     const V* x_v = reinterpret_cast<const V*>(p.x);
@@ -263,16 +382,18 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_apply_kernel(const ApplyParam
     const unsigned int span = gridDim.x * kThreads * kBnUnroll;
     for (unsigned int i0 = blockIdx.x * kThreads * kBnUnroll + threadIdx.x; i0 < p.total_v; i0 += span) {
         V x[kBnUnroll] = {}, r[kBnUnroll] = {};
-        float2 ss[kBnUnroll] = {};
+        float2 ss[kBnUnroll] = {}, st[kBnUnroll] = {};
+        unsigned int cut[kBnUnroll] = {};
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
             const unsigned int i = i0 + u * kThreads;
             if (i < p.total_v) {
                 x[u] = ld_stream(x_v + i);                 // last use of x in the forward pass
                 if (RES) r[u] = ld_stream(r_v + i);
-                const unsigned int plane = i / p.hwv;      // = sample * C + channel
-                const unsigned int smp = plane / p.c, ch = plane - smp * p.c;
-                ss[u] = __ldg(table + (smp / p.n) * p.c + ch);
+                unsigned int s0, s1;
+                apply_slots<FLAT>(p, i, true, s0, s1, cut[u]);
+                ss[u] = __ldg(table + s0);
+                st[u] = (FLAT && s1 != s0) ? __ldg(table + s1) : ss[u];
             }
         }
 #pragma unroll
@@ -281,8 +402,9 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_apply_kernel(const ApplyParam
             if (i < p.total_v) {
                 V o;
                 if constexpr (VEC == 4) {
-                    o.x = fmaf(x[u].x, ss[u].x, ss[u].y); o.y = fmaf(x[u].y, ss[u].x, ss[u].y);
-                    o.z = fmaf(x[u].z, ss[u].x, ss[u].y); o.w = fmaf(x[u].w, ss[u].x, ss[u].y);
+                    const float2 t1 = (!FLAT || cut[u] > 1u) ? ss[u] : st[u], t2 = (!FLAT || cut[u] > 2u) ? ss[u] : st[u], t3 = (!FLAT || cut[u] > 3u) ? ss[u] : st[u];
+                    o.x = fmaf(x[u].x, ss[u].x, ss[u].y); o.y = fmaf(x[u].y, t1.x, t1.y);
+                    o.z = fmaf(x[u].z, t2.x, t2.y); o.w = fmaf(x[u].w, t3.x, t3.y);
                     if (RES) { o.x += r[u].x; o.y += r[u].y; o.z += r[u].z; o.w += r[u].w; }
                     if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                 } else {
@@ -296,7 +418,7 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_apply_kernel(const ApplyParam
     }
 }
 
-template <int VEC, bool RELU, bool DRES>
+template <int VEC, bool RELU, bool DRES, bool FLAT = false>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParams p) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
     const V* dy_v = reinterpret_cast<const V*>(p.x);
@@ -308,7 +430,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParam
     const unsigned int span = gridDim.x * kThreads * kBnUnroll;
     for (unsigned int i0 = blockIdx.x * kThreads * kBnUnroll + threadIdx.x; i0 < p.total_v; i0 += span) {
         V dy[kBnUnroll] = {}, x[kBnUnroll] = {}, y[kBnUnroll] = {};
-        float4 cf[kBnUnroll] = {};
+        float4 cf[kBnUnroll] = {}, cg[kBnUnroll] = {};
+        unsigned int cut[kBnUnroll] = {};
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
             const unsigned int i = i0 + u * kThreads;
@@ -316,9 +439,10 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParam
                 dy[u] = ld_stream(dy_v + i);
                 x[u] = ld_stream(x_v + i);
                 if (RELU) y[u] = ld_stream(y_v + i);
-                const unsigned int plane = i / p.hwv;
-                const unsigned int smp = plane / p.c, ch = plane - smp * p.c;
-                cf[u] = __ldg(coef + (smp / p.n) * p.c + ch);
+                unsigned int s0, s1;
+                apply_slots<FLAT>(p, i, true, s0, s1, cut[u]);
+                cf[u] = __ldg(coef + s0);
+                cg[u] = (FLAT && s1 != s0) ? __ldg(coef + s1) : cf[u];
             }
         }
 #pragma unroll
@@ -327,16 +451,18 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParam
             if (i < p.total_v) {
                 V dx, dr;
                 // dx = w*invstd * (dy_eff - mean(dy) - (x - mean) * invstd * mean(dy*xhat))
-                auto one = [&](float d, float xv, float yv, float& o, float& r) {
+                auto one = [&](const float4 c4, float d, float xv, float yv, float& o, float& r) {
                     const float de = (RELU && !(yv > 0.f)) ? 0.f : d;
                     r = de;
-                    o = cf[u].x * (de - cf[u].y - (xv - cf[u].w) * cf[u].z);
+                    o = c4.x * (de - c4.y - (xv - c4.w) * c4.z);
                 };
                 if constexpr (VEC == 4) {
-                    one(dy[u].x, x[u].x, y[u].x, dx.x, dr.x); one(dy[u].y, x[u].y, y[u].y, dx.y, dr.y);
-                    one(dy[u].z, x[u].z, y[u].z, dx.z, dr.z); one(dy[u].w, x[u].w, y[u].w, dx.w, dr.w);
+                    one(cf[u], dy[u].x, x[u].x, y[u].x, dx.x, dr.x);
+                    one((!FLAT || cut[u] > 1u) ? cf[u] : cg[u], dy[u].y, x[u].y, y[u].y, dx.y, dr.y);
+                    one((!FLAT || cut[u] > 2u) ? cf[u] : cg[u], dy[u].z, x[u].z, y[u].z, dx.z, dr.z);
+                    one((!FLAT || cut[u] > 3u) ? cf[u] : cg[u], dy[u].w, x[u].w, y[u].w, dx.w, dr.w);
                 } else {
-                    one(dy[u], x[u], y[u], dx, dr);
+                    one(cf[u], dy[u], x[u], y[u], dx, dr);
                 }
                 dx_v[i] = dx;
                 if (DRES) dr_v[i] = dr;
@@ -345,10 +471,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const ApplyParam
     }
 }
 
-
 // Backward of the frozen-statistics affine (afan_bn_affine_f32): dx = scale[c] * dy_eff, dresidual = dy_eff, with
 // dy_eff = dy where the forward output was positive (ReLU) -- one pass: reads dy (+ y), writes dx (+ dresidual).
-template <int VEC, bool RELU, bool DRES>
+template <int VEC, bool RELU, bool DRES, bool FLAT = false>
 __global__ void __launch_bounds__(kThreads) bn_affine_bwd_kernel(const ApplyParams p) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
     const V* dy_v = reinterpret_cast<const V*>(p.x);
@@ -359,15 +484,18 @@ __global__ void __launch_bounds__(kThreads) bn_affine_bwd_kernel(const ApplyPara
     const unsigned int span = gridDim.x * kThreads * kBnUnroll;
     for (unsigned int i0 = blockIdx.x * kThreads * kBnUnroll + threadIdx.x; i0 < p.total_v; i0 += span) {
         V dy[kBnUnroll] = {}, y[kBnUnroll] = {};
-        float sc[kBnUnroll] = {};
+        float sc[kBnUnroll] = {}, sd[kBnUnroll] = {};
+        unsigned int cut[kBnUnroll] = {};
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
             const unsigned int i = i0 + u * kThreads;
             if (i < p.total_v) {
                 dy[u] = ld_stream(dy_v + i);
                 if (RELU) y[u] = __ldg(y_v + i);               // y stays live: it is the next layer's saved input
-                const unsigned int plane = i / p.hwv;
-                sc[u] = __ldg(table + (plane % p.c)).x;
+                unsigned int s0, s1;
+                apply_slots<FLAT>(p, i, false, s0, s1, cut[u]);
+                sc[u] = __ldg(table + s0).x;
+                sd[u] = (FLAT && s1 != s0) ? __ldg(table + s1).x : sc[u];
             }
         }
 #pragma unroll
@@ -375,16 +503,18 @@ __global__ void __launch_bounds__(kThreads) bn_affine_bwd_kernel(const ApplyPara
             const unsigned int i = i0 + u * kThreads;
             if (i < p.total_v) {
                 V dx, dr;
-                auto one = [&](float d, float yv, float& o, float& r) {
+                auto one = [&](float scale, float d, float yv, float& o, float& r) {
                     const float de = (RELU && !(yv > 0.f)) ? 0.f : d;
                     r = de;
-                    o = sc[u] * de;
+                    o = scale * de;
                 };
                 if constexpr (VEC == 4) {
-                    one(dy[u].x, y[u].x, dx.x, dr.x); one(dy[u].y, y[u].y, dx.y, dr.y);
-                    one(dy[u].z, y[u].z, dx.z, dr.z); one(dy[u].w, y[u].w, dx.w, dr.w);
+                    one(sc[u], dy[u].x, y[u].x, dx.x, dr.x);
+                    one((!FLAT || cut[u] > 1u) ? sc[u] : sd[u], dy[u].y, y[u].y, dx.y, dr.y);
+                    one((!FLAT || cut[u] > 2u) ? sc[u] : sd[u], dy[u].z, y[u].z, dx.z, dr.z);
+                    one((!FLAT || cut[u] > 3u) ? sc[u] : sd[u], dy[u].w, y[u].w, dx.w, dr.w);
                 } else {
-                    one(dy[u], y[u], dx, dr);
+                    one(sc[u], dy[u], y[u], dx, dr);
                 }
                 dx_v[i] = dx;
                 if (DRES) dr_v[i] = dr;
@@ -456,6 +586,7 @@ __device__ __forceinline__ double2 cluster_fold(cg::cluster_group& cluster, doub
 template <int VEC, bool RELU, bool RES>
 __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const ClusterParams p) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
+    constexpr int U = VEC == 4 ? kBnUnroll : 4 * kBnUnroll;       // scalar path (H*W % 4 != 0): same bytes in flight per thread
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
     pdl_wait();                                                     // PDL: scheduled during the previous kernel's tail
@@ -478,11 +609,11 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const C
         const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
         const float kshift = __ldg(p.a + plane0 * VEC);               // accumulate x - K (see unshift_sums)
         float acc0 = 0.f, acc1 = 0.f;
-        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
-            V a[kBnUnroll];
-            bool ok[kBnUnroll];
+        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * U) {
+            V a[U];
+            bool ok[U];
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const unsigned int j = j0 + u * kClusterThreads;
                 ok[u] = j < hi;
                 if constexpr (VEC == 4) a[u] = make_float4(kshift, kshift, kshift, kshift); else a[u] = kshift;
@@ -492,7 +623,7 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const C
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 if constexpr (VEC == 4) {
                     const float tx = a[u].x - kshift, ty = a[u].y - kshift, tz = a[u].z - kshift, tw = a[u].w - kshift;
                     acc0 += (tx + ty) + (tz + tw);
@@ -541,11 +672,11 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const C
     for (unsigned int g = 0; g < p.groups; ++g) {
         const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
         const float2 ss = s_ss[g];
-        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
-            V a[kBnUnroll] = {}, r[kBnUnroll] = {};
-            size_t idx[kBnUnroll];
+        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * U) {
+            V a[U] = {}, r[U] = {};
+            size_t idx[U];
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const unsigned int j = j0 + u * kClusterThreads;
                 if (j < hi) {
                     const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
@@ -555,7 +686,7 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const C
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const unsigned int j = j0 + u * kClusterThreads;
                 if (j < hi) {
                     V o;
@@ -580,6 +711,7 @@ __global__ void __launch_bounds__(kClusterThreads) bn_fwd_cluster_kernel(const C
 template <int VEC, bool RELU, bool DRES>
 __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const ClusterParams p) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
+    constexpr int U = VEC == 4 ? kBnUnroll : 4 * kBnUnroll;       // scalar path (H*W % 4 != 0): same bytes in flight per thread
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), ch = blockIdx.x / cs;
     pdl_wait();                                                     // PDL: scheduled during the previous kernel's tail
@@ -604,10 +736,10 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
         const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
         const float mean = p.save_mean[g * p.c + ch];
         float acc0 = 0.f, acc1 = 0.f;
-        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
-            V d[kBnUnroll] = {}, x[kBnUnroll] = {}, y[kBnUnroll] = {};
+        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * U) {
+            V d[U] = {}, x[U] = {}, y[U] = {};
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const unsigned int j = j0 + u * kClusterThreads;
                 if (j < hi) {
                     const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
@@ -618,7 +750,7 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const unsigned int j = j0 + u * kClusterThreads;
                 if (j < hi) {
                     auto one = [&](float dv, float xv, float yv) {
@@ -661,11 +793,11 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
     for (unsigned int g = 0; g < p.groups; ++g) {
         const size_t plane0 = (static_cast<size_t>(g) * p.n * p.c + ch) * p.hwv;
         const float4 cf = s_cf[g];
-        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * kBnUnroll) {
-            V d[kBnUnroll] = {}, x[kBnUnroll] = {}, y[kBnUnroll] = {};
-            size_t idx[kBnUnroll];
+        for (unsigned int j0 = lo + threadIdx.x; j0 < hi; j0 += kClusterThreads * U) {
+            V d[U] = {}, x[U] = {}, y[U] = {};
+            size_t idx[U];
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const unsigned int j = j0 + u * kClusterThreads;
                 if (j < hi) {
                     const unsigned int nn = j / p.hwv, off = j - nn * p.hwv;
@@ -676,7 +808,7 @@ __global__ void __launch_bounds__(kClusterThreads) bn_bwd_cluster_kernel(const C
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kBnUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const unsigned int j = j0 + u * kClusterThreads;
                 if (j < hi) {
                     V dx, dr;
@@ -1330,8 +1462,8 @@ __host__ inline int launch_plane(K kernel, const PlaneParams& p, size_t smem, cu
 
 // ---- host helpers -------------------------------------------------------------------------------
 struct BnShape {
-    bool ok, vec;
-    unsigned int groups, n, c, hwv, splits, total_v;
+    bool ok, vec, aligned, flat; // flat: H*W % 4 != 0, but bases are 16-byte aligned and the element count is a multiple of 4
+    unsigned int groups, n, c, hwv, splits, total_v, hw, total;
     int err;
 };
 
@@ -1343,6 +1475,10 @@ __host__ inline BnShape bn_shape(int64_t groups, int64_t n, int64_t c, int64_t h
     const int64_t total = groups * n * c * hw;
     if (total >= (int64_t(1) << 32) || n * hw >= (int64_t(1) << 32)) { s.err = AFAN_ERR_UNSUPPORTED; return s; }
     s.vec = all_aligned && (hw % 4 == 0);
+    s.aligned = all_aligned;
+    s.flat = all_aligned && !s.vec && (total % 4 == 0);
+    s.hw = static_cast<unsigned int>(hw);
+    s.total = static_cast<unsigned int>(total);
     const int64_t v = s.vec ? 4 : 1;
     s.groups = static_cast<unsigned int>(groups);
     s.n = static_cast<unsigned int>(n);
@@ -1366,8 +1502,13 @@ __host__ inline int apply_grid(unsigned int total_v) {
 }
 
 template <bool BWD>
-int launch_reduce(const ReduceParams& p, bool vec, bool relu, cudaStream_t st) {
+int launch_reduce(const ReduceParams& p, bool vec, bool relu, cudaStream_t st, bool peel = false) {
     dim3 grid(p.splits, p.groups * p.c);
+    if (!vec && peel) {
+        if (BWD && relu) bn_reduce_peel_kernel<BWD, true><<<grid, kThreads, 0, st>>>(p);
+        else bn_reduce_peel_kernel<BWD, false><<<grid, kThreads, 0, st>>>(p);
+        return launch_status();
+    }
     if (vec) {
         if (BWD && relu) bn_reduce_kernel<4, BWD, true><<<grid, kThreads, 0, st>>>(p);
         else bn_reduce_kernel<4, BWD, false><<<grid, kThreads, 0, st>>>(p);
@@ -1378,10 +1519,22 @@ int launch_reduce(const ReduceParams& p, bool vec, bool relu, cudaStream_t st) {
     return launch_status();
 }
 
+// element-wise kernels: 16-byte vectors whenever the bases allow it -- over planes (H*W % 4 == 0) or over the flat index
+// space with plane-straddling vectors (apply_slots); returns the launcher's `vec`
+__host__ inline bool apply_mode(ApplyParams& p, const BnShape& s) {
+    p.c = s.c; p.n = s.n;
+    if (s.vec || !s.flat) { p.total_v = s.total_v; p.hwv = s.hwv; p.hw_flat = 0u; return s.vec; }
+    p.total_v = s.total / 4u; p.hwv = 0u; p.hw_flat = s.hw;
+    return true;
+}
+
 int launch_fwd_apply(const ApplyParams& p, bool vec, bool relu, bool res, cudaStream_t st) {
     const int grid = apply_grid(p.total_v);
 #define AFAN_FA(V, R, S) bn_fwd_apply_kernel<V, R, S><<<grid, kThreads, 0, st>>>(p)
-    if (vec) { if (relu) { if (res) AFAN_FA(4, true, true); else AFAN_FA(4, true, false); }
+    if (p.hw_flat) {
+        if (relu) { if (res) bn_fwd_apply_kernel<4, true, true, true><<<grid, kThreads, 0, st>>>(p); else bn_fwd_apply_kernel<4, true, false, true><<<grid, kThreads, 0, st>>>(p); }
+        else      { if (res) bn_fwd_apply_kernel<4, false, true, true><<<grid, kThreads, 0, st>>>(p); else bn_fwd_apply_kernel<4, false, false, true><<<grid, kThreads, 0, st>>>(p); }
+    } else if (vec) { if (relu) { if (res) AFAN_FA(4, true, true); else AFAN_FA(4, true, false); }
                else      { if (res) AFAN_FA(4, false, true); else AFAN_FA(4, false, false); } }
     else     { if (relu) { if (res) AFAN_FA(1, true, true); else AFAN_FA(1, true, false); }
                else      { if (res) AFAN_FA(1, false, true); else AFAN_FA(1, false, false); } }
@@ -1392,7 +1545,10 @@ int launch_fwd_apply(const ApplyParams& p, bool vec, bool relu, bool res, cudaSt
 int launch_bwd_apply(const ApplyParams& p, bool vec, bool relu, bool dres, cudaStream_t st) {
     const int grid = apply_grid(p.total_v);
 #define AFAN_BA(V, R, S) bn_bwd_apply_kernel<V, R, S><<<grid, kThreads, 0, st>>>(p)
-    if (vec) { if (relu) { if (dres) AFAN_BA(4, true, true); else AFAN_BA(4, true, false); }
+    if (p.hw_flat) {
+        if (relu) { if (dres) bn_bwd_apply_kernel<4, true, true, true><<<grid, kThreads, 0, st>>>(p); else bn_bwd_apply_kernel<4, true, false, true><<<grid, kThreads, 0, st>>>(p); }
+        else      { if (dres) bn_bwd_apply_kernel<4, false, true, true><<<grid, kThreads, 0, st>>>(p); else bn_bwd_apply_kernel<4, false, false, true><<<grid, kThreads, 0, st>>>(p); }
+    } else if (vec) { if (relu) { if (dres) AFAN_BA(4, true, true); else AFAN_BA(4, true, false); }
                else      { if (dres) AFAN_BA(4, false, true); else AFAN_BA(4, false, false); } }
     else     { if (relu) { if (dres) AFAN_BA(1, true, true); else AFAN_BA(1, true, false); }
                else      { if (dres) AFAN_BA(1, false, true); else AFAN_BA(1, false, false); } }
@@ -1403,7 +1559,10 @@ int launch_bwd_apply(const ApplyParams& p, bool vec, bool relu, bool dres, cudaS
 int launch_affine_bwd(const ApplyParams& p, bool vec, bool relu, bool dres, cudaStream_t st) {
     const int grid = apply_grid(p.total_v);
 #define AFAN_AB(V, R, S) bn_affine_bwd_kernel<V, R, S><<<grid, kThreads, 0, st>>>(p)
-    if (vec) { if (relu) { if (dres) AFAN_AB(4, true, true); else AFAN_AB(4, true, false); }
+    if (p.hw_flat) {
+        if (relu) { if (dres) bn_affine_bwd_kernel<4, true, true, true><<<grid, kThreads, 0, st>>>(p); else bn_affine_bwd_kernel<4, true, false, true><<<grid, kThreads, 0, st>>>(p); }
+        else      { if (dres) bn_affine_bwd_kernel<4, false, true, true><<<grid, kThreads, 0, st>>>(p); else bn_affine_bwd_kernel<4, false, false, true><<<grid, kThreads, 0, st>>>(p); }
+    } else if (vec) { if (relu) { if (dres) AFAN_AB(4, true, true); else AFAN_AB(4, true, false); }
                else      { if (dres) AFAN_AB(4, false, true); else AFAN_AB(4, false, false); } }
     else     { if (relu) { if (dres) AFAN_AB(1, true, true); else AFAN_AB(1, true, false); }
                else      { if (dres) AFAN_AB(1, false, true); else AFAN_AB(1, false, false); } }
@@ -1449,7 +1608,7 @@ static int bn_fwd_reduce_impl(const float* x, double* sums_out, bool finalize, c
     p.count = static_cast<double>(n) * static_cast<double>(hw);
     p.eps = eps; p.momentum = momentum; p.replay = replay;
     p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv; p.splits = s.splits;
-    return launch_reduce<false>(p, s.vec, false, st);
+    return launch_reduce<false>(p, s.vec, false, st, s.aligned && hw >= 256);
 }
 
 AFAN_EXPORT int afan_bn_fwd_apply_f32(const float* x, const float* residual, float* y, const void* workspace,
@@ -1463,8 +1622,8 @@ AFAN_EXPORT int afan_bn_fwd_apply_f32(const float* x, const float* residual, flo
     ApplyParams p{};
     p.x = x; p.b = residual; p.out = y;
     p.table = wsp(workspace, bn_layout(groups, c).table);
-    p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
-    return launch_fwd_apply(p, s.vec, relu != 0, residual != nullptr, static_cast<cudaStream_t>(stream));
+    const bool vec = apply_mode(p, s);
+    return launch_fwd_apply(p, vec, relu != 0, residual != nullptr, static_cast<cudaStream_t>(stream));
 }
 
 AFAN_EXPORT int afan_bn_fwd_f32(const float* x, const float* residual, const float* weight, const float* bias,
@@ -1564,8 +1723,8 @@ AFAN_EXPORT int afan_bn_affine_f32(const float* x, const float* residual, const 
     if (!x || !y || !scale_shift) return AFAN_ERR_NULL;
     ApplyParams p{};
     p.x = x; p.b = residual; p.out = y; p.table = scale_shift;
-    p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
-    return launch_fwd_apply(p, s.vec, relu != 0, residual != nullptr, static_cast<cudaStream_t>(stream));
+    const bool vec = apply_mode(p, s);
+    return launch_fwd_apply(p, vec, relu != 0, residual != nullptr, static_cast<cudaStream_t>(stream));
 }
 
 AFAN_EXPORT int afan_bn_affine_bwd_f32(const float* dy, const float* y, const float* scale_shift, float* dx, float* dresidual,
@@ -1576,8 +1735,8 @@ AFAN_EXPORT int afan_bn_affine_bwd_f32(const float* dy, const float* y, const fl
     if (!dy || !dx || !scale_shift || (relu && !y)) return AFAN_ERR_NULL;
     ApplyParams p{};
     p.x = dy; p.y = y; p.out = dx; p.out2 = dresidual; p.table = scale_shift;
-    p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
-    return launch_affine_bwd(p, s.vec, relu != 0, dresidual != nullptr, static_cast<cudaStream_t>(stream));
+    const bool vec = apply_mode(p, s);
+    return launch_affine_bwd(p, vec, relu != 0, dresidual != nullptr, static_cast<cudaStream_t>(stream));
 }
 
 // ---- backward -----------------------------------------------------------------------------------
@@ -1603,7 +1762,7 @@ static int bn_bwd_reduce_impl(const float* dy, const float* x, const float* y, c
     p.dweight = dweight; p.dbias = dbias;
     p.count = static_cast<double>(n) * static_cast<double>(hw);
     p.groups = s.groups; p.n = s.n; p.c = s.c; p.hwv = s.hwv; p.splits = s.splits;
-    return launch_reduce<true>(p, s.vec, relu != 0, st);
+    return launch_reduce<true>(p, s.vec, relu != 0, st, s.aligned && hw >= 256);
 }
 
 AFAN_EXPORT int afan_bn_bwd_apply_f32(const float* dy, const float* x, const float* y, float* dx, float* dresidual,
@@ -1619,8 +1778,8 @@ AFAN_EXPORT int afan_bn_bwd_apply_f32(const float* dy, const float* x, const flo
     ApplyParams p{};
     p.x = dy; p.b = x; p.y = y; p.out = dx; p.out2 = dresidual;
     p.table = wsp(workspace, bn_layout(groups, c).coef);
-    p.total_v = s.total_v; p.hwv = s.hwv; p.c = s.c; p.n = s.n;
-    return launch_bwd_apply(p, s.vec, relu != 0, dresidual != nullptr, static_cast<cudaStream_t>(stream));
+    const bool vec = apply_mode(p, s);
+    return launch_bwd_apply(p, vec, relu != 0, dresidual != nullptr, static_cast<cudaStream_t>(stream));
 }
 
 AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y, const float* weight,
