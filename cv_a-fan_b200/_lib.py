@@ -33,6 +33,9 @@ SIGNATURES = {
     "afan_l2ball_proj_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp]),
     "afan_mix_feature_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "afan_sat_mix_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _i64, _vp]),
+    "afan_shortcut_a_fwd_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "afan_shortcut_a_bwd_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "afan_linear_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "afan_nms_workspace_bytes": (_i64, [_i64]),
     "afan_nms_f32": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64, _i64, _vp]),
     "afan_nms_batched_workspace_bytes": (_i64, [_i64, _i64]),

@@ -59,6 +59,78 @@ __global__ void __launch_bounds__(kThreads) ffma_probe_kernel(float* __restrict_
     out[blockIdx.x * kThreads + threadIdx.x] = s;
 }
 
+
+// Option-A shortcut of a stage transition (Classification/resnet_s.py:60-63: F.pad(x[:, :, ::2, ::2], (0,0,0,0,p,p))): the
+// library runs it as a strided copy + a zero fill + a padded copy (and three more launches backwards).  One pass each way:
+// forward writes every element of y [n][c+2p][h/2][w/2] (zeros in the padded channels), backward writes every element of
+// dx [n][c][h][w] (dy at the even positions, zero elsewhere).
+__global__ void __launch_bounds__(kThreads)
+shortcut_a_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long total, int c, int h, int w, int pad) {
+    const int ho = (h + 1) >> 1, wo = (w + 1) >> 1, co = c + 2 * pad;
+    const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total; i += stride) {
+        const int j = static_cast<int>(i % wo);
+        long long t = i / wo;
+        const int r = static_cast<int>(t % ho);
+        t /= ho;
+        const int ch = static_cast<int>(t % co) - pad;
+        const long long n = t / co;
+        y[i] = (ch >= 0 && ch < c) ? __ldg(x + ((n * c + ch) * h + 2 * r) * w + 2 * j) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+shortcut_a_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long total, int c, int h, int w, int pad) {
+    const int ho = (h + 1) >> 1, wo = (w + 1) >> 1, co = c + 2 * pad;
+    const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+    for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total; i += stride) {
+        const int j = static_cast<int>(i % w);
+        long long t = i / w;
+        const int r = static_cast<int>(t % h);
+        t /= h;
+        const int ch = static_cast<int>(t % c);
+        const long long n = t / c;
+        dx[i] = ((r | j) & 1) ? 0.f : __ldg(dy + ((n * co + ch + pad) * ho + (r >> 1)) * wo + (j >> 1));
+    }
+}
+
+// Weight / bias gradient of the classifier (nn.Linear at the end of resnet_s.py:93-95): dW[o][i] = sum_b dy[b][o] * x[b][i],
+// db[o] = sum_b dy[b][o].  A 100 x 64 x 256 problem: the library's SIMT sgemm takes 91 us for it (ncu launch list); one CTA
+// per output row, one thread per input feature, batch walked in order (deterministic), dy staged through shared memory.
+__global__ void __launch_bounds__(256)
+linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, float* __restrict__ db,
+                    int batch, int out_f, int in_f) {
+    __shared__ float s_dy[1024];
+    const int o = blockIdx.x;
+    float bsum = 0.f;
+    for (int i0 = 0; i0 < in_f; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        float acc = 0.f;
+        for (int b0 = 0; b0 < batch; b0 += 1024) {
+            const int nb = min(1024, batch - b0);
+            __syncthreads();
+            for (int b = threadIdx.x; b < nb; b += blockDim.x) s_dy[b] = __ldg(dy + static_cast<size_t>(b0 + b) * out_f + o);
+            __syncthreads();
+            if (i < in_f) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                // four chains, combined in a fixed order
+                int b = 0;
+                for (; b + 4 <= nb; b += 4) {
+                    a0 = fmaf(s_dy[b], __ldg(x + static_cast<size_t>(b0 + b) * in_f + i), a0);
+                    a1 = fmaf(s_dy[b + 1], __ldg(x + static_cast<size_t>(b0 + b + 1) * in_f + i), a1);
+                    a2 = fmaf(s_dy[b + 2], __ldg(x + static_cast<size_t>(b0 + b + 2) * in_f + i), a2);
+                    a3 = fmaf(s_dy[b + 3], __ldg(x + static_cast<size_t>(b0 + b + 3) * in_f + i), a3);
+                }
+                for (; b < nb; ++b) a0 = fmaf(s_dy[b], __ldg(x + static_cast<size_t>(b0 + b) * in_f + i), a0);
+                acc += (a0 + a1) + (a2 + a3);
+            }
+            if (i0 == 0 && threadIdx.x == 0 && db)
+                for (int b = 0; b < nb; ++b) bsum += s_dy[b];
+        }
+        if (i < in_f) dw[static_cast<size_t>(o) * in_f + i] = acc;
+    }
+    if (threadIdx.x == 0 && db) db[o] = bsum;
+}
+
 }  // namespace afan
 
 using namespace afan;
@@ -120,5 +192,43 @@ AFAN_EXPORT int afan_sgd_momentum_f32(float* param, const float* grad, float* mo
         sgd_momentum_kernel<1><<<static_cast<unsigned int>(want < cap ? want : cap), kThreads, 0, st>>>(
             param, grad, momentum_buf, n_elem, lr_device, momentum, weight_decay, grad_scale);
     }
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_shortcut_a_fwd_f32(const float* x, float* y, int64_t n, int64_t c, int64_t h, int64_t w, int64_t pad,
+                                        afan_stream_t stream) {
+    if (n < 0 || c < 0 || h < 0 || w < 0 || pad < 0) return AFAN_ERR_SIZE;
+    const int64_t total = n * (c + 2 * pad) * ((h + 1) / 2) * ((w + 1) / 2);
+    if (total == 0) return AFAN_OK;
+    if (!x || !y) return AFAN_ERR_NULL;
+    if (c + 2 * pad >= (int64_t(1) << 31) || h >= (int64_t(1) << 30) || w >= (int64_t(1) << 30)) return AFAN_ERR_UNSUPPORTED;
+    const int64_t want = (total + kThreads - 1) / kThreads, cap = static_cast<int64_t>(sm_count()) * kCtasPerSm;
+    shortcut_a_fwd_kernel<<<static_cast<unsigned int>(want < cap ? want : cap), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, y, total, static_cast<int>(c), static_cast<int>(h), static_cast<int>(w), static_cast<int>(pad));
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_shortcut_a_bwd_f32(const float* dy, float* dx, int64_t n, int64_t c, int64_t h, int64_t w, int64_t pad,
+                                        afan_stream_t stream) {
+    if (n < 0 || c < 0 || h < 0 || w < 0 || pad < 0) return AFAN_ERR_SIZE;
+    const int64_t total = n * c * h * w;
+    if (total == 0) return AFAN_OK;
+    if (!dy || !dx) return AFAN_ERR_NULL;
+    if (c + 2 * pad >= (int64_t(1) << 31) || h >= (int64_t(1) << 30) || w >= (int64_t(1) << 30)) return AFAN_ERR_UNSUPPORTED;
+    const int64_t want = (total + kThreads - 1) / kThreads, cap = static_cast<int64_t>(sm_count()) * kCtasPerSm;
+    shortcut_a_bwd_kernel<<<static_cast<unsigned int>(want < cap ? want : cap), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        dy, dx, total, static_cast<int>(c), static_cast<int>(h), static_cast<int>(w), static_cast<int>(pad));
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_linear_wgrad_f32(const float* dy, const float* x, float* dweight, float* dbias, int64_t batch,
+                                      int64_t out_features, int64_t in_features, afan_stream_t stream) {
+    if (batch < 0 || out_features < 0 || in_features < 0) return AFAN_ERR_SIZE;
+    if (out_features == 0) return AFAN_OK;
+    if (!dweight || (batch > 0 && (!dy || !x))) return AFAN_ERR_NULL;
+    if (batch >= (int64_t(1) << 31) || out_features >= (int64_t(1) << 31) || in_features >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
+    const int threads = in_features >= 256 ? 256 : (in_features > 32 ? static_cast<int>((in_features + 31) / 32 * 32) : 32);
+    linear_wgrad_kernel<<<static_cast<unsigned int>(out_features), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        dy, x, dweight, dbias, static_cast<int>(batch), static_cast<int>(out_features), static_cast<int>(in_features));
     return launch_status();
 }

@@ -307,6 +307,59 @@ def nms_flags(boxes: torch.Tensor, scores: torch.Tensor, threshold: float):
     return keep, count
 
 
+class _ShortcutAFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        y = torch.empty(n, c + 2 * pad, (h + 1) // 2, (w + 1) // 2, dtype=x.dtype, device=x.device)
+        check(_lib.lib().afan_shortcut_a_fwd_f32(f32(x, "x"), f32(y), n, c, h, w, pad, stream()), "afan_shortcut_a_fwd_f32")
+        ctx.cfg = (n, c, h, w, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, pad = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty(n, c, h, w, dtype=dy.dtype, device=dy.device)
+        check(_lib.lib().afan_shortcut_a_bwd_f32(f32(dy, "dy"), f32(dx), n, c, h, w, pad, stream()), "afan_shortcut_a_bwd_f32")
+        return dx, None
+
+
+def shortcut_a(x: torch.Tensor, pad: int) -> torch.Tensor:
+    """Option-A shortcut of a stage transition: F.pad(x[:, :, ::2, ::2], (0, 0, 0, 0, pad, pad)) in one launch each way
+    (Classification/resnet_s.py:60-63)."""
+    return _ShortcutAFn.apply(x, int(pad))
+
+
+class _LinearFn(torch.autograd.Function):
+    """F.linear whose weight / bias gradient is ONE deterministic launch (afan_linear_wgrad_f32); output and input gradient
+    stay library GEMMs (5-6 us each at the classifier's 256 x 64 x 100)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dx = dy.mm(weight) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dy_c, x_c = dy.contiguous(), x.contiguous()
+            dw = torch.empty_like(weight)
+            db = torch.empty(weight.shape[0], dtype=weight.dtype, device=weight.device) if ctx.has_bias else None
+            check(_lib.lib().afan_linear_wgrad_f32(f32(dy_c, "dy"), f32(x_c, "x"), f32(dw), f32(db), x_c.shape[0], weight.shape[0],
+                                                   weight.shape[1], stream()), "afan_linear_wgrad_f32")
+        return dx, dw, db
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _LinearFn.apply(x, weight, bias)
+
+
 def nms_batched(boxes_sorted: torch.Tensor, threshold: float, max_keep: int, want_flags: bool = False):
     """Greedy NMS of `images` ranked box lists in one launch pair.  boxes_sorted [B, N, 4] (descending score per image).
     Returns (kept boxes [B, max_keep, 4] in rank order, zero-padded; counts int32 [B]; keep flags uint8 [B, N] by rank or

@@ -29,6 +29,8 @@ from .dual_bn import DualBatchNorm2d
 # consumer convolution exchanges the folded sums with its peers in its prologue; with the NCCL split form the block keeps
 # its four launches.
 FUSE_BN1 = os.environ.get("AFAN_FUSE_BN1", "1") == "1"
+# AFAN_TAIL_KERNELS=0: option-A shortcut and classifier weight gradient back on the library's launches (A/B)
+SHORTCUT_KERNEL = LINEAR_KERNEL = os.environ.get("AFAN_TAIL_KERNELS", "1") == "1"
 fused_forward_calls = 0       # host-side count of folded block forwards (eager calls + graph captures): evidence for the parity checks
 
 
@@ -113,6 +115,8 @@ class BasicBlock(nn.Module):
     def _shortcut(self, x):
         if not self.downsample:
             return x
+        if x.is_cuda and x.dtype == torch.float32 and SHORTCUT_KERNEL:
+            return ops.shortcut_a(x, self.pad)                       # one launch each way instead of slice + fill + pad
         return F.pad(x[:, :, ::2, ::2], (0, 0, 0, 0, self.pad, self.pad), "constant", 0.0)
 
     def forward(self, x, groups: int = 1, replay: int = 1):
@@ -163,7 +167,12 @@ class ResNet(nn.Module):
                 x = m(x, relu=fuse, groups=groups, replay=replay)
                 i += 2 if fuse else 1
                 continue
-            x = m(x, groups=groups, replay=replay) if isinstance(m, BasicBlock) else m(x)
+            if isinstance(m, BasicBlock):
+                x = m(x, groups=groups, replay=replay)
+            elif isinstance(m, nn.Linear) and LINEAR_KERNEL and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2:
+                x = ops.linear(x, m.weight, m.bias)                  # weight / bias gradient in one deterministic launch
+            else:
+                x = m(x)
             i += 1
         return x
 

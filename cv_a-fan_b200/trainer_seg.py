@@ -108,7 +108,7 @@ class SegAfanTrainer:
                  clip: bool = False, mix_sd: bool = False, noise_sd: float = 0.0, mix_layer: str = "00",
                  lr: float = 0.01, momentum: float = 0.9, weight_decay: float = 1e-4,
                  criterion: Optional[nn.Module] = None, head_cache: bool = True, rng: str = "philox", seed: int = 0,
-                 dual_bn: bool = True):
+                 dual_bn: bool = True, use_cuda_graph: bool = False):
         """Flag names / units follow Segmentation/args.py:19-40 (eps, gamma_* in 1/255).
 
         dual_bn: the BatchNorm layers of the TAIL (backbone stages after `pertub_idx_se`, ASPP, decoder:
@@ -154,6 +154,15 @@ class SegAfanTrainer:
                          (_StatArena(aspp, self.device), 2)] if head_cache else []
         self.rng_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.iterations = 0
+        # use_cuda_graph: the whole iteration (head sweep, both ascents, four training forwards, backward, both SGD launches)
+        # is captured once and replayed -- the eager iteration is HOST-bound at config 5 (45.8 ms to enqueue ~4500 launches
+        # against 47.6 ms of device time, profiles/probes/host_vs_device.py).  Needs rng='philox' (device-side offsets) or
+        # injected noise; the learning rate already lives on the device.
+        self.use_graph = bool(use_cuda_graph)
+        if self.use_graph and self.randinit and self.rng != "philox":
+            raise AfanError("use_cuda_graph needs rng='philox' (the CPU random stream of rng='reference' cannot be replayed)")
+        self._graph, self._static = None, {}
+        self._dual = [m for m in model.modules() if isinstance(m, DualBatchNorm2d)]
 
     def set_lr(self, lr: float):
         """Base learning rate (PolyLR, utils/scheduler.py:3-12, is applied by the caller): backbone gets 0.1 x."""
@@ -239,14 +248,71 @@ class SegAfanTrainer:
         loss = 0.7 * l0 + 0.1 * l1 + 0.1 * l2 + 0.1 * l3                                                     # :233
         return loss, torch.stack([l0.detach(), l1.detach(), l2.detach(), l3.detach()])
 
-    def step(self, images: torch.Tensor, labels: torch.Tensor, noise: Optional[Dict[str, torch.Tensor]] = None):
-        """One training iteration on device tensors; returns {'loss', 'losses' (l0..l3)} as DEVICE tensors."""
-        self.model.train()
+    def _eager(self, images, labels, noise):
         for a in self.arenas:
             a.grad.zero_()                                                                                   # :162
         loss, parts = self._iteration(images, labels, noise)
         loss.backward()                                                                                      # :235
         for a in self.arenas:                                                                                # :236
             ops.sgd_momentum_(a.param, a.grad, a.buf, a.lr, momentum=self.momentum, weight_decay=self.weight_decay)
+        return loss.detach(), parts
+
+    def _capture(self, images, labels, noise):
+        st = self._static
+        st["images"], st["labels"] = images.clone(), labels.clone()
+        st["noise"] = {k: v.clone() for k, v in noise.items()} if noise else None
+        for m in self._dual:
+            m.flush_batches_tracked()
+        tensors = dict(self.model.named_parameters())
+        tensors.update({"buffer:" + k: v for k, v in self.model.named_buffers()})
+        snap = {"model": {k: v.detach().clone() for k, v in tensors.items()},
+                "arena": [(a.param.clone(), a.buf.clone()) for a in self.arenas], "rng": self.rng_offset.clone(),
+                "pending": [m._pending_batches for m in self._dual], "torch_rng": torch.cuda.get_rng_state(self.device)}
+        side = self._stream = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # warm-up on the capture stream: cuDNN autotune, lazy module loads
+                self._eager(st["images"], st["labels"], st["noise"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        with torch.no_grad():                        # the warm-up must not leak into the training state
+            for (p, b), a in zip(snap["arena"], self.arenas):
+                a.param.copy_(p); a.buf.copy_(b)
+            for k, v in snap["model"].items():
+                tensors[k].copy_(v)
+            self.rng_offset.copy_(snap["rng"])
+        for m, pend in zip(self._dual, snap["pending"]):
+            m._pending_batches = pend
+        torch.cuda.set_rng_state(snap["torch_rng"], self.device)
+        pend0 = [m._pending_batches for m in self._dual]
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=side):
+            st["loss"], st["parts"] = self._eager(st["images"], st["labels"], st["noise"])
+        self._dual_per_iter = [m._pending_batches - p0 for m, p0 in zip(self._dual, pend0)]
+        for m, p0 in zip(self._dual, pend0):
+            m._pending_batches = p0                  # capture records launches, it does not run them
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor, noise: Optional[Dict[str, torch.Tensor]] = None):
+        """One training iteration on device tensors; returns {'loss', 'losses' (l0..l3)} as DEVICE tensors."""
+        self.model.train()
+        if not self.use_graph:
+            loss, parts = self._eager(images, labels, noise)
+            self.iterations += 1
+            return {"loss": loss, "losses": parts}
+        if self._graph is None:
+            self._capture(images, labels, noise)
+        st = self._static
+        st["images"].copy_(images, non_blocking=True)
+        st["labels"].copy_(labels, non_blocking=True)
+        if noise:
+            for k, v in noise.items():
+                st["noise"][k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        for m, inc in zip(self._dual, self._dual_per_iter):
+            m._pending_batches += inc
         self.iterations += 1
-        return {"loss": loss.detach(), "losses": parts}
+        return {"loss": st["loss"], "losses": st["parts"]}
+
+    def close(self):
+        """Drop the captured graph and its static buffers."""
+        self._graph, self._static = None, {}

@@ -210,6 +210,18 @@ int afan_bn_affine_f32(const float* x, const float* residual, const float* scale
 int afan_bn_affine_bwd_f32(const float* dy, const float* y, const float* scale_shift, float* dx, float* dresidual,
                            int64_t n, int64_t c, int64_t hw, int relu, afan_stream_t stream);
 
+/* ---- small launches of the Classification tail (round 2: the library ran them as 3-6 launches / a 91 us SIMT sgemm) ----
+ * Option-A shortcut of a stage transition, Classification/resnet_s.py:60-63 `F.pad(x[:, :, ::2, ::2], (0,0,0,0,pad,pad))`:
+ * x [n][c][h][w] -> y [n][c+2*pad][ceil(h/2)][ceil(w/2)] and its backward dy -> dx (every output element written once). */
+int afan_shortcut_a_fwd_f32(const float* x, float* y, int64_t n, int64_t c, int64_t h, int64_t w, int64_t pad,
+                            afan_stream_t stream);
+int afan_shortcut_a_bwd_f32(const float* dy, float* dx, int64_t n, int64_t c, int64_t h, int64_t w, int64_t pad,
+                            afan_stream_t stream);
+/* Weight / bias gradient of the classifier `nn.Linear` (resnet_s.py:93-95): dweight [out][in] = dy^T x, dbias [out]
+ * (nullable) = column sums of dy [batch][out]; x [batch][in].  Batch walked in a fixed order (deterministic). */
+int afan_linear_wgrad_f32(const float* dy, const float* x, float* dweight, float* dbias, int64_t batch,
+                          int64_t out_features, int64_t in_features, afan_stream_t stream);
+
 /* ---- f4: greedy NMS, fully on the device ---------------------------------------------------------------------
  * Replaces Detection/support/src/cuda/nms.cu:23-131 (+ its D2H mask copy and serial CPU sweep, :99-123).
  * boxes_sorted: [n][4] (x1,y1,x2,y2) ALREADY sorted by score descending (16-byte aligned); order[i] = original index

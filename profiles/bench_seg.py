@@ -57,5 +57,11 @@ for hc, dbn in ((False, False), (True, False), (True, True)):
                                         noise_sd=0.0, mix_layer="01", head_cache=hc, dual_bn=dbn)
     res[f"afan_head_cache_{int(hc)}_dual_bn_{int(dbn)}_ms"] = timed(lambda: tr.step(images, labels))
     del m, tr
+m = model_()
+tr = PKG.trainer_seg.SegAfanTrainer(m, pertub_idx_se=c["se"], pertub_idx_sd=c["sd"], steps=c["steps"], eps=c["eps"], gamma_se=c["gamma_se"],
+                                    gamma_sd=c["gamma_sd"], randinit=True, clip=False, mix_sd=True, noise_sd=0.0, mix_layer="01",
+                                    head_cache=True, dual_bn=True, use_cuda_graph=True)
+res["afan_head_cache_1_dual_bn_1_graph_ms"] = timed(lambda: tr.step(images, labels))
+del m, tr
 res["img_per_s"] = {k.replace("_ms", ""): round(1e3 * B / v, 2) for k, v in res.items() if k.endswith("_ms")}
 print(json.dumps(res))
