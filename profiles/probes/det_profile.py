@@ -17,7 +17,10 @@ bw, bh = 50 + torch.rand(B, G, generator=g) * 250, 50 + torch.rand(B, G, generat
 boxes = torch.stack((x0, y0, x0 + bw, y0 + bh), dim=2).to(dev)
 labels = torch.randint(1, NC, (B, G), generator=g).to(dev)
 torch.manual_seed(3)
-m = PKG.faster_rcnn.FasterRCNN(NC, sampler="device").to(dev)
+m = PKG.faster_rcnn.FasterRCNN(NC, sampler="device", fuse_frozen_bn="--nofuse" not in sys.argv).to(dev)
+if "--cl" in sys.argv:
+    m = m.to(memory_format=torch.channels_last)
+    images = images.contiguous(memory_format=torch.channels_last)
 for n_, p in m.named_parameters():
     if ("_anchor_" in n_ or "_proposal_" in n_) and n_.endswith("weight"):
         p.data.mul_(0.01)
