@@ -97,7 +97,9 @@ def per_image_losses(logits, targets, pred_deltas, gt_deltas, batch_indices, bat
     by (4 * n_foreground + 1e-8).  An image without samples gives NaN (mean of nothing), as in the reference."""
     seg = F.one_hot(batch_indices, batch_size).to(logits.dtype).t()              # [B, S]
     ce = F.cross_entropy(logits, targets, reduction="none")
-    cross_entropies = (seg @ ce) / seg.sum(dim=1)
+    cnt = seg.sum(dim=1)
+    # an image without samples: NaN like the reference's mean of nothing, but without 0/0 in the backward of the others
+    cross_entropies = torch.where(cnt > 0, (seg @ ce) / cnt.clamp(min=1.0), torch.full_like(cnt, float("nan")))
     fg = targets != 0
     # background rows may hold inf / NaN regression targets (log of a zero-area ratio): their difference is replaced by 0
     # BEFORE the loss, so neither the value nor the gradient sees them (the reference gathers the foreground rows)

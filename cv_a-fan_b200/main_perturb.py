@@ -119,8 +119,9 @@ class CifarLoaders:
 
 
 def to_device(loader, device):
-    for x, y in loader:
-        yield x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+    """Batches on the device, copied one step ahead on a copy stream (prefetch.DevicePrefetcher)."""
+    from .prefetch import DevicePrefetcher
+    return iter(DevicePrefetcher(loader, device))
 
 
 def validate(trainer, loader, print_freq, tag, rank):

@@ -40,3 +40,21 @@ def test_linear_weight_gradient_vs_fp64(batch, inf, outf, bias):
     # deterministic: a second evaluation is bit-identical
     again = torch.autograd.grad(PKG.ops.linear(x, w, b), [w], dy)[0]
     assert torch.equal(again, grads[1])
+
+
+def test_device_prefetcher_delivers_every_batch_in_order():
+    """prefetch.DevicePrefetcher: batch i+1 is copied on a side stream while batch i is consumed; contents, order and None
+    entries must come through unchanged, also when the consumer keeps the GPU busy between batches."""
+    g = torch.Generator().manual_seed(5)
+    host = [(torch.rand(64, 3, 32, 32, generator=g).pin_memory(), torch.randint(0, 100, (64,), generator=g).pin_memory(), None)
+            for _ in range(7)]
+    busy = torch.randn(2048, 2048, device=dev())
+    seen = []
+    for x, y, u in PKG.prefetch.DevicePrefetcher(host, dev()):
+        assert u is None and x.is_cuda and y.is_cuda
+        busy = busy @ busy * 1e-3                                    # work on the consumer's stream
+        seen.append((x.clone(), y.clone()))
+    torch.cuda.synchronize()
+    assert len(seen) == len(host)
+    for (x, y), (hx, hy, _) in zip(seen, host):
+        assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)

@@ -219,3 +219,83 @@ def test_bench_line_stays_parseable_from_a_short_stdout_tail(tmp_path, capsys):
         assert k in parsed, k
     assert parsed["value"] > 0 and parsed["e2e"]["value"] > 0
     assert json.load(open(A.detail_file))["kernels"]
+
+
+# ---- Detection flavour: host-side pieces of cv_a-fan_b200.faster_rcnn / trainer_det that need no GPU -------------------
+def test_detection_box_arithmetic_and_losses_against_their_definitions():
+    pkg = importlib.import_module("cv_a-fan_b200")
+    fr = pkg.faster_rcnn
+    g = torch.Generator().manual_seed(9)
+    xy = torch.rand(2, 40, 2, generator=g) * 200
+    src = torch.cat((xy, xy + 5 + torch.rand(2, 40, 2, generator=g) * 90), dim=2)
+    xy2 = torch.rand(2, 40, 2, generator=g) * 200
+    dst = torch.cat((xy2, xy2 + 5 + torch.rand(2, 40, 2, generator=g) * 90), dim=2)
+    # deltas round-trip (Detection/bbox.py:42-64)
+    torch.testing.assert_close(fr.apply_deltas(src, fr.box_deltas(src, dst)), dst, rtol=1e-4, atol=1e-3)
+    # IoU against the scalar definition, incl. a zero-area pair -> NaN like the reference's 0/0
+    iou = fr.pairwise_iou(src, dst[:, :7])
+    for b, p, q in ((0, 3, 2), (1, 17, 6), (0, 39, 0)):
+        a, c = src[b, p], dst[b, q]
+        w = max(min(a[2], c[2]) - max(a[0], c[0]), 0.0)
+        h = max(min(a[3], c[3]) - max(a[1], c[1]), 0.0)
+        inter = w * h
+        want = inter / ((a[2] - a[0]) * (a[3] - a[1]) + (c[2] - c[0]) * (c[3] - c[1]) - inter)
+        assert abs(float(iou[b, p, q]) - float(want)) < 1e-6
+    assert torch.isnan(fr.pairwise_iou(torch.zeros(1, 1, 4), torch.zeros(1, 1, 4))).all()
+    assert torch.equal(fr.clip_boxes(torch.tensor([[-5.0, -1.0, 300.0, 90.0]]), 200, 80), torch.tensor([[0.0, 0.0, 200.0, 80.0]]))
+    # per-image losses = the reference's loops (model.py:365-377): mean CE over the image's samples, smooth-L1 over its foreground
+    s, ncls, batch = 50, 4, 3
+    logits = torch.randn(s, ncls, generator=g, requires_grad=True)
+    targets = torch.randint(0, ncls, (s,), generator=g)
+    pred, gt = torch.randn(s, 4, generator=g, requires_grad=True), torch.randn(s, 4, generator=g)
+    gt[targets == 0] = float("inf")                                   # background rows carry garbage targets in the model
+    bi = torch.randint(0, batch - 1, (s,), generator=g)               # the last image gets no sample
+    ce, l1 = fr.per_image_losses(logits, targets, pred, gt, bi, batch, beta=1.0)
+    for i in range(batch):
+        sel = (bi == i).nonzero().view(-1)
+        if len(sel) == 0:
+            assert torch.isnan(ce[i]) and float(l1[i]) == 0.0
+            continue
+        torch.testing.assert_close(ce[i], torch.nn.functional.cross_entropy(logits[sel], targets[sel]), rtol=1e-5, atol=1e-6)
+        fg = sel[targets[sel] != 0]
+        d = (pred[fg] - gt[fg]).abs()
+        want = torch.where(d < 1.0, 0.5 * d ** 2, d - 0.5).sum() / (d.numel() + 1e-8)
+        torch.testing.assert_close(l1[i], want, rtol=1e-5, atol=1e-6)
+    (ce[:batch - 1].sum() + l1.sum()).backward()
+    assert torch.isfinite(logits.grad).all() and torch.isfinite(pred.grad).all()       # masked rows give 0, not NaN
+    assert float(pred.grad[targets == 0].abs().max()) == 0.0
+
+
+def test_detection_sampler_and_anchor_invariants():
+    pkg = importlib.import_module("cv_a-fan_b200")
+    fr = pkg.faster_rcnn
+    g = torch.Generator().manual_seed(4)
+    labels = torch.randint(-1, 3, (3, 500), generator=g)
+    torch.manual_seed(0)
+    bi, ci = fr.select_samples(labels, fg_cap=40, total=120, sampler=fr.Sampler("reference"))
+    picked = labels[bi, ci]
+    assert len(bi) == 120 and int((picked > 0).sum()) == 40 and int((picked == 0).sum()) == 80 and not (picked < 0).any()
+    assert len({(int(a), int(b)) for a, b in zip(bi, ci)}) == 120              # no candidate twice
+    torch.manual_seed(0)                                                       # the reference's three draws, in its order
+    fg, bgc = (labels > 0).nonzero(), (labels == 0).nonzero()
+    fg = fg[torch.randperm(len(fg))[:40]]
+    bgc = bgc[torch.randperm(len(bgc))[:80]]
+    sel = torch.cat([fg, bgc])
+    sel = sel[torch.randperm(len(sel))]
+    assert torch.equal(sel[:, 0], bi) and torch.equal(sel[:, 1], ci)
+    few = torch.tensor([[1, 0, -1, 0]])                                        # fewer candidates than asked for: take all
+    bi, ci = fr.select_samples(few, fg_cap=8, total=16, sampler=fr.Sampler("reference"))
+    assert sorted(ci.tolist()) == [0, 1, 3]
+    rpn = fr.RegionProposalNetwork(8, [(1, 2), (1, 1), (2, 1)], [32, 64], 100, 10, 1.0, fr.Sampler("reference"))
+    a = rpn.generate_anchors(image_width=96, image_height=64, num_x_anchors=3, num_y_anchors=2)
+    assert a.shape == (2 * 3 * 3 * 2, 4)
+    cx, cy = (a[:, 0] + a[:, 2]) / 2, (a[:, 1] + a[:, 3]) / 2
+    assert torch.allclose(cy[:18], torch.full((18,), 64 / 3)) and torch.allclose(cx[:6], torch.full((6,), 24.0))   # y major, then x
+    w, h = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
+    torch.testing.assert_close((w * h)[:6], torch.tensor([32.0 ** 2, 64.0 ** 2] * 3), rtol=1e-5, atol=1e-2)       # ratio keeps the area
+    torch.testing.assert_close((h / w)[:6], torch.tensor([0.5, 0.5, 1.0, 1.0, 2.0, 2.0]), rtol=1e-5, atol=1e-5)
+    assert pkg.trainer_det.warmup_multistep_lr(0, 0.001) == pytest.approx(0.001 * 0.3333)
+    assert pkg.trainer_det.warmup_multistep_lr(250, 0.001) == pytest.approx(0.001 * (0.6667 * 0.5 + 0.3333))
+    assert pkg.trainer_det.warmup_multistep_lr(500, 0.001) == pytest.approx(0.001)
+    assert pkg.trainer_det.warmup_multistep_lr(50000, 0.001) == pytest.approx(0.0001)
+    assert pkg.trainer_det.warmup_multistep_lr(70000, 0.001) == pytest.approx(0.00001)
