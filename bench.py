@@ -790,6 +790,22 @@ def main():
         torch.backends.cudnn.deterministic = det
         line["variants_ms_per_step"] = variants
 
+    if world > 1 and not args.skip_variants and not args.no_sync_bn and not args.no_graph:
+        # context for the scaling number: the SAME sharded step with per-replica BatchNorm statistics -- what the reference's
+        # own multi-GPU mode computes (nn.DataParallel, Segmentation/main_aug_final.py:119,131) -- i.e. the step without the
+        # ~390 per-layer statistics exchanges the global-batch semantics costs.  Not the headline.
+        torch.manual_seed(3)
+        vm = pkg.resnet_s.ResNet(num_blocks=w["num_blocks"], num_classes=w["num_classes"]).to(dev)
+        vt = pkg.trainer.AfanTrainer(vm, perturb_idx=w["perturb_idx"], steps=w["steps"], gamma=w["gamma"], eps=w["eps"],
+                                     randinit=w["randinit"], clip=w["clip"], rng="philox", seed=3 + rank, process_group=pg,
+                                     sync_bn=False, use_cuda_graph=True, bn_exchange=args.bn_exchange)
+        vt.step(dev_x[0], dev_y[0])
+        vsec, _ = timed_run(lambda i: vt.step(dev_x[i % 4], dev_y[i % 4]))
+        detail["per_replica_bn_ms_per_step"] = 1e3 * vsec / args.steps
+        detail["per_replica_bn_img_per_s"] = global_batch * args.steps / vsec
+        vt.close()
+        del vm, vt
+
     if rank == 0 and not args.skip_rooflines:
         ks, peak_src, ffma_peak = kernel_rooflines(pkg, dev, in_step_only=world > 1)
         try:
