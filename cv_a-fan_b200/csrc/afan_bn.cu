@@ -1246,7 +1246,17 @@ int launch_cluster(K kernel, const ClusterParams& p, int cs, cudaStream_t st, co
 // statistics and the normalisation both run out of shared memory, and the result leaves with the same peeled 128-bit
 // pattern.  No cluster, no second HBM read, 2-6 CTAs per SM keep > 64 KB of loads in flight per SM.
 // -----------------------------------------------------------------------------------------------------
-constexpr int kPlaneThreads = 256;
+constexpr int kPlaneThreads = 128;
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned int>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned int>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 
 struct PlaneParams {
     const float* a;          // fwd: x            bwd: dy
@@ -1287,13 +1297,15 @@ __global__ void __launch_bounds__(kPlaneThreads) bn_fwd_plane_kernel(const Plane
     const unsigned int ch = blockIdx.x, planes = p.groups * p.n;
     pdl_wait();
     pdl_launch_dependents();
-    // ---- one HBM read of the whole domain into shared memory ----
+    // ---- one HBM read of the whole domain into shared memory: asynchronous copies (no register per byte in flight, no
+    //      load -> store dependency), so every plane of the channel is requested before the first one has arrived ----
     for (unsigned int pl = 0; pl < planes; ++pl) {
         const float* gp = p.a + (static_cast<size_t>(pl) * p.c + ch) * p.hw;
         plane_sweep(gp, p.hw, pl * p.pitch,
-                    [&](unsigned int gi, unsigned int si) { *reinterpret_cast<float4*>(sh + si) = ld_stream(reinterpret_cast<const float4*>(gp + gi)); },
-                    [&](unsigned int gi, unsigned int si) { sh[si] = ld_stream(gp + gi); });
+                    [&](unsigned int gi, unsigned int si) { cp_async16(sh + si, gp + gi); },
+                    [&](unsigned int gi, unsigned int si) { cp_async4(sh + si, gp + gi); });
     }
+    cp_async_wait_all();
     __syncthreads();
     // ---- statistics per group out of shared memory (fixed order: deterministic) ----
     __shared__ double2 s_raw[16];
@@ -1364,36 +1376,42 @@ __global__ void __launch_bounds__(kPlaneThreads) bn_bwd_plane_kernel(const Plane
     __shared__ float4 s_cf[16];
     __shared__ double2 s_sum[16];
     const unsigned int ch = blockIdx.x, planes = p.groups * p.n;
-    float* sd = sh;                                                    // masked dy
+    float* sd = sh;                                                    // dy (raw: the ReLU mask is applied on use)
     float* sx = sh + static_cast<size_t>(planes) * p.pitch;            // x
+    float* sy = sx + static_cast<size_t>(planes) * p.pitch;            // y (RELU only)
     pdl_wait();
     pdl_launch_dependents();
-    for (unsigned int pl = 0; pl < planes; ++pl) {
+    for (unsigned int pl = 0; pl < planes; ++pl) {                     // asynchronous copies: the whole domain in flight at once
         const size_t goff = (static_cast<size_t>(pl) * p.c + ch) * p.hw;
         const float* dp = p.a + goff;
         const float* xp = p.b + goff;
         const float* yp = RELU ? p.y + goff : nullptr;
         plane_sweep(dp, p.hw, pl * p.pitch,
                     [&](unsigned int gi, unsigned int si) {
-                        float4 d = ld_stream(reinterpret_cast<const float4*>(dp + gi));
-                        if (RELU) {
-                            const float4 yy = ld_stream(reinterpret_cast<const float4*>(yp + gi));
-                            if (!(yy.x > 0.f)) d.x = 0.f;
-                            if (!(yy.y > 0.f)) d.y = 0.f;
-                            if (!(yy.z > 0.f)) d.z = 0.f;
-                            if (!(yy.w > 0.f)) d.w = 0.f;
-                        }
-                        *reinterpret_cast<float4*>(sd + si) = d;
-                        *reinterpret_cast<float4*>(sx + si) = ld_stream(reinterpret_cast<const float4*>(xp + gi));
+                        cp_async16(sd + si, dp + gi);
+                        cp_async16(sx + si, xp + gi);
+                        if (RELU) cp_async16(sy + si, yp + gi);
                     },
                     [&](unsigned int gi, unsigned int si) {
-                        float d = ld_stream(dp + gi);
-                        if (RELU && !(ld_stream(yp + gi) > 0.f)) d = 0.f;
-                        sd[si] = d;
-                        sx[si] = ld_stream(xp + gi);
+                        cp_async4(sd + si, dp + gi);
+                        cp_async4(sx + si, xp + gi);
+                        if (RELU) cp_async4(sy + si, yp + gi);
                     });
     }
+    cp_async_wait_all();
     __syncthreads();
+    auto m1 = [&](float d, unsigned int si) { return (RELU && !(sy[si] > 0.f)) ? 0.f : d; };
+    auto m4 = [&](unsigned int si) {
+        float4 d = *reinterpret_cast<const float4*>(sd + si);
+        if (RELU) {
+            const float4 yy = *reinterpret_cast<const float4*>(sy + si);
+            if (!(yy.x > 0.f)) d.x = 0.f;
+            if (!(yy.y > 0.f)) d.y = 0.f;
+            if (!(yy.z > 0.f)) d.z = 0.f;
+            if (!(yy.w > 0.f)) d.w = 0.f;
+        }
+        return d;
+    };
     for (unsigned int g = 0; g < p.groups; ++g) {
         const float mean = p.save_mean[g * p.c + ch];
         float a0 = 0.f, a1 = 0.f;
@@ -1401,11 +1419,11 @@ __global__ void __launch_bounds__(kPlaneThreads) bn_bwd_plane_kernel(const Plane
             const float* dp = p.a + (static_cast<size_t>(pl) * p.c + ch) * p.hw;
             plane_sweep(dp, p.hw, pl * p.pitch,
                         [&](unsigned int, unsigned int si) {
-                            const float4 d = *reinterpret_cast<const float4*>(sd + si), xv = *reinterpret_cast<const float4*>(sx + si);
+                            const float4 d = m4(si), xv = *reinterpret_cast<const float4*>(sx + si);
                             a0 += (d.x + d.y) + (d.z + d.w);
                             a1 = fmaf(d.x, xv.x - mean, fmaf(d.y, xv.y - mean, fmaf(d.z, xv.z - mean, fmaf(d.w, xv.w - mean, a1))));
                         },
-                        [&](unsigned int, unsigned int si) { a0 += sd[si]; a1 = fmaf(sd[si], sx[si] - mean, a1); });
+                        [&](unsigned int, unsigned int si) { const float d = m1(sd[si], si); a0 += d; a1 = fmaf(d, sx[si] - mean, a1); });
         }
         double d0 = a0, d1 = a1;
         block_sum2(d0, d1, scratch);
@@ -1433,11 +1451,11 @@ __global__ void __launch_bounds__(kPlaneThreads) bn_bwd_plane_kernel(const Plane
         auto one = [&](float d, float xv) { return cf.x * (d - cf.y - (xv - cf.w) * cf.z); };
         plane_sweep(dp, p.hw, pl * p.pitch,
                     [&](unsigned int gi, unsigned int si) {
-                        const float4 d = *reinterpret_cast<const float4*>(sd + si), xv = *reinterpret_cast<const float4*>(sx + si);
+                        const float4 d = m4(si), xv = *reinterpret_cast<const float4*>(sx + si);
                         *reinterpret_cast<float4*>(op + gi) = make_float4(one(d.x, xv.x), one(d.y, xv.y), one(d.z, xv.z), one(d.w, xv.w));
                         if (DRES) *reinterpret_cast<float4*>(rp + gi) = d;
                     },
-                    [&](unsigned int gi, unsigned int si) { op[gi] = one(sd[si], sx[si]); if (DRES) rp[gi] = sd[si]; });
+                    [&](unsigned int gi, unsigned int si) { const float d = m1(sd[si], si); op[gi] = one(d, sx[si]); if (DRES) rp[gi] = d; });
     }
 }
 
@@ -1794,7 +1812,7 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
     if (!s.ok) return AFAN_OK;
     if (!dy || !x || !dx || !save_mean || !save_invstd || (relu && !y)) return AFAN_ERR_NULL;
     if (!ws_ok(workspace, workspace_bytes, groups, c)) return AFAN_ERR_WORKSPACE;
-    if (plane_path_ok(groups, n, c, hw, 2, al)) {                    // odd H*W, small domain: plane-resident single pass
+    if (plane_path_ok(groups, n, c, hw, relu ? 3 : 2, al)) {         // odd H*W, small domain: plane-resident single pass
         PlaneParams pp{};
         pp.a = dy; pp.b = x; pp.y = y; pp.out = dx; pp.out2 = dresidual; pp.weight = weight;
         pp.save_mean = const_cast<float*>(save_mean); pp.save_invstd = const_cast<float*>(save_invstd);
@@ -1802,7 +1820,7 @@ AFAN_EXPORT int afan_bn_bwd_f32(const float* dy, const float* x, const float* y,
         pp.count = static_cast<double>(n) * static_cast<double>(hw);
         pp.groups = static_cast<unsigned int>(groups); pp.n = static_cast<unsigned int>(n); pp.c = static_cast<unsigned int>(c);
         pp.hw = static_cast<unsigned int>(hw); pp.pitch = static_cast<unsigned int>(((hw + 3) / 4) * 4 + 8);
-        const size_t smem = plane_smem_bytes(groups, n, hw, 2);
+        const size_t smem = plane_smem_bytes(groups, n, hw, relu ? 3 : 2);
         const bool r = relu != 0, dr = dresidual != nullptr;
         if (r) return dr ? launch_plane(bn_bwd_plane_kernel<true, true>, pp, smem, st) : launch_plane(bn_bwd_plane_kernel<true, false>, pp, smem, st);
         return dr ? launch_plane(bn_bwd_plane_kernel<false, true>, pp, smem, st) : launch_plane(bn_bwd_plane_kernel<false, false>, pp, smem, st);
