@@ -1466,14 +1466,15 @@ __host__ inline size_t plane_smem_bytes(int64_t groups, int64_t n, int64_t hw, i
     return static_cast<size_t>(groups * n * pitch * tensors) * sizeof(float);
 }
 __host__ inline bool plane_path_ok(int64_t groups, int64_t n, int64_t c, int64_t hw, int tensors, bool bases_aligned) {
-    // measured on B200 (4 x C x 33 x 33): C = 2048 45.7 -> 32.9 us fwd, 67.9 -> 55.4 us bwd; C = 256 is slower than the cluster
-    // paths (256 CTAs do not fill the chip) -> only when the channels alone give >= 4 CTAs per SM
-    return bases_aligned && hw % 4 != 0 && groups <= 16 && c >= 4 * static_cast<int64_t>(sm_count()) &&
-           plane_smem_bytes(groups, n, hw, tensors) <= 100 * 1024;
+    // measured on B200 (graph-replayed launches, L2-cold): 4 x 2048 x 33 x 33 fwd 19.9 us / bwd 40.2 us; 2 x 4 x 256 x 33 x 33 fwd 11.1 us
+    // against 23.7 us on the scalar cluster path -> whenever there is at least one CTA (= channel) per SM
+    static const int64_t min_c = [] { const char* e = getenv("AFAN_PLANE_MIN_C"); return e ? static_cast<int64_t>(atoll(e)) : int64_t(-1); }();
+    return bases_aligned && hw % 4 != 0 && groups <= 16 && c >= (min_c >= 0 ? min_c : static_cast<int64_t>(sm_count())) &&
+           plane_smem_bytes(groups, n, hw, tensors) <= 200 * 1024;
 }
 template <typename K>
 __host__ inline int launch_plane(K kernel, const PlaneParams& p, size_t smem, cudaStream_t st) {
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return (cudaGetLastError(), AFAN_ERR_LAUNCH);
     return launch_pdl(kernel, dim3(p.c), dim3(kPlaneThreads), smem, st, p);
 }
