@@ -210,7 +210,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "A-FAN train img/s", "value": r["value"], "unit": "img/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.gpus),
+            "config": config_dict(args.gpus, args.conv_math, args.conv or "tc3", args.rng),      # the SAME config as the afan arm's line
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
