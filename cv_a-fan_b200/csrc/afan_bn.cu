@@ -856,59 +856,38 @@ __device__ __forceinline__ double2 cluster_fold_p2p(cg::cluster_group& cluster, 
                                                     double2 (*s_all)[kMaxCluster], double2* s_loc, double2* s_glob,
                                                     unsigned int groups, unsigned int ch, const P2PParams& q,
                                                     unsigned long long seq) {
+    // Every CTA of the cluster gathers the cluster's partials over DSMEM (as in cluster_fold) and then collects the ranks'
+    // sums from this GPU's mailbox ITSELF; only cluster rank 0 publishes.  Round 1 had rank 0 do the exchange and hand the
+    // result to its cluster mates through a second cluster barrier + a DSMEM read: that hop sat in the critical chain of every
+    // exchange (390 per step).  The mailbox words are local memory; polling them from cs CTAs costs nothing on the wire.
     __shared__ double s_recv[kP2PMaxWorld][2][2];                   // [src rank][group][k]
     const unsigned int cs = cluster.num_blocks(), rank = cluster.block_rank(), t = threadIdx.x;
-    cluster.sync();                                                 // #1: every CTA's s_part is published
-    if (rank == 0) {
-        if (t < groups * cs) {
-            const unsigned int g = t / cs, r = t - g * cs;
-            s_all[g][r] = *cluster.map_shared_rank(&s_part[g], r);
-        }
-        __syncthreads();
-        if (t < groups) {
-            double2 loc = make_double2(0.0, 0.0);
-            for (unsigned int r = 0; r < cs; ++r) { loc.x += s_all[t][r].x; loc.y += s_all[t][r].y; }
-            s_loc[t] = loc;
-        }
-        __syncthreads();
-        const unsigned int slot = static_cast<unsigned int>(seq % kP2PRing);
-        const unsigned int tag = static_cast<unsigned int>(seq % 0xfffffffeULL) + 1u;     // never 0 (mailboxes start zeroed)
-        const unsigned int words = static_cast<unsigned int>(q.world) * groups * 2;
-        if (t < words) {
-            const unsigned int peer = t / (groups * 2), rem = t - peer * groups * 2, g = rem >> 1, k = rem & 1;
-            // publish: my local sums -> every GPU's mailbox (P2P store over NVLink; peer == my rank is a local store)
-            const double v = k ? s_loc[g].y : s_loc[g].x;
-            const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
-            uint4 w;
-            w.x = static_cast<unsigned int>(bits); w.y = tag; w.z = static_cast<unsigned int>(bits >> 32); w.w = tag;
-            st_sys_u32x4(reinterpret_cast<uint4*>(static_cast<char*>(q.peers[peer]) + p2p_word_off(slot, q.rank, ch, g, k, q.world, q.cmax)), w);
-            // collect: rank `peer`'s sums from MY mailbox (bounded spin on the in-band tags)
-            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const char*>(q.peers[q.rank]) +
-                                                             p2p_word_off(slot, peer, ch, g, k, q.world, q.cmax));
-            const long long t0 = clock64();
-            uint4 r = ld_sys_u32x4(src);
-            while (r.y != tag || r.w != tag) {
-                if (clock64() - t0 > q.timeout_cycles) {                                  // peer lost: never hang, never pass silently
-                    q.state[2] = 1ULL;
-                    r.x = 0u; r.z = 0x7ff80000u;                                          // quiet NaN poisons this layer's statistics
-                    break;
-                }
-                r = ld_sys_u32x4(src);
-            }
-            s_recv[peer][g][k] = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(r.z) << 32) | r.x));
-        }
-        __syncthreads();
-        if (t < groups) {
-            double2 tot = make_double2(0.0, 0.0);
-            for (int r = 0; r < q.world; ++r) { tot.x += s_recv[r][t][0]; tot.y += s_recv[r][t][1]; }   // rank order everywhere
-            s_glob[t] = tot;
-        }
+    cluster.sync();                                                 // every CTA's s_part is published
+    if (t < groups * cs) {
+        const unsigned int g = t / cs, r = t - g * cs;
+        s_all[g][r] = *cluster.map_shared_rank(&s_part[g], r);
     }
-    cluster.sync();                                                 // #2: rank 0's s_glob is published
-    double2 tot = make_double2(0.0, 0.0);
-    if (t < groups) tot = *cluster.map_shared_rank(&s_glob[t], 0);
     __syncthreads();
-    cluster_arrive();
+    cluster_arrive();                                               // remote reads done: peers may exit later
+    if (t < groups) {
+        double2 loc = make_double2(0.0, 0.0);
+        for (unsigned int r = 0; r < cs; ++r) { loc.x += s_all[t][r].x; loc.y += s_all[t][r].y; }
+        s_loc[t] = loc;
+    }
+    __syncthreads();
+    const unsigned int slot = static_cast<unsigned int>(seq % kP2PRing);
+    const unsigned int tag = p2p_tag(seq);
+    const unsigned int words = static_cast<unsigned int>(q.world) * groups * 2;
+    if (t < words) {
+        const unsigned int peer = t / (groups * 2), rem = t - peer * groups * 2, g = rem >> 1, k = rem & 1;
+        if (rank == 0) p2p_publish(q, static_cast<int>(peer), slot, ch, g, k, tag, k ? s_loc[g].y : s_loc[g].x);
+        s_recv[peer][g][k] = p2p_collect(q, static_cast<int>(peer), slot, ch, g, k, tag);
+    }
+    __syncthreads();
+    double2 tot = make_double2(0.0, 0.0);
+    if (t < groups)
+        for (int r = 0; r < q.world; ++r) { tot.x += s_recv[r][t][0]; tot.y += s_recv[r][t][1]; }   // rank order everywhere
+    (void)s_glob;
     return tot;
 }
 
