@@ -20,6 +20,7 @@ SIGNATURES = {
     "afan_strerror": (ctypes.c_char_p, [_int]),
     "afan_device_info": (_int, [ctypes.POINTER(_int)] * 3),
     "afan_ffma_probe": (_int, [_vp, _i64, _i64, ctypes.POINTER(_f64), _vp]),
+    "afan_hbm_probe": (_int, [_int, _vp, _vp, _i64, _vp, _vp]),
     "afan_pgd_init_noise_f32": (_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
     "afan_pgd_init_philox_f32": (_int, [_vp, _vp, _i64, _f32, _u64, _u64, _vp, _vp]),
     "afan_pgd_norms_workspace_bytes": (_i64, [_i64]),

@@ -131,6 +131,33 @@ linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, f
     if (threadIdx.x == 0 && db) db[o] = bsum;
 }
 
+
+// HBM stream probes: what a kernel that ONLY reads, ONLY writes, or copies can move on this device (bench.py reports them
+// beside MEASURED_PEAKS.json's copy bandwidth: the roofline of a read-dominated kernel is the read figure, not the copy one).
+// mode 0: read (sum into one float per CTA), 1: write, 2: copy; 128-bit accesses, 8 independent accesses per thread in flight.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) hbm_probe_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long nv,
+                                                             float* __restrict__ sink) {
+    const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+    float acc = 0.f;
+    for (long long i0 = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i0 < nv; i0 += 8 * stride) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long i = i0 + u * stride;
+            if (MODE != 1) v[u] = i < nv ? ld_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else v[u] = make_float4(1.f, 2.f, 3.f, 4.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long i = i0 + u * stride;
+            if (MODE == 0) acc += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+            else if (i < nv) st_stream(dst + i, v[u]);
+        }
+    }
+    if (MODE == 0 && acc == 123.456f) sink[blockIdx.x] = acc;          // keeps the loads alive
+}
+
 }  // namespace afan
 
 using namespace afan;
@@ -230,5 +257,20 @@ AFAN_EXPORT int afan_linear_wgrad_f32(const float* dy, const float* x, float* dw
     const int threads = in_features >= 256 ? 256 : (in_features > 32 ? static_cast<int>((in_features + 31) / 32 * 32) : 32);
     linear_wgrad_kernel<<<static_cast<unsigned int>(out_features), threads, 0, static_cast<cudaStream_t>(stream)>>>(
         dy, x, dweight, dbias, static_cast<int>(batch), static_cast<int>(out_features), static_cast<int>(in_features));
+    return launch_status();
+}
+
+AFAN_EXPORT int afan_hbm_probe(int mode, const float* src, float* dst, int64_t n_elem, float* sink, afan_stream_t stream) {
+    if (n_elem < 0 || mode < 0 || mode > 2) return AFAN_ERR_SIZE;
+    if ((mode != 1 && !src) || (mode != 0 && !dst) || !sink) return AFAN_ERR_NULL;
+    if ((mode != 1 && !aligned16(src)) || (mode != 0 && !aligned16(dst))) return AFAN_ERR_UNSUPPORTED;
+    const long long nv = n_elem / 4;
+    const int grid = sm_count() * kCtasPerSm;                         // sink: at least `grid` floats
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    if (mode == 0) hbm_probe_kernel<0><<<grid, kThreads, 0, st>>>(s4, d4, nv, sink);
+    else if (mode == 1) hbm_probe_kernel<1><<<grid, kThreads, 0, st>>>(s4, d4, nv, sink);
+    else hbm_probe_kernel<2><<<grid, kThreads, 0, st>>>(s4, d4, nv, sink);
     return launch_status();
 }

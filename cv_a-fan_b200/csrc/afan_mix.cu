@@ -11,6 +11,7 @@
 // states are merged through shared memory in a fixed order (Chan).  Sweep 2 re-reads the tile (L1/L2
 // hot: it was touched microseconds ago) and writes the mixed feature: 12 B/elem of HBM traffic.  The elementwise
 // part is (x - m_c) * (s_a / s_c) + m_a: the reference expression with its division folded into a per-pixel ratio.
+#include <cstdlib>
 #include <type_traits>
 
 #include "afan_common.cuh"
@@ -31,8 +32,8 @@ struct Welford {
 
 // NP = pixel groups per thread (group q sits 32*VEC pixels after group q-1): the scalar path takes NP = 2 so that
 // every thread owns 4 independent Welford chains (2 pixels x 2 tensors) and twice the loads in flight.
-template <int VEC, int NP, int kMixThreads, int kMixUnroll>
-__global__ void __launch_bounds__(kMixThreads, kMixThreads <= 512 ? 2 : 1)
+template <int VEC, int NP, int kMixThreads, int kMixUnroll, int kMinBlocks = (kMixThreads <= 512 ? 2 : 1)>
+__global__ void __launch_bounds__(kMixThreads, kMinBlocks)
 mix_feature_kernel(const float* __restrict__ clean, const float* __restrict__ adv, float* __restrict__ out,
                    unsigned int c, unsigned int hw, unsigned int tiles_per_sample) {
     using V = typename std::conditional<VEC == 4, float4, float>::type;
@@ -359,7 +360,12 @@ AFAN_EXPORT int afan_mix_feature_f32(const float* clean, const float* adv, float
     if (n * tiles >= (int64_t(1) << 31)) return AFAN_ERR_UNSUPPORTED;
     const unsigned int grid = static_cast<unsigned int>(n * tiles);
     const unsigned int uc = static_cast<unsigned int>(c), uhw = static_cast<unsigned int>(hw), ut = static_cast<unsigned int>(tiles);
-    if (vec)
+    // vector path with many tiles: 256-thread CTAs holding 8 channels x 2 tensors x 16 B per thread in flight (115 registers,
+    // one CTA per launch-bound slot): 45.2 -> 41.6 us at 4 x 256 x 128 x 128 (0.68 -> 0.74 of the roofline); the same depth on the
+    // scalar path measured slower at every shape (profiles/r2_mix_ncu.md)
+    if (vec && grid >= 2u * static_cast<unsigned int>(sm_count()))
+        mix_feature_kernel<4, 1, 256, 8, 1><<<grid, 256, 0, st>>>(clean, adv, out, uc, uhw, ut);
+    else if (vec)
         mix_feature_kernel<4, 1, 512, 4><<<grid, 512, 0, st>>>(clean, adv, out, uc, uhw, ut);
     else if (grid < 2u * static_cast<unsigned int>(sm_count()))        // few tiles: one fat CTA per SM keeps 64 KB in flight
         mix_feature_kernel<1, 1, 1024, 8><<<grid, 1024, 0, st>>>(clean, adv, out, uc, uhw, ut);

@@ -46,6 +46,9 @@ int afan_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * `iters` 8x8 outer-product updates) and returns its FLOP count in *flops_out (host pointer); the caller times it with
  * CUDA events to get the fp32 FFMA peak of the device at its current clocks.  out: >= 2 * sm_count * 256 floats. */
 int afan_ffma_probe(float* out, int64_t out_elems, int64_t iters, double* flops_out, afan_stream_t stream);
+/* HBM stream probes for the same purpose: mode 0 = read-only (sum), 1 = write-only, 2 = copy; n_elem floats, 16-byte aligned;
+ * sink: >= 8 * SM-count floats of scratch.  A read-dominated kernel is bounded by the read figure, not by the copy bandwidth. */
+int afan_hbm_probe(int mode, const float* src, float* dst, int64_t n_elem, float* sink, afan_stream_t stream);
 
 /* ---- a2: random start ------------------------------------------------------------------------
  * Replaces Classification/attack_algo.py:41-44 (== Segmentation/attack_algo.py:43-45,
