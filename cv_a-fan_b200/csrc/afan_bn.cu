@@ -16,6 +16,7 @@
 //   pass 2 (bn_apply_kernel): flat streaming sweep, y = relu(x*scale + shift (+res)).
 // HBM bytes per element: fwd 8 algorithmic (read x, write y); the second read of x in pass 2 hits
 // the 126 MB L2 for every shape in BASELINE.json's configs.  bwd: 12 algorithmic (+4 for y if relu).
+#include <algorithm>
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -30,6 +31,7 @@ namespace afan {
 
 constexpr int kBnUnroll = 4;
 
+constexpr int kSplitWaves = 4;
 struct BnLayout {            // workspace carve-up (bytes), shared by every BN entry point
     int64_t counters, table, coef, partials, total;
 };
@@ -40,7 +42,7 @@ __host__ inline BnLayout bn_layout(int64_t groups, int64_t c) {
     l.table = align256(c * 4);
     l.coef = l.table + align256(groups * c * 8);
     l.partials = l.coef + align256(groups * c * 16);
-    l.total = l.partials + (static_cast<int64_t>(sm_count()) * kCtasPerSm + groups * c) * 16;
+    l.total = l.partials + (kSplitWaves * static_cast<int64_t>(sm_count()) * kCtasPerSm + groups * c) * 16;   // room for kSplitWaves waves of CTAs
     return l;
 }
 
@@ -1499,21 +1501,57 @@ __host__ inline int apply_grid(unsigned int total_v) {
     return static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
+// Split count of the two-launch reduce: the CTAs of one launch should fill WHOLE waves of the kernel's real residency.  Round 1
+// took ceil(8 CTAs/SM * SMs / (groups * C)), which lands just above one wave for most shapes (1280 CTAs on 888 resident slots at
+// 2x256x64x56x56: two rounds for 1.44 waves of work).  cost(s) = rounds(s) / s; the smallest s within 3 % of the best is taken.
+template <auto Kernel>
+int reduce_ctas_per_sm() {
+    static const int v = [] {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kernel, kThreads, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+        return n;
+    }();
+    return v;
+}
+__host__ inline unsigned int pick_splits(unsigned int domains, unsigned int by_work, int ctas_per_sm) {
+    const long long cap = static_cast<long long>(ctas_per_sm) * sm_count();
+    long long smax = (static_cast<long long>(kSplitWaves) * sm_count() * kCtasPerSm) / (domains ? domains : 1);
+    if (smax > by_work) smax = by_work;
+    if (smax < 1) smax = 1;
+    double best = 1e30;
+    for (long long sp = 1; sp <= smax; ++sp) {
+        const double cost = static_cast<double>((domains * sp + cap - 1) / cap) / static_cast<double>(sp);
+        if (cost < best) best = cost;
+    }
+    for (long long sp = 1; sp <= smax; ++sp)
+        if (static_cast<double>((domains * sp + cap - 1) / cap) / static_cast<double>(sp) <= best * 1.03) return static_cast<unsigned int>(sp);
+    return 1u;
+}
+
 template <bool BWD>
-int launch_reduce(const ReduceParams& p, bool vec, bool relu, cudaStream_t st, bool peel = false) {
-    dim3 grid(p.splits, p.groups * p.c);
+int launch_reduce(const ReduceParams& p_in, bool vec, bool relu, cudaStream_t st, bool peel = false) {
+    ReduceParams p = p_in;
+    const unsigned int domains = p.groups * p.c;
+    const unsigned long long J = static_cast<unsigned long long>(p.n) * p.hwv;
+    const unsigned int by_work = static_cast<unsigned int>(std::max<unsigned long long>(1ULL, (J + kThreads * kBnUnroll - 1) / (kThreads * kBnUnroll)));
+#define AFAN_RED(KERNEL)                                                                  \
+    do {                                                                                   \
+        p.splits = pick_splits(domains, by_work, reduce_ctas_per_sm<KERNEL>());            \
+        KERNEL<<<dim3(p.splits, domains), kThreads, 0, st>>>(p);                           \
+    } while (0)
     if (!vec && peel) {
-        if (BWD && relu) bn_reduce_peel_kernel<BWD, true><<<grid, kThreads, 0, st>>>(p);
-        else bn_reduce_peel_kernel<BWD, false><<<grid, kThreads, 0, st>>>(p);
+        if (BWD && relu) AFAN_RED((bn_reduce_peel_kernel<BWD, true>));
+        else AFAN_RED((bn_reduce_peel_kernel<BWD, false>));
         return launch_status();
     }
     if (vec) {
-        if (BWD && relu) bn_reduce_kernel<4, BWD, true><<<grid, kThreads, 0, st>>>(p);
-        else bn_reduce_kernel<4, BWD, false><<<grid, kThreads, 0, st>>>(p);
+        if (BWD && relu) AFAN_RED((bn_reduce_kernel<4, BWD, true>));
+        else AFAN_RED((bn_reduce_kernel<4, BWD, false>));
     } else {
-        if (BWD && relu) bn_reduce_kernel<1, BWD, true><<<grid, kThreads, 0, st>>>(p);
-        else bn_reduce_kernel<1, BWD, false><<<grid, kThreads, 0, st>>>(p);
+        if (BWD && relu) AFAN_RED((bn_reduce_kernel<1, BWD, true>));
+        else AFAN_RED((bn_reduce_kernel<1, BWD, false>));
     }
+#undef AFAN_RED
     return launch_status();
 }
 
