@@ -16,7 +16,6 @@ import time
 
 import numpy as np
 import torch
-import torch.nn as nn
 
 from . import conv, resnet_s
 from .trainer import AfanTrainer
