@@ -44,6 +44,18 @@ if which in ("all", "bn"):
             cold(lambda: out.update(r=ops.bn_fwd(x, None, w, b, rm, rv, ws, groups=G, relu=True)))
             y, sm, si = out["r"]
             cold(lambda: ops.bn_bwd(dy, x, y, w, sm, si, ws, groups=G, relu=True))
+if which in ("bn5",):                 # config-5 / config-4 shapes (odd H*W): plane-resident and peeled / flat-vector split paths
+    for G, N, C, H, W in ((1, 4, 2048, 33, 33), (2, 4, 256, 33, 33), (2, 4, 256, 129, 129)):
+        x = torch.randn(G * N, C, H, W, device=dev, generator=g)
+        dy = torch.randn(G * N, C, H, W, device=dev, generator=g)
+        w, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        ws = ops.bn_workspace(G, C, dev)
+        for _ in range(REPS):
+            out = {}
+            cold(lambda: out.update(r=ops.bn_fwd(x, None, w, b, rm, rv, ws, groups=G, relu=True)))
+            y, sm, si = out["r"]
+            cold(lambda: ops.bn_bwd(dy, x, y, w, sm, si, ws, groups=G, relu=True))
 if which in ("all", "mix"):
     for shape in ((4, 2048, 33, 33), (8, 1024, 38, 63), (4, 256, 128, 128)):
         cl = torch.relu(torch.randn(shape, device=dev, generator=g))
