@@ -14,6 +14,8 @@ ops = PKG.ops
 CASES = [  # groups, n, c, h, w
     (1, 128, 16, 32, 32), (2, 128, 16, 32, 32), (2, 128, 32, 16, 16), (2, 128, 64, 8, 8),   # ResNet-56 tail, config 2
     (1, 4, 2048, 33, 33), (2, 2, 256, 33, 33),                                              # DeepLab-shaped, odd HW -> scalar path
+    (2, 4, 256, 33, 33),                                    # plane-resident kernels at C = 256, backward stages dy / x / y (3 x 35 KB)
+    (2, 2, 8, 35, 37), (1, 1, 3, 17, 19), (1, 2, 40, 129, 129),   # split path, odd H*W >= 256: peeled reduce + flat-vector / scalar apply
     (1, 3, 5, 1, 1), (2, 1, 3, 2, 2), (1, 2, 1, 1, 7), (4, 2, 6, 4, 4)]
 
 
