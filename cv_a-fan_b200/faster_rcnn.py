@@ -443,10 +443,16 @@ class FasterRCNN(nn.Module):
                 m.fused_bn = bool(fuse_frozen_bn)
 
     def train(self, mode: bool = True):
+        # the reference calls model.train() before EVERY forward (train_aug_final.py:86-158, attack_algo.py:59); walking ~400
+        # modules ten times per iteration is host time for nothing when the mode does not change
+        mode = bool(mode)
+        if getattr(self, "_mode_set", None) == mode and all(m.training == mode for m in (self, self.features, self.rpn, self.detection)):
+            return self
         super().train(mode)
         for m in self.modules():                       # frozen statistics in every mode (model.py:47-48)
             if isinstance(m, nn.BatchNorm2d):
                 m.eval()
+        self._mode_set = mode
         return self
 
     # -- the halves of a training forward, exposed for the head cache of trainer_det -------------------
