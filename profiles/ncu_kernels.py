@@ -44,6 +44,22 @@ if which in ("all", "bn"):
             cold(lambda: out.update(r=ops.bn_fwd(x, None, w, b, rm, rv, ws, groups=G, relu=True)))
             y, sm, si = out["r"]
             cold(lambda: ops.bn_bwd(dy, x, y, w, sm, si, ws, groups=G, relu=True))
+if which in ("fill",):                # in-step rows that had no ncu traffic yet
+    x = torch.randn(128, 64, 8, 8, device=dev, generator=g)
+    dy = torch.randn(128, 64, 8, 8, device=dev, generator=g)
+    w, b = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    rm, rv = torch.zeros(64, device=dev), torch.ones(64, device=dev)
+    ws = ops.bn_workspace(1, 64, dev)
+    out = {}
+    cold(lambda: out.update(r=ops.bn_fwd(x, None, w, b, rm, rv, ws, groups=1, relu=True)))
+    y, sm, si = out["r"]
+    cold(lambda: ops.bn_bwd(dy, x, y, w, sm, si, ws, groups=1, relu=True))
+    shape = (128, 16, 32, 32)
+    x = torch.relu(1.5 * torch.randn(shape, device=dev, generator=g))
+    gr = 1e-3 * torch.randn(shape, device=dev, generator=g)
+    xa = x.clone()
+    nrm, ws2 = torch.zeros(2, shape[0], device=dev), ops.norms_workspace(shape[0], dev)
+    cold(lambda: ops.pgd_linf_step_(gr, x, xa, 0.5 / 255, 2 / 255, True, norms_out=nrm, workspace=ws2))
 if which in ("bn5",):                 # config-5 / config-4 shapes (odd H*W): plane-resident and peeled / flat-vector split paths
     for G, N, C, H, W in ((1, 4, 2048, 33, 33), (2, 4, 256, 33, 33), (2, 4, 256, 129, 129)):
         x = torch.randn(G * N, C, H, W, device=dev, generator=g)
